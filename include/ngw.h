@@ -1,0 +1,242 @@
+/*
+ * ngw.h — C-ABI of the B200-native batched NovelGridworld simulator (libngw_b200.so)
+ *
+ * One header, three users:
+ *   - gym_novel_gridworlds_b200/csrc/ *.cu   the sm_100a kernels and the C-ABI library (the product),
+ *   - oracle/ngw_oracle.c                    the CPU restatement used ONLY as the parity checker,
+ *   - gym_novel_gridworlds_b200/capi.py      ctypes mirror of these structs (the Python host layer).
+ *
+ * The reference (gtatiya/gym-novel-gridworlds, pure Python) has no FFI layer; its boundary for this
+ * path is the gym-0.18 Python API.  The entry points below are what a maintainer of the reference
+ * would bind (ctypes stub in INTEGRATION.md) to replace:
+ *
+ *   ngw_create / ngw_destroy      <- gym.make + wrapper constructors            (__init__.py:7-60,
+ *                                     pogostick_v1_env.py:26-84, bow_v1_env.py:26-82,
+ *                                     wrappers.py:63-68, observation_wrappers.py:16-30,
+ *                                     novelty_wrappers.py:1586-1674)
+ *   ngw_reset                     <- Env.reset + novelty reset overrides       (pogostick_v1_env.py:86-181,
+ *                                     novelty_wrappers.py:29,456,664,868,904,1013,1071,1126,1161)
+ *   ngw_step / ngw_step_host      <- Env.step through the whole wrapper chain  (pogostick_v1_env.py:230-367,
+ *                                     bow_v1_env.py:228-340, wrappers.py:74-85,
+ *                                     observation_wrappers.py:32-80, novelty_wrappers.py step methods)
+ *   ngw_observe                   <- LidarInFront.observation                  (observation_wrappers.py:70-80)
+ *   ngw_load_state / ngw_state_ptrs <- the `env=` restore branch of reset / get_observation's live
+ *                                     references                              (pogostick_v1_env.py:89-109,214-228)
+ *   ngw_stats                     <- (absent in the reference; episode statistics for the NCCL reduce)
+ *
+ * All wrapper / novelty semantics are flattened by the host layer into one `ngw_config` per distinct
+ * wrapper chain ("config"); every env of a batch carries a config id, so mixed-novelty batches run in
+ * one launch.  No torch types appear here: plain pointers, sizes and a cudaStream_t passed as void*.
+ */
+#ifndef NGW_H
+#define NGW_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGW_ABI_VERSION 3
+
+#define NGW_MAX_ITEMS 24          /* reference asserts len(items) <= 20 (pogostick_v1_env.py:75,220) */
+#define NGW_MAX_ACTIONS 48
+#define NGW_MAX_RECIPES 8
+#define NGW_MAX_RECIPE_INPUTS 4
+#define NGW_MAX_LAYERS 4
+#define NGW_MAX_PLACE 12
+#define NGW_MAX_RESET_OPS 8
+#define NGW_MAX_MAP_SIZE 64
+#define NGW_NONE 0xFF
+
+/* ---- facing ids (pogostick_v1_env.py:33) ---- */
+enum { NGW_NORTH = 0, NGW_SOUTH = 1, NGW_WEST = 2, NGW_EAST = 3 };
+
+/* ---- terminal opcodes: what an external action id finally executes on the base env ---- */
+enum ngw_op {
+    NGW_OP_INVALID = 0,        /* id rejected by LimitActions (wrappers.py:76) or unknown to the base (pogostick_v1_env.py:236) */
+    NGW_OP_NOOP = 1,           /* id known but no branch of the if/elif chain matches (pogostick_v1_env.py:244-347) */
+    NGW_OP_FORWARD = 2,        /* pogostick_v1_env.py:244-257 */
+    NGW_OP_LEFT = 3,           /* pogostick_v1_env.py:258-268 */
+    NGW_OP_RIGHT = 4,          /* pogostick_v1_env.py:269-279 */
+    NGW_OP_BREAK = 5,          /* pogostick_v1_env.py:280-294 and the novelty Break overrides (variant) */
+    NGW_OP_PLACE_TREE_TAP = 6, /* pogostick_v1_env.py:295-314 */
+    NGW_OP_EXTRACT_RUBBER = 7, /* pogostick_v1_env.py:315-331; arg = rubber gained (novelty_wrappers.py:1537-1551) */
+    NGW_OP_EXTRACT_STRING = 8, /* bow_v1_env.py:293-304;      arg = string gained (novelty_wrappers.py:1524-1536) */
+    NGW_OP_CRAFT = 9,          /* pogostick_v1_env.py:413-474 / novelty_wrappers.py:371-436; arg = recipe slot */
+    NGW_OP_SELECT = 10,        /* pogostick_v1_env.py:338-347; arg = item id */
+    NGW_OP_CHOP = 11,          /* novelty_wrappers.py:1288-1307 */
+    NGW_OP_JUMP = 12           /* novelty_wrappers.py:1360-1382 */
+};
+
+/* ---- Break variants (which class's Break block is the outermost terminal interceptor) ---- */
+enum ngw_break_variant {
+    NGW_BRK_BASE = 0,          /* pogostick_v1_env.py:280-294: reward only for tree_log */
+    NGW_BRK_AXE = 1,           /* novelty_wrappers.py:45-84 (AxeEasy/Medium/Hard), arg = axe item id */
+    NGW_BRK_AXE_INC = 2,       /* same with breakincrease == 'true' */
+    NGW_BRK_AXETOBREAK = 3,    /* novelty_wrappers.py:472-504, arg = axe item id */
+    NGW_BRK_INCREASE = 4       /* novelty_wrappers.py:1434-1458, arg = itemtobreakmore id or NGW_NONE (= all) */
+};
+
+/* ---- pass-through layers wrapped around a terminal opcode, outermost first ---- */
+enum ngw_layer {
+    NGW_LAYER_END = 0,
+    NGW_LAYER_CRATE = 1,       /* novelty_wrappers.py:1085-1088: pre-effect on Break when the front block is a crate */
+    NGW_LAYER_FIREWALL = 2,    /* novelty_wrappers.py:1169-1189: post-check after the inner step */
+    NGW_LAYER_FENCE_MEDIUM = 3,/* novelty_wrappers.py:918-973 with difficulty 'medium' */
+    NGW_LAYER_FENCE_HARD = 4   /* novelty_wrappers.py:918-973 with difficulty 'hard' */
+};
+
+/* ---- reset post-processing ops, applied inner -> outer in wrap order ---- */
+enum ngw_reset_kind {
+    NGW_RESET_FENCE = 1,       /* novelty_wrappers.py:868-889: a = fence id, percent in [lo, hi) of non-air non-wall cells */
+    NGW_RESET_ADDITEM = 2,     /* novelty_wrappers.py:1013-1034: a = new item id, percent of air cells */
+    NGW_RESET_REPLACE = 3,     /* novelty_wrappers.py:1126-1148: a = item to replace, b = replacement */
+    NGW_RESET_INVSET = 4       /* novelty_wrappers.py:33,460,668-671: inventory[a] = lo */
+};
+
+typedef struct {
+    uint8_t op;                        /* enum ngw_op */
+    uint8_t arg;
+    uint8_t variant;                   /* enum ngw_break_variant for NGW_OP_BREAK */
+    uint8_t reserved;
+    uint8_t layers[NGW_MAX_LAYERS];    /* enum ngw_layer, outermost first, NGW_LAYER_END terminated */
+} ngw_action_entry;
+
+typedef struct {
+    uint8_t n_inputs;
+    uint8_t in_item[NGW_MAX_RECIPE_INPUTS];
+    uint8_t in_qty[NGW_MAX_RECIPE_INPUTS];
+    uint8_t out_item;
+    uint8_t out_qty;
+    uint8_t needs_table;               /* len(recipe['input']) > 1 (pogostick_v1_env.py:444) */
+    int32_t reward_ok;                 /* 10 in Pogostick (pogostick_v1_env.py:455), 50 in Bow-v1 (bow_v1_env.py:424) */
+    float cost_missing;                /* pogostick_v1_env.py:433-436 */
+    float cost_no_table;               /* pogostick_v1_env.py:447-450, novelty_wrappers.py:409-410 */
+    float cost_ok;                     /* pogostick_v1_env.py:463-470, novelty_wrappers.py:431-432 */
+} ngw_recipe;
+
+typedef struct {
+    uint8_t kind;                      /* enum ngw_reset_kind */
+    uint8_t a;
+    uint8_t b;
+    uint8_t lo;                        /* np.random.randint(low=lo, high=hi) percent range, hi exclusive */
+    uint8_t hi;
+    uint8_t reserved[3];
+} ngw_reset_op;
+
+typedef struct {
+    /* ---- tables of the base env after all wrapper constructors ran ---- */
+    int32_t n_items;                   /* item ids 0..n_items-1, air = 0 (pogostick_v1_env.py:200-212) */
+    int32_t n_actions;                 /* external action ids 0..n_actions-1 */
+    ngw_action_entry actions[NGW_MAX_ACTIONS];
+    uint32_t unbreakable_mask;         /* bit i: item id i in unbreakable_items (pogostick_v1_env.py:41, novelty_wrappers.py:1116) */
+    uint32_t entity_mask;              /* bit i: item id i in entities (pogostick_v1_env.py:47,538-554) */
+    uint8_t id_wall, id_crafting_table, id_tree_log, id_tree_tap, id_rubber, id_wool, id_string, id_goal;
+    uint8_t id_wooden_axe, id_iron_axe; /* ids of the literal names compared at novelty_wrappers.py:56,67 */
+    uint8_t id_fence;                  /* FenceRestriction.env2.fence_name (novelty_wrappers.py:928) */
+    uint8_t id_fire_wall;              /* novelty_wrappers.py:1174 */
+    uint8_t id_crate;                  /* novelty_wrappers.py:1085 */
+    uint8_t reserved0[3];
+    uint8_t crate_add[NGW_MAX_ITEMS];  /* multiset Crate.crate_ingredients as per-item counts (novelty_wrappers.py:1064-1069) */
+    int32_t reward_intermediate;       /* pogostick_v1_env.py:81 */
+    int32_t reward_done;               /* pogostick_v1_env.py:82 */
+    int32_t reward_firewall;           /* -reward_done // 2 (novelty_wrappers.py:1187) */
+    int32_t n_recipes;
+    ngw_recipe recipes[NGW_MAX_RECIPES];
+
+    /* ---- LidarInFront (observation_wrappers.py:16-80); n_beams == 0 => no lidar wrapper, obs_dim 0 ---- */
+    int32_t n_beams;
+    int32_t max_range;                 /* int(sqrt(2 (ms-2)^2)) at wrap time (observation_wrappers.py:25) */
+    int32_t n_lidar_items;
+    int8_t lidar_slot[NGW_MAX_ITEMS];  /* item id -> 0-based lidar slot, -1 = occludes but is not reported */
+    int32_t n_inv_obs;
+    uint8_t inv_obs_item[NGW_MAX_ITEMS]; /* item ids in sorted-name order minus unbreakables (observation_wrappers.py:77-78) */
+    const int8_t* beam_lut;            /* HOST pointer, int8 [4 facings][n_beams][max_range][2] = (d_row, d_col) at sample k+1,
+                                          generated with the reference's own NumPy expression (observation_wrappers.py:39-55) */
+
+    /* ---- reset program (pogostick_v1_env.py:86-181 + novelty reset overrides) ---- */
+    int32_t n_place;
+    uint8_t place_item[NGW_MAX_PLACE]; /* items_quantity in insertion order (pogostick_v1_env.py:147) */
+    uint8_t place_qty[NGW_MAX_PLACE];
+    int32_t n_reset_ops;
+    ngw_reset_op reset_ops[NGW_MAX_RESET_OPS];
+    int32_t reset_obs_after_ops;       /* how many reset ops have run when the reset observation is taken (quirk Q3) */
+} ngw_config;
+
+/* per-env error flags (ngw_error_flags) */
+#define NGW_ERR_INVALID_ACTION 1u      /* AssertionError wrappers.py:76 / ValueError pogostick_v1_env.py:236 */
+#define NGW_ERR_PLACEMENT 2u           /* AssertionError "Cannot place items, increase map size!" pogostick_v1_env.py:167 */
+
+/* index of the counters returned by ngw_stats */
+enum { NGW_STAT_STEPS = 0, NGW_STAT_EPISODES = 1, NGW_STAT_SUCCESSES = 2, NGW_STAT_REWARD_SUM = 3,
+       NGW_STAT_COST_SUM = 4, NGW_STAT_RESETS = 5, NGW_STAT_INVALID = 6, NGW_STAT_RESERVED = 7, NGW_STAT_COUNT = 8 };
+
+/* raw device pointers of the struct-of-arrays state owned by a handle (get_observation's live references) */
+typedef struct {
+    int8_t*  map;        /* [n_envs_padded][map_size*map_size] item ids */
+    uint8_t* pose;       /* [n_envs_padded][4] = row, col, facing id, selected item id (0 = '') */
+    int32_t* inventory;  /* [n_envs_padded][inv_stride] quantity by item id */
+    uint8_t* cfg_id;     /* [n_envs_padded] */
+    uint32_t* episode;   /* [n_envs_padded] episode index (Philox counter word) */
+    int32_t* ep_len;     /* [n_envs_padded] steps taken in the current episode */
+    uint32_t* error_flags; /* [n_envs_padded] */
+    int32_t inv_stride;
+    int32_t obs_dim;     /* row length of the lidar observation = max over configs of L*B + I_obs */
+    int64_t n_envs;
+    int64_t n_envs_padded;
+    int32_t map_size;
+    int32_t n_configs;
+} ngw_state_view;
+
+typedef struct ngw_handle ngw_handle;
+
+/* Create a batch of n_envs environments on `device` sharing one map_size and n_cfgs configs.
+ * first_env_gid = global id of env 0 of this shard (Philox counters are keyed by global id, so a
+ * 1/2/4/8-GPU sharding of the same job generates identical episodes). */
+int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t n_envs, int32_t map_size,
+               int32_t device, int64_t first_env_gid, uint64_t seed);
+void ngw_destroy(ngw_handle* h);
+const char* ngw_last_error(void);
+int ngw_abi_version(void);
+
+int ngw_state(ngw_handle* h, ngw_state_view* out);
+
+/* cfg_id: DEVICE int32[n_envs] (NULL = all zero). */
+int ngw_set_env_configs(ngw_handle* h, const int32_t* cfg_id_dev, void* stream);
+
+/* Load `count` env states starting at env `first` from DEVICE arrays: map int8[count][ms*ms],
+ * pose uint8[count][4], inventory int32[count][inv_stride]. */
+int ngw_load_state(ngw_handle* h, const int8_t* map, const uint8_t* pose, const int32_t* inventory,
+                   int64_t first, int64_t count, void* stream);
+
+/* Reset envs whose mask byte is non-zero (mask DEVICE uint8[n_envs], NULL = all) with the Philox
+ * map generator; obs (DEVICE int32[n_envs][obs_dim], NULL = skip) receives the reset observation of
+ * the reset envs, taken after cfg.reset_obs_after_ops ops as the reference does. */
+int ngw_reset(ngw_handle* h, const uint8_t* mask, int32_t* obs, void* stream);
+
+/* One fused step of every env: action semantics + novelties + reward/done/step_cost + LidarInFront
+ * observation (+ Philox auto-reset of done envs when auto_reset != 0, + truncation when
+ * max_episode_steps > 0).  All pointers are DEVICE pointers; obs may be NULL when obs_dim == 0. */
+int ngw_step(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done,
+             float* step_cost, uint8_t* result, int32_t auto_reset, int32_t max_episode_steps, void* stream);
+
+/* Same call with HOST buffers (the reference-facing path): copies actions in, steps, copies
+ * obs/reward/done/step_cost/result out, chunk-pipelined over internal pinned staging; returns after
+ * the outputs are valid on the host. */
+int ngw_step_host(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done,
+                  float* step_cost, uint8_t* result, int32_t auto_reset, int32_t max_episode_steps);
+
+/* LidarInFront.observation of the current state into DEVICE int32[n_envs][obs_dim]. */
+int ngw_observe(ngw_handle* h, int32_t* obs, void* stream);
+
+/* Copy the NGW_STAT_COUNT accumulated counters (doubles) to DEVICE out8; reset_after != 0 zeroes them. */
+int ngw_stats(ngw_handle* h, double* out8_dev, int32_t reset_after, void* stream);
+
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches claim). */
+int64_t ngw_launch_count(ngw_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGW_H */

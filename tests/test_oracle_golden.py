@@ -1,0 +1,80 @@
+"""CPU suite: the host layer's tables and the C oracle against the golden traces of the unmodified reference."""
+import numpy as np
+import pytest
+
+import golden_util
+import scenarios
+from gym_novel_gridworlds_b200.compiler import compile_chain
+from oracle.oracle_lib import OracleBatch
+
+NAMES = golden_util.names()
+
+
+def _build(name):
+    g = golden_util.get(name)
+    env = scenarios.build_chain(scenarios.b200_namespace(), g['meta'])
+    return g, env, compile_chain(env)
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_host_tables_match_reference(name):
+    g, env, cc = _build(name)
+    meta, base = g['meta'], env.unwrapped
+    assert dict(base.items_id) == meta['items_id']
+    assert dict(base.actions_id) == meta['base_actions_id']
+    assert dict(env.actions_id) == meta['top_actions_id']
+    if meta['limited_actions_id'] is not None:
+        assert dict(env.limited_actions_id) == meta['limited_actions_id']
+    assert sorted(base.unbreakable_items) == meta['unbreakable']
+    assert sorted(base.entities) == meta['entities']
+    assert dict(base.items_quantity) == meta['items_quantity']
+    if meta['lidar_items_id'] is not None:
+        assert dict(env.lidar_items_id) == meta['lidar_items_id']
+    if meta['crate_ingredients'] is not None:
+        assert [str(x) for x in env.crate_ingredients] == meta['crate_ingredients']
+    assert cc.external_ids == meta['external_ids']
+    assert cc.reset_returns == meta['reset_kind']
+    for a in cc.external_ids:
+        assert a not in cc.invalid_reasons, cc.invalid_reasons
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_oracle_reset_reproduces_reference_stream(name):
+    g, env, cc = _build(name)
+    ob = OracleBatch([cc], 1)
+    n_items = g['reset_inv'].shape[1]
+    for ep, seed in enumerate(g['meta']['seeds']):
+        rc, obs = ob.reset_one(0, seed)
+        assert rc == 0
+        assert np.array_equal(ob.map[0], g['reset_map'][ep]), name
+        assert np.array_equal(ob.pose[0], g['reset_pose'][ep])
+        assert np.array_equal(ob.inv[0, :n_items], g['reset_inv'][ep])
+        if g['meta']['reset_kind'] == 'lidar':
+            assert np.array_equal(obs[:cc.obs_dim], g['reset_obs'][ep].astype(np.int32))
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_oracle_replay_matches_reference(name):
+    g, env, cc = _build(name)
+    E, T = g['actions'].shape
+    n_items = g['init_inv'].shape[1]
+    ob = OracleBatch([cc], E)
+    ob.map[:] = g['init_map']
+    ob.pose[:] = g['init_pose']
+    ob.inv[:, :n_items] = g['init_inv']
+    has_obs = g['obs'].shape[2] > 0
+    if has_obs:
+        assert g['obs'].shape[2] == cc.obs_dim
+    for t in range(T):
+        obs, reward, done, cost, result = ob.step(g['actions'][:, t])
+        where = "%s step %d" % (name, t)
+        assert not ob.err.any(), where
+        assert np.array_equal(reward, g['reward'][:, t].astype(np.float32)), where
+        assert np.array_equal(done, g['done'][:, t]), where
+        assert np.array_equal(result, g['result'][:, t]), where
+        np.testing.assert_allclose(cost, g['cost'][:, t], rtol=1e-6, err_msg=where)
+        assert np.array_equal(ob.map, g['map'][:, t]), where
+        assert np.array_equal(ob.pose, g['pose'][:, t]), where
+        assert np.array_equal(ob.inv[:, :n_items], g['inv'][:, t]), where
+        if has_obs:
+            assert np.array_equal(obs, g['obs'][:, t].astype(np.int32)), where

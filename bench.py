@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the fused step + LidarInFront hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...          (one rank per GPU, weak scaling)
+
+A "step" is ONE pass of the hot path over ONE batch of 65,536 envs of BASELINE config C2
+(NovelGridworld-Pogostick-v1 + LimitActions(10 actions) + LidarInFront(8 beams)), random actions.
+To keep L2 cold between timed iterations the run rotates over several independent batches whose combined
+working set (state + outputs) exceeds the 126 MB L2 ("inputs larger than L2").
+
+Prints ONE JSON line (rank 0).  `value` = device-timed throughput with inputs resident in HBM (CUDA-graph
+replay of the K launches, no host in the loop); `e2e` = the same metric through the host-buffer C-ABI call
+(ngw_step_host: pinned H2D of actions, kernel, D2H of obs/reward/done/step_cost/result every step);
+`roofline` = algorithmic bytes per launch / average launch duration vs the measured HBM copy peak;
+`cpu_baseline` = the C oracle port on the box's host cores.  `--impl reference` times that CPU port alone.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_BATCH = 65536
+C2_SET = ['Forward', 'Left', 'Right', 'Break', 'Place_tree_tap', 'Extract_rubber',
+          'Craft_plank', 'Craft_stick', 'Craft_tree_tap', 'Craft_pogo_stick']
+METRIC = "env-steps/sec, Pogostick-v1+LidarInFront, 1/2/4/8 B200 vs host-CPU reference"
+N_ACTION_SETS = 16
+GRAPH_STEPS = 1024
+
+
+def build_c2_chain(num_envs=1, device=None):
+    import gym_novel_gridworlds_b200 as gym
+    env = gym.make('NovelGridworld-Pogostick-v1', num_envs=num_envs, device=device)
+    env = gym.LimitActions(env, set(C2_SET))
+    return gym.LidarInFront(env, num_beams=8)
+
+
+def algorithmic_bytes_per_env_step(cc):
+    """read ms^2 + 4 (pose) + 4 I (inventory) + 4 (action); write 4 (pose) + 4 I + 4 (L B + I_obs)
+    + 4 (reward) + 4 (step_cost) + 1 (done) + 1 (result); grid write-back counted as 0."""
+    ms, n_items, d = cc.map_size, cc.n_items, cc.obs_dim
+    return (ms * ms + 4 + 4 * n_items + 4) + (4 + 4 * n_items + 4 * d + 4 + 4 + 1 + 1)
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons with NVML while the timed regions run."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.max_mhz, self.ok = index, [], False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                self.samples.append((time.perf_counter(), mhz, reasons, util))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self, t0, t1):
+        names = {0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x10: 'sync_boost',
+                 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown', 0x80: 'hw_power_brake_slowdown',
+                 0x100: 'display_clock_setting'}
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or [s for s in self.samples if s[3] > 0] or self.samples
+        reasons = 0
+        for s in inside:
+            reasons |= s[2]
+        return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in names.items() if reasons & b), "samples": len(inside)}
+
+
+def cpu_port_run(cc, envs, steps, warmup, threads, time_budget_s=None):
+    """Times the C oracle port (oracle/ngw_oracle.c) on `envs` environments with all host threads.  Threads own
+    contiguous env slices and run them without a per-step barrier (envs are independent) — the fastest honest CPU
+    arrangement of the reference algorithm; every step still writes obs/reward/done/step_cost/result."""
+    from oracle.oracle_lib import OracleBatch
+    ob = OracleBatch([cc], envs)
+    ob.reset_legacy(1)
+    rng = np.random.RandomState(1234)
+    acts = np.stack([rng.randint(0, cc.c.n_actions, size=envs).astype(np.int32) for _ in range(N_ACTION_SETS)])
+    if warmup:
+        ob.rollout(acts, warmup, n_threads=threads)
+    done, chunk = 0, 16
+    t0 = time.perf_counter()
+    while done < steps:
+        n = min(chunk, steps - done)
+        ob.rollout(acts, n, n_threads=threads)
+        done += n
+        if time_budget_s is not None and time.perf_counter() - t0 > time_budget_s:
+            break
+    return done, time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The reference itself is Python and
+    cannot travel to the GPU box, so this is its C port (the oracle) with every host thread.  A step is one pass
+    over S envs of the same C2 workload, S bounded so that K steps end within a few minutes."""
+    if rank != 0:
+        return
+    from gym_novel_gridworlds_b200.compiler import compile_chain
+    cc = compile_chain(build_c2_chain())
+    threads = os.cpu_count() or 1
+    K = max(args.steps, 1)
+    envs = ENVS_PER_BATCH
+    while envs > 1024 and envs * K > 4e8:
+        envs //= 2
+    steps, dt = cpu_port_run(cc, envs, K, args.warmup, threads)
+    value = steps * envs / dt
+    sample = ("%d steps x %d envs of C2 (bounded sample of the 65536-env batch), C port of the reference path "
+              "(oracle/ngw_oracle.c), %d threads, no per-step barrier" % (steps, envs, threads))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "C2: NovelGridworld-Pogostick-v1 + LimitActions(10) + LidarInFront(8), "
+                               "uniform random actions", "envs_per_step": envs},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from gym_novel_gridworlds_b200.compiler import compile_chain
+    from gym_novel_gridworlds_b200.runtime import BatchHandle
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    cc = compile_chain(build_c2_chain())
+    bytes_step = algorithmic_bytes_per_env_step(cc)
+    per_batch_ws = ENVS_PER_BATCH * bytes_step
+    n_batches = max(2, int(np.ceil(1.6 * 126e6 / per_batch_ws)))       # combined working set ~1.6x L2
+    batches = []
+    for b in range(n_batches):
+        gid0 = (rank * n_batches + b) * ENVS_PER_BATCH
+        h = BatchHandle([cc], ENVS_PER_BATCH, device=dev, seed=0, first_env_gid=gid0)
+        h.reset()
+        batches.append(h)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    acts = [torch.randint(0, cc.c.n_actions, (ENVS_PER_BATCH,), generator=gen, device=dev, dtype=torch.int32)
+            for _ in range(N_ACTION_SETS)]
+
+    def one_step(i):
+        batches[i % n_batches].step(acts[i % N_ACTION_SETS])
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- warm-up (eager launches), then capture the launch sequence into CUDA graphs
+    W, K = max(args.warmup, 3), args.steps
+    for i in range(W):
+        one_step(i)
+    torch.cuda.synchronize(dev)
+    launches_before = sum(h.launch_count() for h in batches)
+    g_steps = min(K, GRAPH_STEPS)
+    g_steps -= g_steps % n_batches if g_steps >= n_batches else 0       # whole rotations per replay
+    g_steps = max(g_steps, 1)
+    stream = torch.cuda.Stream(dev)
+
+    def capture(n):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(n):
+                    one_step(i)
+        return g
+
+    graph = capture(g_steps)
+    launches_per_step = (sum(h.launch_count() for h in batches) - launches_before) / g_steps
+    replays, rem = K // g_steps, K % g_steps
+    graph_rem = capture(rem) if rem else None
+    with torch.cuda.stream(stream):
+        graph.replay()                                                   # graph warm-up (uploads the exec graph)
+        if graph_rem:
+            graph_rem.replay()
+    torch.cuda.synchronize(dev)
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream, barrier + sync on both sides
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(replays):
+            graph.replay()
+        if graph_rem:
+            graph_rem.replay()
+        ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t_wall1 = time.perf_counter()
+    ms_total = ev0.elapsed_time(ev1)
+
+    # ---- eager (one python call per launch) figure, for the launch-bound picture
+    n_eager = min(K, 2000)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_eager):
+        one_step(i)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    eager_ms = e0.elapsed_time(e1) / n_eager
+
+    # ---- end-to-end through the host-buffer C-ABI call (ngw_step_host), pinned buffers, every step H2D + D2H
+    n_e2e = min(K, 200)
+    host_acts = [a.cpu().numpy() for a in acts]
+    for i in range(3):
+        batches[i % n_batches].step_host(host_acts[i % N_ACTION_SETS])
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for i in range(n_e2e):
+        obs, rew, dn, cost, res = batches[i % n_batches].step_host(host_acts[i % N_ACTION_SETS])
+        checksum += float(rew[0]) + float(obs[0, 0])                    # touch the results on the host
+    t_e2e = time.perf_counter() - t0
+    t_timed_end = time.perf_counter()
+
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    clocks = sampler.summary(t_wall0, t_timed_end)
+
+    stats = torch.zeros(8, dtype=torch.float64, device=dev)
+    for h in batches:
+        stats += h.stats()
+    times = torch.tensor([ms_total, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)                     # max over ranks
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)                     # episode statistics over NCCL
+    ms_total, e2e_ms_total = float(times[0].item()), float(times[1].item())
+
+    if rank == 0:
+        ms_per_step = ms_total / K
+        value = world * ENVS_PER_BATCH * K / (ms_total * 1e-3)
+        peak, peak_src = measured_hbm_peak()
+        achieved = ENVS_PER_BATCH * bytes_step / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')) as f:
+                traffic = json.load(f).get('dram_bytes_per_launch')
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "C2: NovelGridworld-Pogostick-v1 + LimitActions(10) + LidarInFront(8), "
+                                   "65536 envs/batch, uniform random actions",
+                       "envs_per_batch": ENVS_PER_BATCH, "batches_rotated": n_batches,
+                       "l2": "inputs larger than L2: %d rotating batches, %.0f MB combined working set vs 126 MB L2"
+                             % (n_batches, n_batches * per_batch_ws / 1e6),
+                       "launch": "CUDA-graph replay of %d-step graphs; eager python loop = %.2f us/step"
+                                 % (g_steps, eager_ms * 1e3),
+                       "per_gpu_envs": n_batches * ENVS_PER_BATCH, "parallelism": "independent shards x%d" % world},
+            "clocks": clocks,
+            "e2e": {"value": world * ENVS_PER_BATCH * n_e2e / (e2e_ms_total * 1e-3), "unit": "env-steps/s",
+                    "h2d_bytes_per_step": 4 * ENVS_PER_BATCH,
+                    "d2h_bytes_per_step": (4 * cc.obs_dim + 4 + 4 + 1 + 1) * ENVS_PER_BATCH,
+                    "steps": n_e2e, "api": "ngw_step_host (pinned host buffers, 8 chunks over 3 streams)"},
+            "gpu_launches": int(round(launches_per_step * K)),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "ngw::step_kernel<true>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_env_step": bytes_step,
+                         "algorithmic_bytes_per_launch": ENVS_PER_BATCH * bytes_step,
+                         "avg_launch_us": ms_per_step * 1e3},
+            "eager": {"value": ENVS_PER_BATCH / (eager_ms * 1e-3), "unit": "env-steps/s", "us_per_step": eager_ms * 1e3},
+            "episode_stats": dict(zip(('steps', 'episodes', 'successes', 'reward_sum', 'cost_sum', 'resets',
+                                       'invalid'), [float(x) for x in stats.cpu().numpy()[:7]])),
+            "wall_ms_timed_region": (t_wall1 - t_wall0) * 1e3,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            steps_cpu, dt = cpu_port_run(cc, ENVS_PER_BATCH, 10 ** 9, 16, threads, time_budget_s=3.0)
+            line["cpu_baseline"] = {
+                "value": steps_cpu * ENVS_PER_BATCH / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                "sample": "%d steps x %d envs (%.1f s wall, ~%.0f s of CPU work), C port of the reference path "
+                          "(oracle/ngw_oracle.c), %d threads, no per-step barrier"
+                          % (steps_cpu, ENVS_PER_BATCH, dt, dt * threads, threads)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=32768)
+    ap.add_argument('--warmup', type=int, default=64)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,445 @@
+// ngw_device.cuh — per-env device code of the batched NovelGridworld simulator (sm_100a).
+//
+// One lane owns one environment.  The lane's grid row, inventory row and observation row live in
+// shared memory (staged by the kernels in ngw_kernels.cu); everything here works on those rows through
+// plain pointers, so the same code also runs straight on global memory in the (cold) reset kernel.
+//
+// Semantics follow the reference file:line cited at each function (paths under
+// /root/reference/gym_novel_gridworlds/); the wrapper chain arrives flattened as an ngw_config.
+#pragma once
+#include <stdint.h>
+#include "../../include/ngw.h"
+
+namespace ngw {
+
+// ------------------------------------------------------------------ Philox4x32-10 (counter-based RNG)
+// counter = (global env id lo, hi, episode index, (stream << 20) | block), key = seed: draws depend only on
+// (seed, global env id, episode, stream, position) => identical episodes for any sharding over GPUs.
+struct Philox {
+    uint32_t c0, c1, c2, c3base, k0, k1;
+    uint32_t buf[4];
+    uint32_t blk;
+    int have;
+
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t stream) {
+        c0 = (uint32_t)gid; c1 = (uint32_t)(gid >> 32); c2 = episode; c3base = stream << 20;
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+        blk = 0; have = 0;
+    }
+    __device__ __forceinline__ void refill() {
+        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3base | blk, a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+            uint32_t y0 = hi1 ^ x1 ^ a, y1 = lo1, y2 = hi0 ^ x3 ^ b, y3 = lo0;
+            x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        buf[0] = x0; buf[1] = x1; buf[2] = x2; buf[3] = x3;
+        blk++; have = 4;
+    }
+    __device__ __forceinline__ uint32_t next() {
+        if (have == 0) refill();
+        have--;
+        // static indexing keeps buf in registers
+        return have == 3 ? buf[0] : have == 2 ? buf[1] : have == 1 ? buf[2] : buf[3];
+    }
+    // unbiased uniform integer in [0, n), n >= 1 (mask + rejection, like NumPy's legacy bounded draw)
+    __device__ __forceinline__ uint32_t below(uint32_t n) {
+        uint32_t max = n - 1;
+        if (max == 0) return 0;
+        uint32_t mask = 0xFFFFFFFFu >> __clz(max);
+        uint32_t v;
+        do { v = next() & mask; } while (v > max);
+        return v;
+    }
+};
+
+// ------------------------------------------------------------------ per-env view
+struct EnvRow {
+    const ngw_config* __restrict__ cfg;   // global memory, L1-resident (uniform across a config-homogeneous warp)
+    int8_t* m;                            // staged grid row [cells]
+    int8_t* gm;                           // the same row in global memory (write-through of the few changed cells), or nullptr
+    int32_t* inv;                         // staged inventory row
+    int ms;
+    int r, c, facing, sel;
+};
+
+struct StepOut {
+    int reward;
+    int done;
+    int result;
+    float cost;
+};
+
+__device__ __forceinline__ int cell(const EnvRow& e, int r, int c) { return e.m[r * e.ms + c]; }
+
+__device__ __forceinline__ void set_cell(EnvRow& e, int r, int c, int v) {
+    int idx = r * e.ms + c;
+    e.m[idx] = (int8_t)v;
+    if (e.gm) e.gm[idx] = (int8_t)v;
+}
+
+__device__ __forceinline__ bool in_mask(uint32_t mask, int item) { return (mask >> (item & 31)) & 1u; }
+
+// update_block_in_front (pogostick_v1_env.py:369-383)
+__device__ __forceinline__ void front_of(const EnvRow& e, int& fr, int& fc) {
+    fr = e.r + (e.facing == NGW_SOUTH) - (e.facing == NGW_NORTH);
+    fc = e.c + (e.facing == NGW_EAST) - (e.facing == NGW_WEST);
+}
+
+// bounds-checked neighbour test shared by is_block_in_front_next_to (pogostick_v1_env.py:391-411)
+// and the fire_wall check (novelty_wrappers.py:1171-1184)
+__device__ __forceinline__ bool next_to(const EnvRow& e, int r, int c, int item) {
+    int hi = e.ms - 1;
+    bool hit = false;
+    if (r - 1 >= 0 && r - 1 <= hi && c >= 0 && c <= hi) hit |= cell(e, r - 1, c) == item;
+    if (r + 1 >= 0 && r + 1 <= hi && c >= 0 && c <= hi) hit |= cell(e, r + 1, c) == item;
+    if (c - 1 >= 0 && c - 1 <= hi && r >= 0 && r <= hi) hit |= cell(e, r, c - 1) == item;
+    if (c + 1 >= 0 && c + 1 <= hi && r >= 0 && r <= hi) hit |= cell(e, r, c + 1) == item;
+    return hit;
+}
+
+// grab_entities (pogostick_v1_env.py:538-554); the agent is always interior so the 3x3 is in bounds
+__device__ __forceinline__ void grab_entities(EnvRow& e) {
+    uint32_t mask = e.cfg->entity_mask;
+    if (mask == 0) return;
+    for (int rr = e.r - 1; rr <= e.r + 1; rr++)
+        for (int cc = e.c - 1; cc <= e.c + 1; cc++) {
+            int id = cell(e, rr, cc);
+            if (id != 0 && in_mask(mask, id)) {
+                set_cell(e, rr, cc, 0);
+                e.inv[id] += 1;
+            }
+        }
+}
+
+// craft (pogostick_v1_env.py:413-474, bow_v1_env.py:386-441, novelty_wrappers.py:371-436)
+__device__ __forceinline__ void craft(EnvRow& e, const ngw_recipe& rc, StepOut& o) {
+    bool have_all = true;
+    int n_in = rc.n_inputs;
+    for (int i = 0; i < n_in; i++) {
+        int item = rc.in_item[i];
+        have_all &= (item != NGW_NONE) && (e.inv[item == NGW_NONE ? 0 : item] >= (int)rc.in_qty[i]);
+    }
+    if (!have_all) { o.result = 0; o.cost = rc.cost_missing; return; }
+    if (rc.needs_table) {
+        int fr, fc;
+        front_of(e, fr, fc);
+        if (cell(e, fr, fc) != e.cfg->id_crafting_table) { o.result = 0; o.cost = rc.cost_no_table; return; }
+    }
+    o.reward = rc.reward_ok;
+    for (int i = 0; i < n_in; i++) e.inv[rc.in_item[i]] -= (int)rc.in_qty[i];
+    e.inv[rc.out_item] += (int)rc.out_qty;
+    o.cost = rc.cost_ok;
+}
+
+// terminal opcode: the innermost step body that finally handles the action, WITHOUT its trailing
+// grab_entities / done block (applied by the caller, once, as the reference's paths all do)
+__device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_action_entry a, StepOut& o) {
+    const ngw_config* cfg = e.cfg;
+    int fr, fc;
+    front_of(e, fr, fc);
+    o.reward = -1; o.result = 1; o.cost = 0.0f; o.done = 0;         // pogostick_v1_env.py:239-242
+    switch (a.op) {
+        case NGW_OP_FORWARD:                                          // pogostick_v1_env.py:244-257
+            if (cell(e, fr, fc) == 0) { e.r = fr; e.c = fc; } else o.result = 0;
+            o.cost = 27.906975f;
+            break;
+        case NGW_OP_LEFT:                                             // N->W S->E W->S E->N  (0->2 1->3 2->1 3->0)
+            e.facing = (0x0132 >> (e.facing * 4)) & 0xF; o.cost = 24.0f;
+            break;
+        case NGW_OP_RIGHT:                                            // N->E S->W W->N E->S  (0->3 1->2 2->0 3->1)
+            e.facing = (0x1023 >> (e.facing * 4)) & 0xF; o.cost = 24.0f;
+            break;
+        case NGW_OP_BREAK: {
+            int front = cell(e, fr, fc);
+            o.cost = 3600.0f;
+            if (in_mask(cfg->unbreakable_mask, front)) { o.result = 0; break; }
+            int variant = a.variant;
+            if (variant == NGW_BRK_BASE) {                            // pogostick_v1_env.py:283-289
+                set_cell(e, fr, fc, 0);
+                e.inv[front] += 1;
+                if (front == cfg->id_tree_log) o.reward = cfg->reward_intermediate;
+            } else if (variant == NGW_BRK_INCREASE) {                 // novelty_wrappers.py:1444-1454
+                set_cell(e, fr, fc, 0);
+                e.inv[front] += (a.arg == NGW_NONE || a.arg == front) ? 2 : 1;
+                o.reward = cfg->reward_intermediate;
+            } else {                                                  // axe / axetobreak, novelty_wrappers.py:55-81, 482-501
+                bool has_axe = e.inv[a.arg] >= 1;
+                bool wooden = has_axe && cfg->id_wooden_axe != NGW_NONE && e.sel == cfg->id_wooden_axe;
+                bool iron = has_axe && !wooden && cfg->id_iron_axe != NGW_NONE && e.sel == cfg->id_iron_axe;
+                if (wooden || iron) {
+                    set_cell(e, fr, fc, 0);
+                    e.inv[front] += (variant == NGW_BRK_AXE_INC) ? 2 : 1;
+                    o.reward = cfg->reward_intermediate;
+                    o.cost = wooden ? 1800.0f : 900.0f;
+                } else if (variant == NGW_BRK_AXETOBREAK) {
+                    o.result = 0;
+                } else {                                              // breaks, but no reward even for tree_log (Q4)
+                    set_cell(e, fr, fc, 0);
+                    e.inv[front] += 1;
+                }
+            }
+            break;
+        }
+        case NGW_OP_PLACE_TREE_TAP:                                   // pogostick_v1_env.py:295-314
+            o.cost = 300.0f;
+            if (e.inv[cfg->id_tree_tap] >= 1 && cell(e, fr, fc) == 0) {
+                set_cell(e, fr, fc, cfg->id_tree_tap);
+                e.inv[cfg->id_tree_tap] -= 1;
+                if (next_to(e, fr, fc, cfg->id_tree_log)) o.reward = cfg->reward_intermediate;
+            } else o.result = 0;
+            break;
+        case NGW_OP_EXTRACT_RUBBER:                                   // pogostick_v1_env.py:315-331, novelty_wrappers.py:1537-1551
+            o.cost = 120.0f;
+            if (cell(e, fr, fc) == cfg->id_tree_tap && next_to(e, fr, fc, cfg->id_tree_log)) {
+                e.inv[cfg->id_rubber] += a.arg;
+                o.reward = cfg->reward_intermediate; o.cost = 50000.0f;
+            } else o.result = 0;
+            break;
+        case NGW_OP_EXTRACT_STRING:                                   // bow_v1_env.py:293-304, novelty_wrappers.py:1524-1536
+            o.cost = 120.0f;
+            if (cell(e, fr, fc) == cfg->id_wool) {
+                e.inv[cfg->id_string] += a.arg;
+                set_cell(e, fr, fc, 0);
+                o.reward = cfg->reward_intermediate; o.cost = 5000.0f;
+            } else o.result = 0;
+            break;
+        case NGW_OP_CRAFT:
+            craft(e, cfg->recipes[a.arg], o);
+            break;
+        case NGW_OP_SELECT:                                           // pogostick_v1_env.py:338-347
+            o.cost = 120.0f;
+            if (a.arg != NGW_NONE && e.inv[a.arg] >= 1) e.sel = a.arg; else o.result = 0;
+            break;
+        case NGW_OP_CHOP: {                                           // novelty_wrappers.py:1291-1307
+            int front = cell(e, fr, fc);
+            o.cost = 3600.0f * 1.2f;
+            if (!in_mask(cfg->unbreakable_mask, front)) {
+                set_cell(e, fr, fc, 0);
+                e.inv[front] += 2;
+                o.reward = cfg->reward_intermediate;
+            } else o.result = 0;
+            break;
+        }
+        case NGW_OP_JUMP: {                                           // novelty_wrappers.py:1363-1382
+            int tr = e.r + 2 * (fr - e.r), tc = e.c + 2 * (fc - e.c);
+            if (tr >= 0 && tr <= e.ms - 1 && tc >= 0 && tc <= e.ms - 1 && cell(e, tr, tc) == 0) { e.r = tr; e.c = tc; }
+            else o.result = 0;
+            o.cost = 27.906975f * 2.0f;
+            break;
+        }
+        default: break;                                               // NGW_OP_NOOP
+    }
+}
+
+// "Update after each step" (pogostick_v1_env.py:349-357 and its copies in every intercepting novelty)
+__device__ __forceinline__ void post_step(EnvRow& e, StepOut& o) {
+    grab_entities(e);
+    o.done = 0;
+    if (e.inv[e.cfg->id_goal] >= 1) { o.reward = e.cfg->reward_done; o.done = 1; }
+}
+
+// One full reference step() through the flattened wrapper chain.  Layers are walked outermost-first
+// (what each wrapper does before calling self.env.step), the terminal opcode runs if every
+// FenceRestriction on the way let it through, then the layers' post blocks run innermost-first.
+__device__ __forceinline__ void step_env(EnvRow& e, const ngw_action_entry a, StepOut& o) {
+    uint32_t layers = (uint32_t)a.layers[0] | ((uint32_t)a.layers[1] << 8) | ((uint32_t)a.layers[2] << 16) |
+                      ((uint32_t)a.layers[3] << 24);
+    if (layers == 0) {                       // the common case: no pass-through novelty around this action
+        terminal_op(e, a, o);
+        post_step(e, o);
+        return;
+    }
+    const ngw_config* cfg = e.cfg;
+    int fr, fc;
+    front_of(e, fr, fc);
+    int front = cell(e, fr, fc);             // nothing before the terminal opcode changes the grid
+    int n = 0, stop = -1;                    // stop = index of the FenceRestriction layer that refused, -1 = none
+    for (; n < NGW_MAX_LAYERS; n++) {
+        int layer = (layers >> (8 * n)) & 0xFF;
+        if (layer == NGW_LAYER_END) break;
+        if (layer == NGW_LAYER_CRATE) {                               // novelty_wrappers.py:1085-1088
+            if (front == cfg->id_crate)
+                for (int it = 0; it < cfg->n_items; it++) e.inv[it] += (int)cfg->crate_add[it];
+        } else if (layer == NGW_LAYER_FENCE_MEDIUM || layer == NGW_LAYER_FENCE_HARD) {   // novelty_wrappers.py:926-958
+            bool pass;
+            int fence = cfg->id_fence;
+            if (in_mask(cfg->unbreakable_mask, front)) pass = false;
+            else if (front == fence) pass = true;
+            else if (layer == NGW_LAYER_FENCE_MEDIUM) {
+                bool ns = e.facing == NGW_NORTH || e.facing == NGW_SOUTH;
+                int a0 = ns ? cell(e, e.r, e.c - 1) : cell(e, e.r - 1, e.c);
+                int a1 = ns ? cell(e, e.r, e.c + 1) : cell(e, e.r + 1, e.c);
+                pass = !(a0 == fence || a1 == fence);
+            } else {
+                bool any = false;
+                for (int rr = fr - 1; rr <= fr + 1; rr++)
+                    for (int cc = fc - 1; cc <= fc + 1; cc++)
+                        if (rr >= 0 && rr < e.ms && cc >= 0 && cc < e.ms) any |= cell(e, rr, cc) == fence;
+                pass = !any;
+            }
+            if (!pass) { stop = n; break; }
+        }
+    }
+    int first_post;                           // innermost layer whose post block runs
+    if (stop < 0) {
+        terminal_op(e, a, o);
+        post_step(e, o);
+        first_post = n - 1;
+    } else {
+        o.reward = -1; o.result = 0; o.cost = 3600.0f; o.done = 0;
+        first_post = stop;
+    }
+    for (int i = first_post; i >= 0; i--) {
+        int layer = (layers >> (8 * i)) & 0xFF;
+        if (layer == NGW_LAYER_FIREWALL) {                            // novelty_wrappers.py:1171-1189
+            if (next_to(e, e.r, e.c, cfg->id_fire_wall)) { o.reward = cfg->reward_firewall; o.done = 1; }
+        } else if (layer == NGW_LAYER_FENCE_MEDIUM || layer == NGW_LAYER_FENCE_HARD) {
+            // outer post block re-runs and overwrites info (Q5, novelty_wrappers.py:960-973); reward is the inner one
+            int reward = o.reward;
+            post_step(e, o);                  // sets done / reward_done from the goal test, done = 0 otherwise
+            if (!o.done) o.reward = reward;
+            o.result = (i == stop) ? 0 : 1;
+            o.cost = 3600.0f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ LidarInFront (observation_wrappers.py:32-80)
+// lut: int16 [4][B][K] linear offsets d_row * ms + d_col of sample k+1 (built on the host with the reference's
+// NumPy expression).  obs row must be zero-filled for the lidar part by the caller.
+__device__ __forceinline__ void lidar_observe(const EnvRow& e, const int16_t* lut, int32_t* obs) {
+    const ngw_config* cfg = e.cfg;
+    int B = cfg->n_beams, K = cfg->max_range, L = cfg->n_lidar_items;
+    int cells = e.ms * e.ms;
+    int pos = e.r * e.ms + e.c;
+    const int16_t* row = lut + e.facing * B * K;
+    for (int b = 0; b < B; b++, row += K) {
+        for (int k = 0; k < K; k++) {
+            int idx = pos + row[k];
+            if ((unsigned)idx >= (unsigned)cells) break;              // unreachable on a walled grid
+            int id = e.m[idx];
+            if (id != 0) {
+                int slot = cfg->lidar_slot[id];
+                if (slot >= 0) obs[b * L + slot] = k + 1;
+                break;
+            }
+        }
+    }
+    int n_tail = cfg->n_inv_obs;
+    int32_t* tail = obs + L * B;
+    for (int i = 0; i < n_tail; i++) tail[i] = e.inv[cfg->inv_obs_item[i]];   // sorted-name order (Q7)
+}
+
+// ------------------------------------------------------------------ reset (pogostick_v1_env.py:86-181 + novelty resets)
+// Same DISTRIBUTION as the reference, not the same stream: the reference draws uniformly from a list it
+// shrinks by popping every drawn cell; a popped cell is either the agent cell, a placed item or a cell that
+// can never become placeable again, so "first placeable cell in a uniformly random order" == uniform over
+// the currently placeable cells == draw-with-replacement-until-placeable, which needs no list.
+__device__ __forceinline__ bool placeable(const EnvRow& e, int r, int c) {
+    return cell(e, r, c) == 0 && cell(e, r - 1, c) == 0 && cell(e, r + 1, c) == 0 && cell(e, r, c - 1) == 0 &&
+           cell(e, r, c + 1) == 0;
+}
+
+__device__ __noinline__ uint32_t reset_base(EnvRow& e, int inv_stride, uint64_t seed, uint64_t gid, uint32_t episode) {
+    const ngw_config* cfg = e.cfg;
+    int ms = e.ms;
+    uint32_t err = 0;
+    for (int i = 0; i < inv_stride; i++) e.inv[i] = 0;                // pogostick_v1_env.py:119-120
+    e.sel = 0;
+    int wall = cfg->id_wall;
+    for (int r = 0; r < ms; r++)                                      // pogostick_v1_env.py:129-130
+        for (int c = 0; c < ms; c++)
+            e.m[r * ms + c] = (r == 0 || c == 0 || r == ms - 1 || c == ms - 1) ? (int8_t)wall : (int8_t)0;
+    Philox rng;
+    rng.init(seed, gid, episode, 0);
+    int side = ms - 4;                                                // rows/cols 2 .. ms-3 (pogostick_v1_env.py:136-138)
+    uint32_t n_av = (uint32_t)(side * side);
+    uint32_t a = rng.below(n_av);
+    e.r = 2 + (int)(a / side); e.c = 2 + (int)(a % side);             // pogostick_v1_env.py:141-142
+    e.facing = (int)rng.below(4);                                     // pogostick_v1_env.py:145
+    int agent = e.r * ms + e.c;
+    for (int i = 0; i < cfg->n_place; i++) {                          // pogostick_v1_env.py:147-148,159-181
+        int item = cfg->place_item[i], qty = cfg->place_qty[i];
+        for (int count = 0; count < qty; count++) {
+            bool placed = false;
+            for (uint32_t attempt = 0; attempt < 8 * n_av && !placed; attempt++) {
+                uint32_t d = rng.below(n_av);
+                int r = 2 + (int)(d / side), c = 2 + (int)(d % side);
+                if (r * ms + c != agent && placeable(e, r, c)) { e.m[r * ms + c] = (int8_t)item; placed = true; }
+            }
+            if (!placed) {                                            // rare: count the placeable cells exactly
+                uint32_t good = 0;
+                for (int r = 2; r <= ms - 3; r++)
+                    for (int c = 2; c <= ms - 3; c++) good += (r * ms + c != agent && placeable(e, r, c));
+                if (good == 0) { err |= NGW_ERR_PLACEMENT; i = cfg->n_place; break; }   // pogostick_v1_env.py:167
+                uint32_t pick = rng.below(good);
+                for (int r = 2; r <= ms - 3 && !placed; r++)
+                    for (int c = 2; c <= ms - 3 && !placed; c++)
+                        if (r * ms + c != agent && placeable(e, r, c)) {
+                            if (pick == 0) { e.m[r * ms + c] = (int8_t)item; placed = true; }
+                            pick--;
+                        }
+            }
+        }
+    }
+    return err;
+}
+
+// Post-ops [op_begin, op_end).  A uniformly random m-subset of the candidate cells (what "shuffle, take the
+// first m" selects) is drawn by selection sampling in row-major order: candidate j of n is taken with
+// probability (m - taken) / (n - j).  m = ceil(n * (pct / 100)) in IEEE doubles exactly as NumPy computes it.
+__device__ __noinline__ void reset_ops(EnvRow& e, int op_begin, int op_end, uint64_t seed, uint64_t gid, uint32_t episode) {
+    const ngw_config* cfg = e.cfg;
+    int ms = e.ms, cells = ms * ms;
+    int agent = e.r * ms + e.c;
+    if (op_end > cfg->n_reset_ops) op_end = cfg->n_reset_ops;
+    for (int k = op_begin; k < op_end; k++) {
+        const ngw_reset_op op = cfg->reset_ops[k];
+        if (op.kind == NGW_RESET_INVSET) { e.inv[op.a] = op.lo; continue; }          // novelty_wrappers.py:33,460,668-671
+        Philox rng;
+        rng.init(seed, gid, episode, 1 + k);
+        int wall = cfg->id_wall;
+        int n = 0;
+        for (int i = 0; i < cells; i++) {
+            int id = e.m[i];
+            bool cand = op.kind == NGW_RESET_FENCE ? (id != 0 && id != wall)          // novelty_wrappers.py:872
+                      : op.kind == NGW_RESET_ADDITEM ? (id == 0)                      // novelty_wrappers.py:1017
+                      : (id == op.a);                                                 // novelty_wrappers.py:1130
+            n += cand;
+        }
+        int pct = op.lo + (int)rng.below((uint32_t)(op.hi - op.lo));                  // randint(low, high), high exclusive
+        int m = (int)ceil((double)n * ((double)pct / 100.0));                         // novelty_wrappers.py:881,1025,1139
+        if (m > n) m = n;
+        int seen = 0, taken = 0;
+        for (int i = 0; i < cells && taken < m; i++) {
+            int id = e.m[i] & 0x7F;
+            bool marked = e.m[i] & 0x80;
+            bool cand = !marked && (op.kind == NGW_RESET_FENCE ? (id != 0 && id != wall)
+                                  : op.kind == NGW_RESET_ADDITEM ? (id == 0) : (id == op.a));
+            if (!cand) continue;
+            bool take = rng.below((uint32_t)(n - seen)) < (uint32_t)(m - taken);
+            seen++;
+            if (!take) continue;
+            taken++;
+            if (op.kind == NGW_RESET_FENCE) e.m[i] = (int8_t)(id | 0x80);             // mark; fences go in afterwards
+            else if (i != agent) e.m[i] = (int8_t)(op.kind == NGW_RESET_ADDITEM ? op.a : op.b);
+        }
+        if (op.kind == NGW_RESET_FENCE) {                                             // add_fence_around, pogostick_v1_env.py:524-536
+            for (int i = 0; i < cells; i++) {
+                if (!(e.m[i] & 0x80)) continue;
+                e.m[i] = (int8_t)(e.m[i] & 0x7F);
+                int r = i / ms, c = i % ms;
+                for (int rr = r - 1; rr <= r + 1; rr++)
+                    for (int cc = c - 1; cc <= c + 1; cc++)
+                        if (rr >= 0 && rr < ms && cc >= 0 && cc < ms && e.m[rr * ms + cc] == 0 && rr * ms + cc != agent)
+                            e.m[rr * ms + cc] = (int8_t)op.a;
+            }
+        }
+    }
+}
+
+}  // namespace ngw

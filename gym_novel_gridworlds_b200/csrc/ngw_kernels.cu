@@ -1,0 +1,646 @@
+// ngw_kernels.cu — kernels + C-ABI of libngw_b200.so (sm_100a only; see include/ngw.h for the contract).
+//
+// Data layout in HBM (struct of arrays, rows padded to a multiple of 32 envs so a warp's tile of 32 envs is
+// one contiguous, 128-byte aligned span in every array):
+//     map   int8  [Np][ms*ms]      pose uchar4 [Np] (row, col, facing, selected)      inventory int32 [Np][Is]
+//     cfg_id uint8 [Np]            episode u32 [Np]     ep_len i32 [Np]     error_flags u32 [Np]
+//
+// step_kernel: one warp = one tile of 32 envs, one lane = one env.  The tile's grid rows and inventory rows are
+// brought into shared memory with two TMA 1-D bulk copies (cp.async.bulk + mbarrier), the lanes run the
+// flattened reference step on their row, cast the LidarInFront beams into an observation tile in shared
+// memory, and the inventory tile and observation tile leave with two TMA bulk stores; pose / reward / done /
+// step_cost / result are plain coalesced accesses.  Algorithmic bytes per env-step are in DESIGN.md.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "ngw_device.cuh"
+
+namespace ngw {
+
+// ------------------------------------------------------------------ PTX helpers (TMA 1-D bulk copies, mbarrier)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait sleeps in hardware; the time bound turns a lost transaction into a trap instead of a hung GPU
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > 4000000000ll) __trap();
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------ parameters
+struct StepParams {
+    const ngw_config* cfgs;
+    int8_t* map;
+    uchar4* pose;
+    int32_t* inv;
+    const uint8_t* cfg_id;
+    uint32_t* episode;
+    int32_t* ep_len;
+    uint32_t* err;
+    const int32_t* actions;     // nullptr => observe only (no step, no outputs but obs)
+    int32_t* obs;               // nullptr => no observation
+    float* reward;
+    uint8_t* done;
+    float* cost;
+    uint8_t* result;
+    double* stats;              // [NGW_STAT_SLOTS][NGW_STAT_COUNT] or nullptr
+    long long env_begin, env_end;   // env range of this launch (env_begin multiple of 32)
+    long long first_gid;
+    unsigned long long seed;
+    int ms, cells, inv_stride, obs_dim;
+    int map_bytes, inv_bytes, obs_bytes, lut_bytes, region_bytes;   // per-warp shared-memory carve-up
+    int auto_reset, max_episode_steps;
+};
+
+#define NGW_STAT_SLOTS 32
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void warp_copy16(void* dst, const void* src, int bytes, int lane) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    for (int i = lane; i < (bytes >> 4); i += 32) d[i] = s[i];
+}
+
+// ------------------------------------------------------------------ the fused step + LidarInFront kernel
+template <bool kTma>
+__global__ void __launch_bounds__(128) step_kernel(const StepParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const long long e0 = p.env_begin + ((long long)blockIdx.x * warps + warp) * 32;
+    if (e0 >= p.env_end) return;                                     // whole warp leaves together
+    const long long e = e0 + lane;
+    const bool valid = e < p.env_end;
+    const bool full_tile = e0 + 32 <= p.env_end;
+
+    unsigned char* region = smem + (size_t)warp * p.region_bytes;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(region);
+    int8_t* smap = reinterpret_cast<int8_t*>(region + 16);
+    int32_t* sinv = reinterpret_cast<int32_t*>(region + 16 + p.map_bytes);
+    int32_t* sobs = reinterpret_cast<int32_t*>(region + 16 + p.map_bytes + p.inv_bytes);
+    int16_t* slut = reinterpret_cast<int16_t*>(region + 16 + p.map_bytes + p.inv_bytes + p.obs_bytes);
+
+    // ---- stage the tile: grid rows + inventory rows (state arrays are padded, a full tile is always readable)
+    const int8_t* gmap = p.map + e0 * p.cells;
+    int32_t* ginv = p.inv + e0 * p.inv_stride;
+    if (kTma) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, (uint32_t)(p.map_bytes + p.inv_bytes));
+            bulk_g2s(smap, gmap, (uint32_t)p.map_bytes, bar);
+            bulk_g2s(sinv, ginv, (uint32_t)p.inv_bytes, bar);
+        }
+    } else {
+        warp_copy16(smap, gmap, p.map_bytes, lane);
+        warp_copy16(sinv, ginv, p.inv_bytes, lane);
+    }
+    __syncwarp();                                                    // barrier init visible before anyone waits on it
+
+    // ---- while the copies fly: per-lane scalars, config, beam LUT, zero the observation tile
+    uchar4 ps = p.pose[e];
+    const int cfg_i = p.cfg_id[e];
+    const ngw_config* cfg = p.cfgs + cfg_i;
+    const int cfg_first = __shfl_sync(0xFFFFFFFFu, cfg_i, 0);
+    const bool uniform = __all_sync(0xFFFFFFFFu, !valid || cfg_i == cfg_first);
+    const int16_t* lut = reinterpret_cast<const int16_t*>(cfg->beam_lut);
+    if (p.obs != nullptr) {
+        const ngw_config* c0 = p.cfgs + cfg_first;
+        const int16_t* glut = reinterpret_cast<const int16_t*>(c0->beam_lut);
+        if (uniform && glut != nullptr) {                            // config-homogeneous warp: LUT into shared memory
+            int n = 4 * c0->n_beams * c0->max_range;
+            for (int i = lane; i < n; i += 32) slut[i] = glut[i];
+            lut = slut;
+        }
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* o4 = reinterpret_cast<uint4*>(sobs);
+        for (int i = lane; i < (p.obs_bytes >> 4); i += 32) o4[i] = z;
+    }
+    int action = 0;
+    if (p.actions != nullptr && valid) action = p.actions[e];
+
+    if (kTma) mbar_wait(bar, 0);
+    __syncwarp();
+
+    EnvRow env;
+    env.cfg = cfg;
+    env.m = smap + lane * p.cells;
+    env.gm = p.map + e * p.cells;
+    env.inv = sinv + lane * p.inv_stride;
+    env.ms = p.ms;
+    env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+
+    if (p.actions != nullptr) {
+        StepOut o;
+        o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f;
+        int invalid = 0, did_reset = 0, success = 0;
+        if (valid) {
+            ngw_action_entry a;
+            a.op = NGW_OP_INVALID;
+            if (action >= 0 && action < cfg->n_actions) {
+                uint2 raw = *reinterpret_cast<const uint2*>(&cfg->actions[action]);
+                memcpy(&a, &raw, sizeof(a));
+            }
+            if (a.op == NGW_OP_INVALID) {                             // wrappers.py:76 / pogostick_v1_env.py:236 would raise
+                invalid = 1;
+                p.err[e] |= NGW_ERR_INVALID_ACTION;
+            } else {
+                step_env(env, a, o);
+                success = o.done && env.inv[cfg->id_goal] >= 1;
+                int finished = o.done;
+                if (p.max_episode_steps > 0) {
+                    int len = p.ep_len[e] + 1;
+                    if (len >= p.max_episode_steps) { finished = 1; o.done = 1; }     // harness truncation knob
+                    p.ep_len[e] = finished && p.auto_reset ? 0 : len;
+                }
+                if (finished && p.auto_reset) {                       // fused auto-reset (rare lanes only)
+                    did_reset = 1;
+                    uint32_t ep = p.episode[e] + 1;
+                    p.episode[e] = ep;
+                    env.gm = nullptr;
+                    uint32_t err = reset_base(env, p.inv_stride, p.seed, (uint64_t)(p.first_gid + e), ep);
+                    reset_ops(env, 0, NGW_MAX_RESET_OPS, p.seed, (uint64_t)(p.first_gid + e), ep);
+                    if (err) p.err[e] |= err;
+                    int8_t* grow = p.map + e * p.cells;
+                    for (int i = 0; i < p.cells; i++) grow[i] = env.m[i];
+                }
+            }
+            p.pose[e] = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
+                                    (unsigned char)env.sel);
+            p.reward[e] = (float)o.reward;
+            p.done[e] = (uint8_t)o.done;
+            p.cost[e] = o.cost;
+            p.result[e] = (uint8_t)o.result;
+        }
+        if (p.stats != nullptr) {
+            int n_done = __reduce_add_sync(0xFFFFFFFFu, valid ? o.done : 0);
+            int n_succ = __reduce_add_sync(0xFFFFFFFFu, success);
+            int n_reset = __reduce_add_sync(0xFFFFFFFFu, did_reset);
+            int n_inv = __reduce_add_sync(0xFFFFFFFFu, invalid);
+            int n_valid = __reduce_add_sync(0xFFFFFFFFu, valid ? 1 : 0);
+            int r_sum = __reduce_add_sync(0xFFFFFFFFu, o.reward);
+            float c_sum = warp_sum(o.cost);
+            if (lane == 0) {
+                double* s = p.stats + (size_t)(blockIdx.x % NGW_STAT_SLOTS) * NGW_STAT_COUNT;
+                atomicAdd(&s[NGW_STAT_STEPS], (double)(n_valid - n_inv));
+                atomicAdd(&s[NGW_STAT_REWARD_SUM], (double)r_sum);
+                atomicAdd(&s[NGW_STAT_COST_SUM], (double)c_sum);
+                if (n_done) atomicAdd(&s[NGW_STAT_EPISODES], (double)n_done);
+                if (n_succ) atomicAdd(&s[NGW_STAT_SUCCESSES], (double)n_succ);
+                if (n_reset) atomicAdd(&s[NGW_STAT_RESETS], (double)n_reset);
+                if (n_inv) atomicAdd(&s[NGW_STAT_INVALID], (double)n_inv);
+            }
+        }
+    }
+
+    // ---- LidarInFront observation of the (possibly auto-reset) state into the shared-memory tile
+    if (p.obs != nullptr && valid && cfg->n_beams > 0) lidar_observe(env, lut, sobs + lane * p.obs_dim);
+
+    // ---- write back: inventory tile (only when stepping) and observation tile
+    __syncwarp();
+    if (kTma && full_tile) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            if (p.actions != nullptr) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
+            if (p.obs != nullptr) bulk_s2g(p.obs + e0 * p.obs_dim, sobs, (uint32_t)p.obs_bytes);
+            bulk_commit();
+            bulk_wait_read0();                                       // shared memory must outlive the reads
+        }
+    } else {
+        if (p.actions != nullptr) warp_copy16(ginv, sinv, p.inv_bytes, lane);
+        if (p.obs != nullptr) {
+            int n = (int)((p.env_end - e0 < 32 ? p.env_end - e0 : 32)) * p.obs_dim;
+            int32_t* gobs = p.obs + e0 * p.obs_dim;
+            if (full_tile) warp_copy16(gobs, sobs, p.obs_bytes, lane);
+            else for (int i = lane; i < n; i += 32) gobs[i] = sobs[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ cold-path kernels (one thread per env, global memory)
+struct ResetParams {
+    const ngw_config* cfgs;
+    int8_t* map;
+    uchar4* pose;
+    int32_t* inv;
+    const uint8_t* cfg_id;
+    uint32_t* episode;
+    int32_t* ep_len;
+    uint32_t* err;
+    const uint8_t* mask;
+    long long n_envs, first_gid;
+    unsigned long long seed;
+    int ms, cells, inv_stride;
+    int phase;   // 0: base + ops before the reset observation, 1: ops after it, 2: everything
+};
+
+__global__ void reset_kernel(const ResetParams p) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n_envs) return;
+    if (p.mask != nullptr && p.mask[e] == 0) return;
+    const ngw_config* cfg = p.cfgs + p.cfg_id[e];
+    EnvRow env;
+    env.cfg = cfg;
+    env.m = p.map + e * p.cells;
+    env.gm = nullptr;
+    env.inv = p.inv + e * p.inv_stride;
+    env.ms = p.ms;
+    uchar4 ps = p.pose[e];
+    env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+    uint64_t gid = (uint64_t)(p.first_gid + e);
+    int k = cfg->reset_obs_after_ops;
+    uint32_t ep;
+    if (p.phase != 1) {
+        ep = p.episode[e] + 1;
+        p.episode[e] = ep;
+        p.ep_len[e] = 0;
+        uint32_t err = reset_base(env, p.inv_stride, p.seed, gid, ep);
+        p.err[e] = err;
+        reset_ops(env, 0, p.phase == 0 ? k : NGW_MAX_RESET_OPS, p.seed, gid, ep);
+    } else {
+        ep = p.episode[e];
+        reset_ops(env, k, NGW_MAX_RESET_OPS, p.seed, gid, ep);
+    }
+    p.pose[e] = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing, (unsigned char)env.sel);
+}
+
+__global__ void observe_masked_kernel(const ResetParams p, int32_t* obs, int obs_dim) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n_envs) return;
+    if (p.mask != nullptr && p.mask[e] == 0) return;
+    const ngw_config* cfg = p.cfgs + p.cfg_id[e];
+    EnvRow env;
+    env.cfg = cfg;
+    env.m = p.map + e * p.cells;
+    env.gm = nullptr;
+    env.inv = p.inv + e * p.inv_stride;
+    env.ms = p.ms;
+    uchar4 ps = p.pose[e];
+    env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+    int32_t* row = obs + e * obs_dim;
+    for (int i = 0; i < obs_dim; i++) row[i] = 0;
+    if (cfg->n_beams > 0) lidar_observe(env, reinterpret_cast<const int16_t*>(cfg->beam_lut), row);
+}
+
+__global__ void set_cfg_kernel(const int32_t* src, uint8_t* dst, long long n, int n_cfgs, uint32_t* err) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    int v = src ? src[e] : 0;
+    if (v < 0 || v >= n_cfgs) { v = 0; err[e] |= 0x80000000u; }
+    dst[e] = (uint8_t)v;
+}
+
+__global__ void stats_fold_kernel(double* slots, double* out, int reset_after) {
+    int k = threadIdx.x;
+    if (k >= NGW_STAT_COUNT) return;
+    double s = 0.0;
+    for (int i = 0; i < NGW_STAT_SLOTS; i++) {
+        s += slots[i * NGW_STAT_COUNT + k];
+        if (reset_after) slots[i * NGW_STAT_COUNT + k] = 0.0;
+    }
+    out[k] = s;
+}
+
+}  // namespace ngw
+
+// ====================================================================== host side: handle + C-ABI
+using namespace ngw;
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+#define HOST_STREAMS 3
+
+struct ngw_handle {
+    int device = 0;
+    long long n = 0, np = 0, first_gid = 0;
+    unsigned long long seed = 0;
+    int ms = 0, cells = 0, inv_stride = 0, obs_dim = 0, n_cfgs = 0;
+    int map_bytes = 0, inv_bytes = 0, obs_bytes = 0, lut_bytes = 0, region_bytes = 0, warps = 4;
+    bool use_tma = true, collect_stats = true;
+    ngw_config* d_cfgs = nullptr;
+    std::vector<int16_t*> d_luts;
+    std::vector<ngw_config> h_cfgs;
+    int8_t* map = nullptr; uchar4* pose = nullptr; int32_t* inv = nullptr; uint8_t* cfg_id = nullptr;
+    uint32_t* episode = nullptr; int32_t* ep_len = nullptr; uint32_t* err = nullptr; double* stats = nullptr;
+    long long launches = 0;
+    // host-buffer path
+    cudaStream_t hs[HOST_STREAMS] = {nullptr, nullptr, nullptr};
+    int32_t* h_actions = nullptr; int32_t* h_obs = nullptr; float* h_reward = nullptr; uint8_t* h_done = nullptr;
+    float* h_cost = nullptr; uint8_t* h_result = nullptr;
+};
+
+static int align16(int x) { return (x + 15) & ~15; }
+
+extern "C" {
+
+const char* ngw_last_error(void) { return g_err.c_str(); }
+int ngw_abi_version(void) { return NGW_ABI_VERSION; }
+
+void ngw_destroy(ngw_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto p : h->d_luts) cudaFree(p);
+    cudaFree(h->d_cfgs); cudaFree(h->map); cudaFree(h->pose); cudaFree(h->inv); cudaFree(h->cfg_id);
+    cudaFree(h->episode); cudaFree(h->ep_len); cudaFree(h->err); cudaFree(h->stats);
+    cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_done); cudaFree(h->h_cost);
+    cudaFree(h->h_result);
+    for (int i = 0; i < HOST_STREAMS; i++)
+        if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+    delete h;
+}
+
+int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t n_envs, int32_t map_size,
+               int32_t device, int64_t first_env_gid, uint64_t seed) {
+    if (!out || !cfgs || n_cfgs < 1 || n_cfgs > 255) return fail("ngw_create: need 1..255 configs");
+    if (n_envs < 1) return fail("ngw_create: n_envs must be >= 1");
+    if (map_size < 5 || map_size > NGW_MAX_MAP_SIZE) return fail("ngw_create: map_size out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("ngw_create: this library is built for sm_100a (B200) only");
+    ngw_handle* h = new ngw_handle();
+    h->device = device; h->n = n_envs; h->np = (n_envs + 31) / 32 * 32; h->first_gid = first_env_gid; h->seed = seed;
+    h->ms = map_size; h->cells = map_size * map_size; h->n_cfgs = n_cfgs;
+    h->use_tma = getenv("NGW_NO_TMA") == nullptr;
+    h->collect_stats = getenv("NGW_NO_STATS") == nullptr;
+    int max_lut = 0;
+    for (int i = 0; i < n_cfgs; i++) {
+        const ngw_config& c = cfgs[i];
+        if (c.n_items < 1 || c.n_items > NGW_MAX_ITEMS || c.n_actions < 0 || c.n_actions > NGW_MAX_ACTIONS ||
+            c.n_recipes > NGW_MAX_RECIPES || c.n_place > NGW_MAX_PLACE || c.n_reset_ops > NGW_MAX_RESET_OPS ||
+            c.n_beams < 0 || c.max_range < 0 || c.n_beams * c.max_range > 4096) {
+            delete h;
+            return fail("ngw_create: config " + std::to_string(i) + " out of range");
+        }
+        if (c.n_items > h->inv_stride) h->inv_stride = c.n_items;
+        int d = c.n_beams > 0 ? c.n_lidar_items * c.n_beams + c.n_inv_obs : 0;
+        if (d > h->obs_dim) h->obs_dim = d;
+        if (c.n_beams > 0 && c.beam_lut == nullptr) { delete h; return fail("ngw_create: lidar config without beam_lut"); }
+        int l = 4 * c.n_beams * c.max_range * 2;
+        if (l > max_lut) max_lut = l;
+    }
+    // device copies of the configs, beam LUTs converted to linear int16 offsets for this map size
+    h->h_cfgs.assign(cfgs, cfgs + n_cfgs);
+    for (int i = 0; i < n_cfgs; i++) {
+        ngw_config& c = h->h_cfgs[i];
+        int16_t* d_lut = nullptr;
+        if (c.n_beams > 0) {
+            int n = 4 * c.n_beams * c.max_range;
+            std::vector<int16_t> lin(n);
+            for (int j = 0; j < n; j++) lin[j] = (int16_t)(c.beam_lut[2 * j] * map_size + c.beam_lut[2 * j + 1]);
+            CK(cudaMalloc(&d_lut, n * sizeof(int16_t)));
+            CK(cudaMemcpy(d_lut, lin.data(), n * sizeof(int16_t), cudaMemcpyHostToDevice));
+            h->d_luts.push_back(d_lut);
+        }
+        c.beam_lut = reinterpret_cast<const int8_t*>(d_lut);
+    }
+    CK(cudaMalloc(&h->d_cfgs, sizeof(ngw_config) * n_cfgs));
+    CK(cudaMemcpy(h->d_cfgs, h->h_cfgs.data(), sizeof(ngw_config) * n_cfgs, cudaMemcpyHostToDevice));
+    // state
+    CK(cudaMalloc(&h->map, (size_t)h->np * h->cells));
+    CK(cudaMalloc(&h->pose, (size_t)h->np * 4));
+    CK(cudaMalloc(&h->inv, (size_t)h->np * h->inv_stride * 4));
+    CK(cudaMalloc(&h->cfg_id, (size_t)h->np));
+    CK(cudaMalloc(&h->episode, (size_t)h->np * 4));
+    CK(cudaMalloc(&h->ep_len, (size_t)h->np * 4));
+    CK(cudaMalloc(&h->err, (size_t)h->np * 4));
+    CK(cudaMalloc(&h->stats, sizeof(double) * NGW_STAT_SLOTS * NGW_STAT_COUNT));
+    CK(cudaMemset(h->map, 0, (size_t)h->np * h->cells));
+    CK(cudaMemset(h->pose, 0, (size_t)h->np * 4));
+    CK(cudaMemset(h->inv, 0, (size_t)h->np * h->inv_stride * 4));
+    CK(cudaMemset(h->cfg_id, 0, (size_t)h->np));
+    CK(cudaMemset(h->episode, 0, (size_t)h->np * 4));
+    CK(cudaMemset(h->ep_len, 0, (size_t)h->np * 4));
+    CK(cudaMemset(h->err, 0, (size_t)h->np * 4));
+    CK(cudaMemset(h->stats, 0, sizeof(double) * NGW_STAT_SLOTS * NGW_STAT_COUNT));
+    // shared-memory carve-up per warp
+    h->map_bytes = 32 * h->cells;                       // multiple of 32
+    h->inv_bytes = 128 * h->inv_stride;
+    h->obs_bytes = 128 * (h->obs_dim > 0 ? h->obs_dim : 0);
+    h->lut_bytes = align16(max_lut);
+    h->region_bytes = 16 + h->map_bytes + h->inv_bytes + h->obs_bytes + h->lut_bytes;
+    h->region_bytes = (h->region_bytes + 127) & ~127;
+    int warps = 4;
+    while (warps > 1 && warps * h->region_bytes > 56 * 1024) warps >>= 1;
+    if (warps * h->region_bytes > 227 * 1024) { ngw_destroy(h); return fail("ngw_create: map too large for shared memory"); }
+    h->warps = warps;
+    CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    *out = h;
+    return 0;
+}
+
+int ngw_state(ngw_handle* h, ngw_state_view* o) {
+    if (!h || !o) return fail("ngw_state: null");
+    o->map = h->map; o->pose = reinterpret_cast<uint8_t*>(h->pose); o->inventory = h->inv; o->cfg_id = h->cfg_id;
+    o->episode = h->episode; o->ep_len = h->ep_len; o->error_flags = h->err;
+    o->inv_stride = h->inv_stride; o->obs_dim = h->obs_dim; o->n_envs = h->n; o->n_envs_padded = h->np;
+    o->map_size = h->ms; o->n_configs = h->n_cfgs;
+    return 0;
+}
+
+int ngw_set_env_configs(ngw_handle* h, const int32_t* cfg_id_dev, void* stream) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    int blocks = (int)((h->n + 255) / 256);
+    set_cfg_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cfg_id_dev, h->cfg_id, h->n, h->n_cfgs, h->err);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ngw_load_state(ngw_handle* h, const int8_t* map, const uint8_t* pose, const int32_t* inventory, int64_t first,
+                   int64_t count, void* stream) {
+    if (!h) return fail("null handle");
+    if (first < 0 || count < 0 || first + count > h->n) return fail("ngw_load_state: range outside the batch");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (map) CK(cudaMemcpyAsync(h->map + first * h->cells, map, (size_t)count * h->cells, cudaMemcpyDeviceToDevice, s));
+    if (pose) CK(cudaMemcpyAsync(h->pose + first, pose, (size_t)count * 4, cudaMemcpyDeviceToDevice, s));
+    if (inventory)
+        CK(cudaMemcpyAsync(h->inv + first * h->inv_stride, inventory, (size_t)count * h->inv_stride * 4,
+                           cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemsetAsync(h->ep_len + first, 0, (size_t)count * 4, s));
+    return 0;
+}
+
+static ResetParams reset_params(ngw_handle* h, const uint8_t* mask, int phase) {
+    ResetParams p;
+    p.cfgs = h->d_cfgs; p.map = h->map; p.pose = h->pose; p.inv = h->inv; p.cfg_id = h->cfg_id; p.episode = h->episode;
+    p.ep_len = h->ep_len; p.err = h->err; p.mask = mask; p.n_envs = h->n; p.first_gid = h->first_gid; p.seed = h->seed;
+    p.ms = h->ms; p.cells = h->cells; p.inv_stride = h->inv_stride; p.phase = phase;
+    return p;
+}
+
+int ngw_reset(ngw_handle* h, const uint8_t* mask, int32_t* obs, void* stream) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int blocks = (int)((h->n + 127) / 128);
+    bool split = false;
+    for (auto& c : h->h_cfgs) split |= c.reset_obs_after_ops < c.n_reset_ops;
+    if (obs == nullptr || h->obs_dim == 0 || !split) {
+        reset_kernel<<<blocks, 128, 0, s>>>(reset_params(h, mask, 2));
+        h->launches++;
+        if (obs != nullptr && h->obs_dim > 0) {
+            observe_masked_kernel<<<blocks, 128, 0, s>>>(reset_params(h, mask, 2), obs, h->obs_dim);
+            h->launches++;
+        }
+    } else {
+        reset_kernel<<<blocks, 128, 0, s>>>(reset_params(h, mask, 0));
+        observe_masked_kernel<<<blocks, 128, 0, s>>>(reset_params(h, mask, 0), obs, h->obs_dim);
+        reset_kernel<<<blocks, 128, 0, s>>>(reset_params(h, mask, 1));
+        h->launches += 3;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static StepParams step_params(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done,
+                              float* cost, uint8_t* result, int auto_reset, int max_episode_steps, long long begin,
+                              long long end) {
+    StepParams p;
+    p.cfgs = h->d_cfgs; p.map = h->map; p.pose = h->pose; p.inv = h->inv; p.cfg_id = h->cfg_id; p.episode = h->episode;
+    p.ep_len = h->ep_len; p.err = h->err; p.actions = actions; p.obs = h->obs_dim > 0 ? obs : nullptr; p.reward = reward;
+    p.done = done; p.cost = cost; p.result = result; p.stats = h->collect_stats ? h->stats : nullptr;
+    p.env_begin = begin; p.env_end = end; p.first_gid = h->first_gid; p.seed = h->seed;
+    p.ms = h->ms; p.cells = h->cells; p.inv_stride = h->inv_stride; p.obs_dim = h->obs_dim;
+    p.map_bytes = h->map_bytes; p.inv_bytes = h->inv_bytes; p.obs_bytes = h->obs_bytes; p.lut_bytes = h->lut_bytes;
+    p.region_bytes = h->region_bytes; p.auto_reset = auto_reset; p.max_episode_steps = max_episode_steps;
+    return p;
+}
+
+static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
+    long long tiles = (p.env_end - p.env_begin + 31) / 32;
+    if (tiles <= 0) return 0;
+    int blocks = (int)((tiles + h->warps - 1) / h->warps);
+    size_t smem = (size_t)h->warps * h->region_bytes;
+    if (h->use_tma) step_kernel<true><<<blocks, 32 * h->warps, smem, s>>>(p);
+    else step_kernel<false><<<blocks, 32 * h->warps, smem, s>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ngw_step(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done, float* step_cost,
+             uint8_t* result, int32_t auto_reset, int32_t max_episode_steps, void* stream) {
+    if (!h) return fail("null handle");
+    if (!actions || !reward || !done || !step_cost || !result) return fail("ngw_step: null output/action pointer");
+    if (h->obs_dim > 0 && obs && ((uintptr_t)obs & 15)) return fail("ngw_step: obs must be 16-byte aligned");
+    CK(cudaSetDevice(h->device));
+    return launch_step(h, step_params(h, actions, obs, reward, done, step_cost, result, auto_reset, max_episode_steps,
+                                      0, h->n), (cudaStream_t)stream);
+}
+
+int ngw_observe(ngw_handle* h, int32_t* obs, void* stream) {
+    if (!h) return fail("null handle");
+    if (h->obs_dim == 0) return 0;
+    if (!obs || ((uintptr_t)obs & 15)) return fail("ngw_observe: obs must be a 16-byte aligned device pointer");
+    CK(cudaSetDevice(h->device));
+    return launch_step(h, step_params(h, nullptr, obs, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, h->n),
+                       (cudaStream_t)stream);
+}
+
+static int ensure_host_path(ngw_handle* h) {
+    if (h->hs[0]) return 0;
+    for (int i = 0; i < HOST_STREAMS; i++) CK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
+    CK(cudaMalloc(&h->h_actions, (size_t)h->np * 4));
+    if (h->obs_dim > 0) CK(cudaMalloc(&h->h_obs, (size_t)h->np * h->obs_dim * 4));
+    CK(cudaMalloc(&h->h_reward, (size_t)h->np * 4));
+    CK(cudaMalloc(&h->h_done, (size_t)h->np));
+    CK(cudaMalloc(&h->h_cost, (size_t)h->np * 4));
+    CK(cudaMalloc(&h->h_result, (size_t)h->np));
+    return 0;
+}
+
+int ngw_step_host(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done, float* step_cost,
+                  uint8_t* result, int32_t auto_reset, int32_t max_episode_steps) {
+    if (!h) return fail("null handle");
+    if (!actions || !reward || !done || !step_cost || !result) return fail("ngw_step_host: null pointer");
+    CK(cudaSetDevice(h->device));
+    if (ensure_host_path(h)) return 1;
+    // chunk-pipelined: H2D(actions) -> step -> D2H(outputs) per chunk, chunks rotate over HOST_STREAMS streams
+    long long n = h->n;
+    int chunks = n >= 32768 ? 8 : (n >= 4096 ? 2 : 1);
+    long long per = ((n + chunks - 1) / chunks + 31) / 32 * 32;
+    for (int c = 0; c < chunks; c++) {
+        long long b = c * per, e = b + per < n ? b + per : n;
+        if (b >= n) break;
+        cudaStream_t s = h->hs[c % HOST_STREAMS];
+        size_t cnt = (size_t)(e - b);
+        CK(cudaMemcpyAsync(h->h_actions + b, actions + b, cnt * 4, cudaMemcpyHostToDevice, s));
+        if (launch_step(h, step_params(h, h->h_actions, h->h_obs, h->h_reward, h->h_done, h->h_cost, h->h_result,
+                                       auto_reset, max_episode_steps, b, e), s)) return 1;
+        if (h->obs_dim > 0 && obs)
+            CK(cudaMemcpyAsync(obs + b * h->obs_dim, h->h_obs + b * h->obs_dim, cnt * h->obs_dim * 4,
+                               cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(reward + b, h->h_reward + b, cnt * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(done + b, h->h_done + b, cnt, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(step_cost + b, h->h_cost + b, cnt * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(result + b, h->h_result + b, cnt, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < HOST_STREAMS; i++) CK(cudaStreamSynchronize(h->hs[i]));
+    return 0;
+}
+
+int ngw_stats(ngw_handle* h, double* out8_dev, int32_t reset_after, void* stream) {
+    if (!h || !out8_dev) return fail("ngw_stats: null");
+    CK(cudaSetDevice(h->device));
+    stats_fold_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->stats, out8_dev, reset_after);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int64_t ngw_launch_count(ngw_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

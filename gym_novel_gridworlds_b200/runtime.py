@@ -1,0 +1,333 @@
+"""Runtime: torch tensors for device memory and streams, libngw_b200.so for everything that computes.
+
+`BatchHandle`  — thin owner of one `ngw_handle` (a batch of envs sharing a map size, 1..255 configs).
+`ChainRuntime` — what `reset()` / `step()` of the outermost wrapper talk to: compiles the chain, (re)creates the
+                 handle when a table changed, and shapes results like the reference does (Dict views or the lidar
+                 vector; python scalars when num_envs == 1, tensors otherwise).
+`MixedBatch`   — several wrapper chains in ONE batch / one launch (per-env config ids).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi
+from . import opcodes as oc
+from .capi import ConfigC, StateViewC
+from .compiler import compile_chain
+
+
+class _DeviceArray(object):
+    """Zero-copy torch view of library-owned device memory (numba-style __cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False),
+                                         'version': 2, 'strides': None}
+        self._owner = owner
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchHandle(object):
+    def __init__(self, compiled, n_envs, device=None, seed=0, first_env_gid=0, cfg_id=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("gym_novel_gridworlds_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.lib = capi.load_library()
+        self.compiled = list(compiled)
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self.n = int(n_envs)
+        self.map_size = self.compiled[0].map_size
+        if any(cc.map_size != self.map_size for cc in self.compiled):
+            raise ValueError("all configs of one batch must share map_size")
+        cfgs = (ConfigC * len(self.compiled))()
+        for i, cc in enumerate(self.compiled):
+            C.memmove(C.byref(cfgs, i * C.sizeof(ConfigC)), C.byref(cc.c), C.sizeof(ConfigC))
+        self._h = C.c_void_p()
+        capi.check(self.lib, self.lib.ngw_create(C.byref(self._h), cfgs, len(self.compiled), self.n, self.map_size,
+                                                 self.device.index, int(first_env_gid), int(seed) & (2 ** 64 - 1)))
+        sv = StateViewC()
+        capi.check(self.lib, self.lib.ngw_state(self._h, C.byref(sv)))
+        self.inv_stride, self.obs_dim, self.n_padded = sv.inv_stride, sv.obs_dim, sv.n_envs_padded
+        ms = self.map_size
+
+        def view(ptr, shape, typestr):
+            return torch.as_tensor(_DeviceArray(ptr, shape, typestr, self), device=self.device)
+
+        # LIVE views of the state (what get_observation hands out, pogostick_v1_env.py:222-226)
+        self.map = view(sv.map, (self.n_padded, ms, ms), '|i1')[:self.n]
+        self.pose = view(sv.pose, (self.n_padded, 4), '|u1')[:self.n]
+        self.inventory = view(sv.inventory, (self.n_padded, self.inv_stride), '<i4')[:self.n]
+        self.cfg_id = view(sv.cfg_id, (self.n_padded,), '|u1')[:self.n]
+        self.episode = view(sv.episode, (self.n_padded,), '<i4')[:self.n]
+        self.ep_len = view(sv.ep_len, (self.n_padded,), '<i4')[:self.n]
+        self.error_flags = view(sv.error_flags, (self.n_padded,), '<i4')[:self.n]
+        with torch.cuda.device(self.device):
+            d = max(self.obs_dim, 1)
+            self.obs = torch.zeros((self.n, d), dtype=torch.int32, device=self.device)
+            self.reward = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+            self.done = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
+            self.step_cost = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+            self.result = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
+            self._stats = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self._host = None
+        if cfg_id is not None:
+            self.set_env_configs(cfg_id)
+
+    # ------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self.lib.ngw_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_env_configs(self, cfg_id):
+        t = torch.as_tensor(cfg_id, dtype=torch.int32, device=self.device).contiguous()
+        assert t.numel() == self.n
+        capi.check(self.lib, self.lib.ngw_set_env_configs(self._h, _ptr(t), self._stream()))
+
+    def load_state(self, map, pose, inventory, first=0):
+        """Inject states (the parity harness's entry; also the `env=` restore of pogostick_v1_env.py:89-109)."""
+        m = torch.as_tensor(map, device=self.device).to(torch.int8).contiguous()
+        count = m.shape[0]
+        m = m.reshape(count, -1)
+        p = torch.as_tensor(pose, device=self.device).to(torch.uint8).contiguous()
+        v = torch.as_tensor(inventory, device=self.device).to(torch.int32)
+        if v.shape[1] != self.inv_stride:
+            full = torch.zeros((count, self.inv_stride), dtype=torch.int32, device=self.device)
+            full[:, :v.shape[1]] = v
+            v = full
+        v = v.contiguous()
+        assert m.shape[1] == self.map_size ** 2 and p.shape == (count, 4)
+        capi.check(self.lib, self.lib.ngw_load_state(self._h, _ptr(m), _ptr(p), _ptr(v), first, count, self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()      # m/p/v may be temporaries
+
+    def export_state(self):
+        return self.map.clone(), self.pose.clone(), self.inventory.clone()
+
+    def reset(self, mask=None, want_obs=True):
+        mk = None
+        if mask is not None:
+            mk = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        obs = self.obs if (want_obs and self.obs_dim > 0) else None
+        capi.check(self.lib, self.lib.ngw_reset(self._h, _ptr(mk), _ptr(obs), self._stream()))
+        if mk is not None:
+            torch.cuda.current_stream(self.device).synchronize()
+        return obs
+
+    def step(self, actions, auto_reset=False, max_episode_steps=0):
+        """Device path: `actions` is an int32 CUDA tensor [n]; outputs are the handle's reused tensors."""
+        if actions.dtype != torch.int32 or not actions.is_cuda or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+        capi.check(self.lib, self.lib.ngw_step(self._h, _ptr(actions), _ptr(self.obs) if self.obs_dim else None,
+                                               _ptr(self.reward), _ptr(self.done), _ptr(self.step_cost),
+                                               _ptr(self.result), int(bool(auto_reset)), int(max_episode_steps),
+                                               self._stream()))
+        return self.obs, self.reward, self.done, self.step_cost, self.result
+
+    def observe(self):
+        if self.obs_dim:
+            capi.check(self.lib, self.lib.ngw_observe(self._h, _ptr(self.obs), self._stream()))
+        return self.obs
+
+    def _host_buffers(self):
+        if self._host is None:
+            d = max(self.obs_dim, 1)
+            self._host = {
+                'actions': torch.zeros(self.n, dtype=torch.int32).pin_memory(),
+                'obs': torch.zeros((self.n, d), dtype=torch.int32).pin_memory(),
+                'reward': torch.zeros(self.n, dtype=torch.float32).pin_memory(),
+                'done': torch.zeros(self.n, dtype=torch.uint8).pin_memory(),
+                'step_cost': torch.zeros(self.n, dtype=torch.float32).pin_memory(),
+                'result': torch.zeros(self.n, dtype=torch.uint8).pin_memory(),
+            }
+        return self._host
+
+    def step_host(self, actions, auto_reset=False, max_episode_steps=0):
+        """Host path: numpy in, numpy views of pinned buffers out; H2D + step + D2H inside libngw_b200."""
+        hb = self._host_buffers()
+        hb['actions'].numpy()[:] = np.asarray(actions, dtype=np.int32).reshape(self.n)
+        capi.check(self.lib, self.lib.ngw_step_host(
+            self._h, _ptr(hb['actions']), _ptr(hb['obs']) if self.obs_dim else None, _ptr(hb['reward']),
+            _ptr(hb['done']), _ptr(hb['step_cost']), _ptr(hb['result']), int(bool(auto_reset)),
+            int(max_episode_steps)))
+        return (hb['obs'].numpy(), hb['reward'].numpy(), hb['done'].numpy(), hb['step_cost'].numpy(),
+                hb['result'].numpy())
+
+    def stats(self, reset=False):
+        """float64[8] on device, order = opcodes.STAT_NAMES; all-reduce it with NCCL for the job total."""
+        capi.check(self.lib, self.lib.ngw_stats(self._h, _ptr(self._stats), int(bool(reset)), self._stream()))
+        return self._stats
+
+    def launch_count(self):
+        return int(self.lib.ngw_launch_count(self._h))
+
+
+class LazyInfo(object):
+    """info of a batched step: tensors, converted to the reference's dict only on demand."""
+
+    def __init__(self, result, step_cost):
+        self.result, self.step_cost = result, step_cost
+
+    def __getitem__(self, key):
+        if key == 'result':
+            return self.result
+        if key == 'step_cost':
+            return self.step_cost
+        if key == 'message':
+            return None          # host-side string formatting is outside the accelerated path
+        raise KeyError(key)
+
+    def keys(self):
+        return ['result', 'step_cost', 'message']
+
+
+class ChainRuntime(object):
+    """Drives one wrapper chain (one config) through a BatchHandle with the reference's return conventions."""
+
+    def __init__(self, base):
+        self.base = base
+        self.handle = None
+        self.compiled = None
+        self._fingerprint = None
+        self.auto_reset = False
+        self.max_episode_steps = 0
+
+    # ------------------------------------------------------------------
+    def _ensure(self):
+        cc = compile_chain(self.base._top)
+        fp = cc.fingerprint()
+        if self.handle is None or fp != self._fingerprint:
+            if self.handle is not None:
+                self.handle.close()
+            self.compiled, self._fingerprint = cc, fp
+            self.handle = BatchHandle([cc], self.base.num_envs, self.base.device, self.base.rng_seed,
+                                      self.base.first_env_gid)
+        return self.handle
+
+    def close(self):
+        if self.handle is not None:
+            self.handle.close()
+            self.handle = None
+
+    @property
+    def single(self):
+        return self.base.num_envs == 1
+
+    def dict_observation(self):
+        h = self.handle
+        names = self.compiled.item_names
+        if self.single:
+            inv = h.inventory[0].cpu().numpy()
+            pose = h.pose[0].cpu().numpy()
+            return {'map': h.map[0].cpu().numpy().astype(np.int64),
+                    'agent_location': (int(pose[0]), int(pose[1])),
+                    'agent_facing_id': int(pose[2]),
+                    'inventory_items_quantity': {n: int(inv[i]) for i, n in enumerate(names) if n in self.base.items}}
+        return {'map': h.map, 'agent_location': h.pose[:, 0:2], 'agent_facing_id': h.pose[:, 2],
+                'inventory_items_quantity': {n: h.inventory[:, i] for i, n in enumerate(names) if n in self.base.items}}
+
+    def lidar_observation(self):
+        obs = self.handle.observe()[:, :self.compiled.obs_dim]
+        return obs[0].cpu().numpy().astype(np.int64) if self.single else obs
+
+    def _sync_single(self):
+        """num_envs == 1: refresh the attribute mirrors reference scripts read (env.map, env.agent_location, ...)."""
+        b, h = self.base, self.handle
+        pose = h.pose[0].cpu().numpy()
+        inv = h.inventory[0].cpu().numpy()
+        names = self.compiled.item_names
+        b.map = h.map[0].cpu().numpy().astype(np.int64)
+        b.agent_location = (int(pose[0]), int(pose[1]))
+        b.agent_facing_id = int(pose[2])
+        b.agent_facing_str = [k for k, v in b.direction_id.items() if v == b.agent_facing_id][0]
+        b.inventory_items_quantity = {n: int(inv[i]) for i, n in enumerate(names) if n in b.items}
+        b.selected_item = names[int(pose[3])] if pose[3] else ''
+        dr, dc = {0: (-1, 0), 1: (1, 0), 2: (0, -1), 3: (0, 1)}[b.agent_facing_id]
+        fr, fc = b.agent_location[0] + dr, b.agent_location[1] + dc
+        b.block_in_front_location = (fr, fc)
+        b.block_in_front_id = int(b.map[fr][fc])
+        b.block_in_front_str = names[b.block_in_front_id]
+
+    def reset(self, **kwargs):
+        h = self._ensure()
+        cc = self.compiled
+        obs = h.reset(want_obs=(cc.reset_returns == 'lidar'))
+        if self.single:
+            torch.cuda.current_stream(h.device).synchronize()
+            if int(h.error_flags[0].item()) & oc.ERR_PLACEMENT:
+                raise AssertionError("Cannot place items, increase map size!")      # pogostick_v1_env.py:167
+            self._sync_single()
+            self.base.step_count = 0
+        else:
+            b = self.base
+            b.map, b.agent_location, b.agent_facing_id = h.map, h.pose[:, 0:2], h.pose[:, 2]
+            b.inventory_items_quantity = {n: h.inventory[:, i] for i, n in enumerate(cc.item_names) if n in b.items}
+        if cc.reset_returns == 'lidar':
+            o = obs[:, :cc.obs_dim]
+            return o[0].cpu().numpy().astype(np.int64) if self.single else o
+        return self.dict_observation()
+
+    def step(self, action):
+        if self.handle is None:
+            self._ensure()
+        h, cc = self.handle, self.compiled
+        if self.single:
+            a = torch.tensor([int(action)], dtype=torch.int32, device=h.device)
+            obs, reward, done, cost, result = h.step(a)
+            torch.cuda.current_stream(h.device).synchronize()
+            flags = int(h.error_flags[0].item())
+            if flags & oc.ERR_INVALID_ACTION:
+                h.error_flags[0] = flags & ~oc.ERR_INVALID_ACTION
+                why = cc.invalid_reasons.get(int(action), "Action ID " + str(action) + " is not valid")
+                raise (ValueError if why.startswith('ValueError') else AssertionError)(why)
+            self._sync_single()
+            b = self.base
+            b.step_count += 1
+            b.last_reward, b.last_done = int(reward[0].item()), bool(done[0].item())
+            b.last_step_cost = float(cost[0].item())
+            info = {'result': bool(result[0].item()), 'step_cost': b.last_step_cost, 'message': ''}
+            o = (obs[0, :cc.obs_dim].cpu().numpy().astype(np.int64) if cc.obs_dim else self.dict_observation())
+            return o, b.last_reward, b.last_done, info
+        if isinstance(action, torch.Tensor) and action.is_cuda:
+            obs, reward, done, cost, result = h.step(action, self.auto_reset, self.max_episode_steps)
+            o = obs[:, :cc.obs_dim] if cc.obs_dim else self.dict_observation()
+            return o, reward, done.view(torch.bool), LazyInfo(result.view(torch.bool), cost)
+        obs, reward, done, cost, result = h.step_host(action, self.auto_reset, self.max_episode_steps)
+        o = obs[:, :cc.obs_dim] if cc.obs_dim else self.dict_observation()
+        return o, reward, done.view(np.bool_), LazyInfo(result.view(np.bool_), cost)
+
+
+class MixedBatch(object):
+    """Several wrapper chains (configs) in one batch: env i runs config cfg_id[i] — one launch per step."""
+
+    def __init__(self, tops, num_envs, cfg_id=None, device=None, seed=0, first_env_gid=0, assignment='interleaved'):
+        self.compiled = [compile_chain(t) for t in tops]
+        n_cfg = len(self.compiled)
+        if cfg_id is None:
+            idx = np.arange(num_envs, dtype=np.int64)
+            gid = idx + int(first_env_gid)
+            cfg_id = (gid % n_cfg) if assignment == 'interleaved' else np.minimum(idx * n_cfg // num_envs, n_cfg - 1)
+        self.cfg_id_host = np.asarray(cfg_id, dtype=np.int32)
+        self.handle = BatchHandle(self.compiled, num_envs, device, seed, first_env_gid, cfg_id=self.cfg_id_host)
+        self.n_actions = np.array([cc.c.n_actions for cc in self.compiled], dtype=np.int32)
+
+    def reset(self, mask=None):
+        return self.handle.reset(mask)
+
+    def step(self, actions, auto_reset=False, max_episode_steps=0):
+        return self.handle.step(actions, auto_reset, max_episode_steps)
+
+    def close(self):
+        self.handle.close()

@@ -400,17 +400,34 @@ void ngo_beam_offset(int facing, int n_beams, int b, int k, int* d_row, int* d_c
     *d_col = (int)rint((double)k * y);
 }
 
-/* obs[0 .. L*B + n_inv_obs) — observation_wrappers.py:32-80 */
+/* obs[0 .. L*B + n_inv_obs) — observation_wrappers.py:32-80.  The reference evaluates cos/sin once per beam per
+ * call; the per-beam ratios depend only on (facing, n_beams), so they are cached per thread. */
 void ngo_observe(const ngw_config* cfg, int ms, const int8_t* map, const uint8_t* pose, const int32_t* inv,
                  int32_t* obs) {
+    static __thread int cached_beams = -1;
+    static __thread double ratio[4][64][2];
     int L = cfg->n_lidar_items, B = cfg->n_beams;
     int r = pose[0], c = pose[1];
+    if (B != cached_beams && B <= 64) {
+        static const double PI = 3.141592653589793;
+        for (int f = 0; f < 4; f++) {
+            double theta = (f == NGW_NORTH) ? PI : (f == NGW_SOUTH) ? 0.0 : (f == NGW_WEST) ? 3 * PI / 2 : PI / 2;
+            double start = theta - PI, step = ((theta + PI) - start) / (double)B;
+            for (int b = 0; b < B; b++) {
+                double angle = start + (double)b * step;
+                ratio[f][b][0] = rint(cos(angle) * 100.0) / 100.0;      /* np.round(np.cos(angle), 2) */
+                ratio[f][b][1] = rint(sin(angle) * 100.0) / 100.0;
+            }
+        }
+        cached_beams = B;
+    }
     for (int i = 0; i < L * B; i++) obs[i] = 0;
     for (int b = 0; b < B; b++) {
+        double x, y;
+        if (B <= 64) { x = ratio[pose[2]][b][0]; y = ratio[pose[2]][b][1]; }
+        else { int dr, dc; ngo_beam_offset(pose[2], B, b, 1, &dr, &dc); x = dr; y = dc; }
         for (int k = 1; k <= cfg->max_range; k++) {
-            int dr, dc;
-            ngo_beam_offset(pose[2], B, b, k, &dr, &dc);
-            int rr = r + dr, cc = c + dc;
+            int rr = r + (int)rint((double)k * x), cc = c + (int)rint((double)k * y);   /* np.round(k * ratio) */
             if (rr < 0 || rr >= ms || cc < 0 || cc >= ms) break;      /* unreachable on a walled map */
             int id = map[rr * ms + cc];
             if (id != 0) {
@@ -547,6 +564,46 @@ int ngo_step_batch(const ngw_config* cfgs, const uint8_t* cfg_id, int ms, int64_
         jobs[t] = j;
         if (n_threads == 1) batch_worker(&jobs[t]);
         else pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
+    }
+    if (n_threads > 1)
+        for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+    free(jobs); free(th);
+    return 0;
+}
+
+/* n_steps consecutive steps of every env, no lock-step barrier between threads (envs are independent): thread t
+ * owns a contiguous slice and runs it through all steps; step s uses actions[(s % n_action_sets)][env].
+ * This is the CPU-baseline driver: thread start-up is paid once per call, not once per step. */
+typedef struct { job_t j; const int32_t* action_sets; int n_action_sets; int n_steps; int64_t n; } roll_t;
+
+static void* rollout_worker(void* arg) {
+    roll_t* r = (roll_t*)arg;
+    for (int s = 0; s < r->n_steps; s++) {
+        r->j.actions = r->action_sets + (int64_t)(s % r->n_action_sets) * r->n;
+        batch_worker(&r->j);
+    }
+    return NULL;
+}
+
+int ngo_rollout(const ngw_config* cfgs, const uint8_t* cfg_id, int ms, int64_t n, int8_t* map, uint8_t* pose,
+                int32_t* inv, int inv_stride, const int32_t* action_sets, int n_action_sets, int n_steps, int32_t* obs,
+                int obs_stride, float* reward, uint8_t* done, float* cost, uint8_t* result, uint32_t* err,
+                int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 1024) n_threads = 1024;
+    roll_t* jobs = (roll_t*)malloc(sizeof(roll_t) * (size_t)n_threads);
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    int64_t per = (n + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; t++) {
+        int64_t b = t * per, e = b + per;
+        if (b > n) b = n;
+        if (e > n) e = n;
+        job_t j = {cfgs, cfg_id, ms, b, e, map, pose, inv, inv_stride, NULL, obs, obs_stride,
+                   reward, done, cost, result, err};
+        jobs[t].j = j; jobs[t].action_sets = action_sets; jobs[t].n_action_sets = n_action_sets;
+        jobs[t].n_steps = n_steps; jobs[t].n = n;
+        if (n_threads == 1) rollout_worker(&jobs[t]);
+        else pthread_create(&th[t], NULL, rollout_worker, &jobs[t]);
     }
     if (n_threads > 1)
         for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);

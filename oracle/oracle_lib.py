@@ -45,6 +45,9 @@ def lib():
         L.ngo_step_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_int]
+        L.ngo_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.ngo_reset_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
@@ -134,3 +137,17 @@ class OracleBatch(object):
                              self.inv_stride, _p(actions), _p(obs), self.obs_dim, _p(reward), _p(done), _p(cost),
                              _p(result), _p(self.err), n_threads)
         return obs, reward, done, cost, result
+
+    def rollout(self, action_sets, n_steps, n_threads=1):
+        """n_steps steps of every env without a per-step barrier (CPU-baseline driver); step s uses
+        action_sets[s % len(action_sets)].  Returns the outputs of the last step."""
+        acts = np.ascontiguousarray(action_sets, np.int32).reshape(-1, self.n)
+        obs = np.zeros((self.n, max(self.obs_dim, 1)), np.int32)
+        reward = np.zeros(self.n, np.float32)
+        done = np.zeros(self.n, np.uint8)
+        cost = np.zeros(self.n, np.float32)
+        result = np.zeros(self.n, np.uint8)
+        lib().ngo_rollout(self.cfgs, _p(self.cfg_id), self.ms, self.n, _p(self.map), _p(self.pose), _p(self.inv),
+                          self.inv_stride, _p(acts), acts.shape[0], int(n_steps), _p(obs) if self.obs_dim else None,
+                          self.obs_dim, _p(reward), _p(done), _p(cost), _p(result), _p(self.err), n_threads)
+        return obs[:, :self.obs_dim], reward, done, cost, result

@@ -1,0 +1,181 @@
+"""GPU parity (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI (libngw_b200.so):
+   1. every golden trace of the unmodified reference, replayed on the GPU, compared at every step;
+   2. >= 10^6 env-steps against the C oracle from reference-exact (legacy-stream) reset states;
+   3. layout / API edge cases: partial tiles, host-buffer path, plain-copy kernel, invalid actions, N == 1."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util
+import scenarios
+from gym_novel_gridworlds_b200.compiler import compile_chain
+from gym_novel_gridworlds_b200.runtime import BatchHandle, MixedBatch
+from oracle.oracle_lib import OracleBatch
+
+pytestmark = pytest.mark.gpu
+NAMES = golden_util.names()
+
+
+def _compiled(desc):
+    return compile_chain(scenarios.build_chain(scenarios.b200_namespace(), desc))
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_gpu_replays_reference_golden_trace(name):
+    g = golden_util.get(name)
+    cc = _compiled(g['meta'])
+    E, T = g['actions'].shape
+    n_items = g['init_inv'].shape[1]
+    h = BatchHandle([cc], E, seed=1)
+    h.load_state(g['init_map'], g['init_pose'], g['init_inv'])
+    has_obs = g['obs'].shape[2] > 0
+    for t in range(T):
+        obs, reward, done, cost, result = h.step(torch.from_numpy(g['actions'][:, t].copy()).cuda())
+        where = "%s step %d" % (name, t)
+        assert np.array_equal(reward.cpu().numpy(), g['reward'][:, t].astype(np.float32)), where
+        assert np.array_equal(done.cpu().numpy(), g['done'][:, t]), where
+        assert np.array_equal(result.cpu().numpy(), g['result'][:, t]), where
+        np.testing.assert_allclose(cost.cpu().numpy(), g['cost'][:, t], rtol=1e-6, err_msg=where)
+        assert np.array_equal(h.map.cpu().numpy().reshape(E, -1), g['map'][:, t]), where
+        assert np.array_equal(h.pose.cpu().numpy(), g['pose'][:, t]), where
+        assert np.array_equal(h.inventory.cpu().numpy()[:, :n_items], g['inv'][:, t]), where
+        if has_obs:
+            assert np.array_equal(obs.cpu().numpy()[:, :cc.obs_dim], g['obs'][:, t].astype(np.int32)), where
+    assert int(h.error_flags.abs().sum().item()) == 0
+    h.close()
+
+
+def _parity_vs_oracle(compiled, n, steps, seed0, cfg_id=None, rng_seed=0):
+    ob = OracleBatch(compiled, n, cfg_id=cfg_id)
+    err = ob.reset_legacy(seed0)
+    assert not err.any()
+    h = BatchHandle(compiled, n, seed=3, cfg_id=None if cfg_id is None else cfg_id.astype(np.int32))
+    h.load_state(ob.map, ob.pose, ob.inv)
+    n_act = np.array([cc.c.n_actions for cc in compiled])[ob.cfg_id.astype(np.int64)]
+    rng = np.random.RandomState(rng_seed)
+    obs0 = h.observe().cpu().numpy()
+    assert np.array_equal(obs0[:, :ob.obs_dim], ob.observe())
+    for t in range(steps):
+        actions = (rng.randint(0, 1 << 30, size=n) % n_act).astype(np.int32)
+        o_obs, o_rew, o_done, o_cost, o_res = ob.step(actions, n_threads=8)
+        obs, rew, done, cost, res = h.step(torch.from_numpy(actions).cuda())
+        where = "step %d" % t
+        assert np.array_equal(rew.cpu().numpy(), o_rew), where
+        assert np.array_equal(done.cpu().numpy(), o_done), where
+        assert np.array_equal(res.cpu().numpy(), o_res), where
+        np.testing.assert_allclose(cost.cpu().numpy(), o_cost, rtol=1e-6, err_msg=where)
+        if ob.obs_dim:
+            assert np.array_equal(obs.cpu().numpy()[:, :ob.obs_dim], o_obs), where
+        if t % 16 == 15 or t == steps - 1:
+            assert np.array_equal(h.map.cpu().numpy().reshape(n, -1), ob.map), where
+            assert np.array_equal(h.pose.cpu().numpy(), ob.pose), where
+            assert np.array_equal(h.inventory.cpu().numpy(), ob.inv), where
+    h.close()
+    return n * steps
+
+
+def test_million_steps_c2_vs_oracle():
+    """BASELINE config C2 (Pogostick-v1 + LimitActions + LidarInFront): 4096 reference-exact resets x 256 steps."""
+    cc = _compiled({'env': scenarios.POGO, 'map_size': 10, 'chain': [['limit', scenarios.C2_SET], ['lidar', 8]]})
+    assert _parity_vs_oracle([cc], 4096, 256, seed0=1000) >= 10 ** 6
+
+
+def test_c3_bow_axe_fence_vs_oracle():
+    cc = _compiled(golden_util.get('bow_C3_axe_medium_fence_hard')['meta'])
+    _parity_vs_oracle([cc], 2048, 128, seed0=5000)
+
+
+def test_c4_mixed_novelties_one_launch_vs_oracle():
+    """addchop / addjump / additem(medium) / remapaction(hard), env i -> config i mod 4, one launch per step."""
+    base = [['limit', scenarios.C2_SET + ['Chop', 'Jump']], ['lidar', 8]]
+    descs = [{'env': scenarios.POGO, 'map_size': 10, 'chain': base + [extra]} for extra in (
+        ['novelty', 'addchop', 'hard', '', ''], ['novelty', 'addjump', 'hard', '', ''],
+        ['novelty', 'additem', 'medium', 'spring', ''], ['novelty', 'remapaction', 'hard', '', ''])]
+    # Chop/Jump are only valid where the novelty exists: use per-config limited sets
+    descs[0]['chain'][0] = ['limit', scenarios.C2_SET + ['Chop']]
+    descs[1]['chain'][0] = ['limit', scenarios.C2_SET + ['Jump']]
+    descs[2]['chain'][0] = ['limit', scenarios.C2_SET]
+    descs[3]['chain'][0] = ['limit', scenarios.C2_SET]
+    compiled = [_compiled(d) for d in descs]
+    n = 4096 + 7                                  # exercises the partial last tile and heterogeneous warps
+    cfg_id = (np.arange(n) % 4).astype(np.uint8)
+    _parity_vs_oracle(compiled, n, 96, seed0=9000, cfg_id=cfg_id)
+
+
+def test_c5_map40_additem_hard_vs_oracle():
+    cc = _compiled(golden_util.get('pogo_ms40_additem_hard')['meta'])
+    _parity_vs_oracle([cc], 256, 64, seed0=100)
+
+
+def test_plain_copy_kernel_matches_tma_kernel():
+    cc = _compiled({'env': scenarios.POGO, 'map_size': 10, 'chain': [['limit', scenarios.C2_SET], ['lidar', 8]]})
+    os.environ['NGW_NO_TMA'] = '1'
+    try:
+        _parity_vs_oracle([cc], 1000, 48, seed0=77)
+    finally:
+        del os.environ['NGW_NO_TMA']
+
+
+def test_host_buffer_path_matches_device_path():
+    cc = _compiled({'env': scenarios.POGO, 'map_size': 10, 'chain': [['limit', scenarios.C2_SET], ['lidar', 8]]})
+    n = 40000 + 13
+    ob = OracleBatch([cc], n)
+    ob.reset_legacy(42)
+    h1, h2 = BatchHandle([cc], n), BatchHandle([cc], n)
+    for h in (h1, h2):
+        h.load_state(ob.map, ob.pose, ob.inv)
+    rng = np.random.RandomState(1)
+    for t in range(12):
+        a = rng.randint(0, cc.c.n_actions, size=n).astype(np.int32)
+        d = [x.cpu().numpy() for x in h1.step(torch.from_numpy(a).cuda())]
+        hb = h2.step_host(a)
+        for x, y in zip(d, hb):
+            assert np.array_equal(x, y)
+    assert np.array_equal(h1.map.cpu().numpy(), h2.map.cpu().numpy())
+    assert np.array_equal(h1.inventory.cpu().numpy(), h2.inventory.cpu().numpy())
+
+
+def test_invalid_action_sets_flag_and_leaves_state():
+    cc = _compiled({'env': scenarios.POGO, 'map_size': 10, 'chain': [['limit', scenarios.C2_SET], ['lidar', 8]]})
+    h = BatchHandle([cc], 64)
+    h.reset()
+    before = [x.clone() for x in (h.map, h.pose, h.inventory)]
+    a = torch.full((64,), 10, dtype=torch.int32, device='cuda')      # limited ids are 0..9 (wrappers.py:76)
+    a[::2] = -3
+    h.step(a)
+    assert (h.error_flags.cpu().numpy() & 1).all()
+    for x, y in zip(before, (h.map, h.pose, h.inventory)):
+        assert torch.equal(x, y)
+    assert h.stats().cpu().numpy()[6] == 64
+
+
+def test_single_env_api_reproduces_survey_kat():
+    """SURVEY §8c seed-0 known-answer test through the drop-in gym API with num_envs == 1."""
+    import gym_novel_gridworlds_b200 as gym
+    env = gym.make('NovelGridworld-Pogostick-v1')
+    env = gym.LimitActions(env, set(scenarios.C2_SET))
+    env = gym.LidarInFront(env, num_beams=8)
+    env.reset()
+    rt = env.unwrapped._runtime
+    ob = OracleBatch([rt.compiled], 1)
+    ob.reset_one(0, 0)                       # np.random.seed(0) reset of the reference
+    rt.handle.load_state(ob.map, ob.pose, ob.inv)
+    obs = env.observation()
+    nz = np.nonzero(obs)[0]
+    assert list(nz) == [6, 13, 18, 25, 28, 41, 48, 55] and list(obs[nz]) == [2, 3, 4, 4, 3, 3, 2, 3]
+    rewards, costs, results = [], [], []
+    for a in [6, 6, 9, 6, 0, 7, 6, 0, 1, 1, 3, 8, 5]:
+        obs, r, d, info = env.step(a)
+        rewards.append(r); costs.append(info['step_cost']); results.append(info['result'])
+    assert rewards == [-1, -1, -1, -1, -1, -1, -1, 10, 10, -1, 10, -1, -1]
+    np.testing.assert_allclose(costs, [27.906975, 27.906975, 24, 27.906975, 3600, 24, 27.906975, 3600, 1200, 0, 2400,
+                                       300, 120], rtol=1e-6)
+    assert results == [True, True, True, True, False, True, True, True, True, False, True, False, False]
+    assert env.agent_location == (3, 5) and env.agent_facing_str == 'EAST'
+    assert [env.inventory_items_quantity[k] for k in sorted(env.inventory_items_quantity)] == [0, 0, 2, 0, 0, 4, 0, 0, 0]
+    nz = np.nonzero(obs)[0]
+    assert list(nz) == [6, 11, 18, 27, 34, 41, 42, 55, 57, 60] and list(obs[nz]) == [5, 4, 2, 5, 4, 4, 1, 4, 2, 4]
+    with pytest.raises(AssertionError):
+        env.step(10)

@@ -1,0 +1,153 @@
+"""GPU reset / auto-reset (Philox map generator): same invariants and marginals as the reference's reset."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util
+import scenarios
+from gym_novel_gridworlds_b200.compiler import compile_chain
+from gym_novel_gridworlds_b200.runtime import BatchHandle
+from oracle.oracle_lib import OracleBatch
+
+pytestmark = pytest.mark.gpu
+
+
+def _compiled(desc):
+    return compile_chain(scenarios.build_chain(scenarios.b200_namespace(), desc))
+
+
+C2 = {'env': scenarios.POGO, 'map_size': 10, 'chain': [['limit', scenarios.C2_SET], ['lidar', 8]]}
+
+
+def _check_base_invariants(cc, m, pose, inv, ms):
+    n = m.shape[0]
+    m = m.reshape(n, ms, ms)
+    wall = cc.c.id_wall
+    border = np.ones((ms, ms), bool)
+    border[1:-1, 1:-1] = False
+    assert (m[:, border] == wall).all()                               # border = wall
+    inner_ring = np.zeros((ms, ms), bool)
+    inner_ring[1:-1, 1:-1] = True
+    inner_ring[2:-2, 2:-2] = False
+    assert (m[:, inner_ring] == 0).all()                              # items only in [2, ms-3]^2
+    assert ((pose[:, 0] >= 2) & (pose[:, 0] <= ms - 3) & (pose[:, 1] >= 2) & (pose[:, 1] <= ms - 3)).all()
+    assert (pose[:, 2] < 4).all() and (pose[:, 3] == 0).all()
+    assert (m[np.arange(n), pose[:, 0], pose[:, 1]] == 0).all()       # agent cell is air
+    for i in range(cc.c.n_place):                                     # exact item counts
+        assert ((m == cc.c.place_item[i]).sum(axis=(1, 2)) == cc.c.place_qty[i]).all()
+    items = (m != 0) & ~border[None]
+    adj = (items[:, 1:, :] & items[:, :-1, :]).any() or (items[:, :, 1:] & items[:, :, :-1]).any()
+    assert not adj                                                    # no two items 4-adjacent
+    assert (inv == 0).all()
+
+
+def test_reset_invariants_and_marginals_match_reference_generator():
+    cc = _compiled(C2)
+    n = 32768
+    h = BatchHandle([cc], n, seed=11)
+    obs = h.reset()
+    m, pose, inv = [x.cpu().numpy() for x in h.export_state()]
+    assert int(h.error_flags.abs().sum().item()) == 0
+    _check_base_invariants(cc, m, pose, inv, 10)
+    # reset observation == observation of the reset state
+    ob = OracleBatch([cc], n)
+    ob.map[:] = m.reshape(n, -1); ob.pose[:] = pose; ob.inv[:] = inv
+    assert np.array_equal(obs.cpu().numpy()[:, :cc.obs_dim], ob.observe())
+    # marginals vs the reference generator (legacy stream, via the oracle): agent cell, facing, tree_log cells
+    ref = OracleBatch([cc], n)
+    ref.reset_legacy(123456)
+
+    def chi2(a, b, bins):
+        ca = np.bincount(a, minlength=bins).astype(float)
+        cb = np.bincount(b, minlength=bins).astype(float)
+        keep = (ca + cb) > 0
+        return (((ca - cb) ** 2) / (ca + cb))[keep].sum(), keep.sum() - 1
+
+    for a, b, bins in ((pose[:, 0] * 10 + pose[:, 1], ref.pose[:, 0].astype(int) * 10 + ref.pose[:, 1], 100),
+                       (pose[:, 2], ref.pose[:, 2], 4)):
+        stat, dof = chi2(a.astype(int), b.astype(int), bins)
+        assert stat < dof + 6 * np.sqrt(2 * dof) + 10, (stat, dof)
+    log = cc.c.id_tree_log
+    ca = (m.reshape(n, -1) == log).sum(0).astype(float)
+    cb = (ref.map == log).sum(0).astype(float)
+    keep = (ca + cb) > 0
+    stat = (((ca - cb) ** 2) / (ca + cb))[keep].sum()
+    dof = keep.sum() - 1
+    assert stat < dof + 6 * np.sqrt(2 * dof) + 10, (stat, dof)
+    # different envs / episodes differ; same seed reproduces
+    h2 = BatchHandle([cc], n, seed=11)
+    h2.reset()
+    assert torch.equal(h2.map, h.map) and torch.equal(h2.pose, h.pose)
+    h2.reset()
+    assert not torch.equal(h2.map, h.map)
+
+
+def test_sharded_reset_is_independent_of_sharding():
+    cc = _compiled(C2)
+    whole = BatchHandle([cc], 4096, seed=5)
+    whole.reset()
+    half = BatchHandle([cc], 2048, seed=5, first_env_gid=2048)
+    half.reset()
+    assert torch.equal(whole.map[2048:], half.map) and torch.equal(whole.pose[2048:], half.pose)
+
+
+@pytest.mark.parametrize('name', ['bow_C3_axe_medium_fence_hard', 'pogo_A_additem_hard', 'pogo_A_firewall_hard',
+                                  'pogo_A_axetobreak_hard_iron', 'pogo_A_replaceitem_medium_log',
+                                  'pogo_ms40_additem_hard', 'pogo_A_axe_easy_wooden', 'pogo_A_crate_hard'])
+def test_novelty_reset_statistics_match_reference_generator(name):
+    cc = _compiled(golden_util.get(name)['meta'])
+    n = 2048 if cc.map_size > 20 else 8192
+    h = BatchHandle([cc], n, seed=2)
+    h.reset()
+    m, pose, inv = [x.cpu().numpy() for x in h.export_state()]
+    ref = OracleBatch([cc], n)
+    err = ref.reset_legacy(999)
+    ok = err == 0
+    flags = h.error_flags.cpu().numpy()
+    assert abs((flags != 0).mean() - (~ok).mean()) < 0.01
+    m = m.reshape(n, -1)
+    assert np.array_equal(np.unique(inv, axis=0), np.unique(ref.inv[ok], axis=0))     # inventory patches
+    for item in range(1, cc.n_items):                                                  # per-item cell-count distribution
+        a, b = (m[flags == 0] == item).sum(1), (ref.map[ok] == item).sum(1)
+        assert abs(a.mean() - b.mean()) <= 0.05 * max(1.0, b.mean()) + 4 * (b.std() + 0.01) / np.sqrt(n) * 3, (item, a.mean(), b.mean())
+        assert a.min() >= b.min() - 2 and a.max() <= b.max() + 2, (item, a.min(), a.max(), b.min(), b.max())
+    assert (m[np.arange(n), pose[:, 0].astype(int) * cc.map_size + pose[:, 1]] == 0).all()
+
+
+def test_auto_reset_and_truncation():
+    cc = _compiled(C2)
+    n = 4096
+    h = BatchHandle([cc], n, seed=9)
+    h.reset()
+    rng = np.random.RandomState(0)
+    total_done = 0
+    for t in range(40):
+        a = torch.from_numpy(rng.randint(0, 10, size=n).astype(np.int32)).cuda()
+        obs, rew, done, cost, res = h.step(a, auto_reset=True, max_episode_steps=16)
+        d = done.cpu().numpy()
+        total_done += d.sum()
+        if (t + 1) % 16 == 0:
+            assert d.all()                                            # every env truncated on the same step
+            m, pose, inv = [x.cpu().numpy() for x in h.export_state()]
+            _check_base_invariants(cc, m, pose, inv, 10)              # fresh episodes, written back to HBM
+            ob = OracleBatch([cc], n)
+            ob.map[:] = m.reshape(n, -1); ob.pose[:] = pose; ob.inv[:] = inv
+            assert np.array_equal(obs.cpu().numpy()[:, :cc.obs_dim], ob.observe())   # obs of the new episode
+            assert (h.ep_len.cpu().numpy() == 0).all()
+        else:
+            assert not d.any()
+    st = h.stats().cpu().numpy()
+    assert st[0] == n * 40 and st[1] == total_done and st[5] == total_done
+    assert (h.episode.cpu().numpy() == 3).all()
+
+
+def test_sticky_done_without_auto_reset():
+    cc = _compiled(C2)
+    h = BatchHandle([cc], 32)
+    h.reset()
+    inv = h.inventory.clone()
+    inv[:, cc.c.id_goal] = 1
+    h.load_state(h.map.clone(), h.pose.clone(), inv)
+    for _ in range(3):
+        obs, rew, done, cost, res = h.step(torch.zeros(32, dtype=torch.int32, device='cuda') + 7)
+        assert done.all() and (rew == 50).all()

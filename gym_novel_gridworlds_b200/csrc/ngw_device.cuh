@@ -58,7 +58,6 @@ struct Philox {
 
 // ------------------------------------------------------------------ per-env view
 struct EnvRow {
-    const ngw_config* __restrict__ cfg;   // global memory, L1-resident (uniform across a config-homogeneous warp)
     int8_t* m;                            // staged grid row [cells]
     int8_t* gm;                           // the same row in global memory (write-through of the few changed cells), or nullptr
     int32_t* inv;                         // staged inventory row
@@ -102,8 +101,8 @@ __device__ __forceinline__ bool next_to(const EnvRow& e, int r, int c, int item)
 }
 
 // grab_entities (pogostick_v1_env.py:538-554); the agent is always interior so the 3x3 is in bounds
-__device__ __forceinline__ void grab_entities(EnvRow& e) {
-    uint32_t mask = e.cfg->entity_mask;
+__device__ __forceinline__ void grab_entities(EnvRow& e, const ngw_config& cfg) {
+    uint32_t mask = cfg.entity_mask;
     if (mask == 0) return;
     for (int rr = e.r - 1; rr <= e.r + 1; rr++)
         for (int cc = e.c - 1; cc <= e.c + 1; cc++) {
@@ -116,7 +115,7 @@ __device__ __forceinline__ void grab_entities(EnvRow& e) {
 }
 
 // craft (pogostick_v1_env.py:413-474, bow_v1_env.py:386-441, novelty_wrappers.py:371-436)
-__device__ __forceinline__ void craft(EnvRow& e, const ngw_recipe& rc, StepOut& o) {
+__device__ __forceinline__ void craft(EnvRow& e, const ngw_config& cfg, const ngw_recipe& rc, StepOut& o) {
     bool have_all = true;
     int n_in = rc.n_inputs;
     for (int i = 0; i < n_in; i++) {
@@ -127,7 +126,7 @@ __device__ __forceinline__ void craft(EnvRow& e, const ngw_recipe& rc, StepOut& 
     if (rc.needs_table) {
         int fr, fc;
         front_of(e, fr, fc);
-        if (cell(e, fr, fc) != e.cfg->id_crafting_table) { o.result = 0; o.cost = rc.cost_no_table; return; }
+        if (cell(e, fr, fc) != cfg.id_crafting_table) { o.result = 0; o.cost = rc.cost_no_table; return; }
     }
     o.reward = rc.reward_ok;
     for (int i = 0; i < n_in; i++) e.inv[rc.in_item[i]] -= (int)rc.in_qty[i];
@@ -137,8 +136,7 @@ __device__ __forceinline__ void craft(EnvRow& e, const ngw_recipe& rc, StepOut& 
 
 // terminal opcode: the innermost step body that finally handles the action, WITHOUT its trailing
 // grab_entities / done block (applied by the caller, once, as the reference's paths all do)
-__device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_action_entry a, StepOut& o) {
-    const ngw_config* cfg = e.cfg;
+__device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_config& cfg, const ngw_action_entry a, StepOut& o) {
     int fr, fc;
     front_of(e, fr, fc);
     o.reward = -1; o.result = 1; o.cost = 0.0f; o.done = 0;         // pogostick_v1_env.py:239-242
@@ -156,24 +154,24 @@ __device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_action_entry a,
         case NGW_OP_BREAK: {
             int front = cell(e, fr, fc);
             o.cost = 3600.0f;
-            if (in_mask(cfg->unbreakable_mask, front)) { o.result = 0; break; }
+            if (in_mask(cfg.unbreakable_mask, front)) { o.result = 0; break; }
             int variant = a.variant;
             if (variant == NGW_BRK_BASE) {                            // pogostick_v1_env.py:283-289
                 set_cell(e, fr, fc, 0);
                 e.inv[front] += 1;
-                if (front == cfg->id_tree_log) o.reward = cfg->reward_intermediate;
+                if (front == cfg.id_tree_log) o.reward = cfg.reward_intermediate;
             } else if (variant == NGW_BRK_INCREASE) {                 // novelty_wrappers.py:1444-1454
                 set_cell(e, fr, fc, 0);
                 e.inv[front] += (a.arg == NGW_NONE || a.arg == front) ? 2 : 1;
-                o.reward = cfg->reward_intermediate;
+                o.reward = cfg.reward_intermediate;
             } else {                                                  // axe / axetobreak, novelty_wrappers.py:55-81, 482-501
                 bool has_axe = e.inv[a.arg] >= 1;
-                bool wooden = has_axe && cfg->id_wooden_axe != NGW_NONE && e.sel == cfg->id_wooden_axe;
-                bool iron = has_axe && !wooden && cfg->id_iron_axe != NGW_NONE && e.sel == cfg->id_iron_axe;
+                bool wooden = has_axe && cfg.id_wooden_axe != NGW_NONE && e.sel == cfg.id_wooden_axe;
+                bool iron = has_axe && !wooden && cfg.id_iron_axe != NGW_NONE && e.sel == cfg.id_iron_axe;
                 if (wooden || iron) {
                     set_cell(e, fr, fc, 0);
                     e.inv[front] += (variant == NGW_BRK_AXE_INC) ? 2 : 1;
-                    o.reward = cfg->reward_intermediate;
+                    o.reward = cfg.reward_intermediate;
                     o.cost = wooden ? 1800.0f : 900.0f;
                 } else if (variant == NGW_BRK_AXETOBREAK) {
                     o.result = 0;
@@ -186,29 +184,29 @@ __device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_action_entry a,
         }
         case NGW_OP_PLACE_TREE_TAP:                                   // pogostick_v1_env.py:295-314
             o.cost = 300.0f;
-            if (e.inv[cfg->id_tree_tap] >= 1 && cell(e, fr, fc) == 0) {
-                set_cell(e, fr, fc, cfg->id_tree_tap);
-                e.inv[cfg->id_tree_tap] -= 1;
-                if (next_to(e, fr, fc, cfg->id_tree_log)) o.reward = cfg->reward_intermediate;
+            if (e.inv[cfg.id_tree_tap] >= 1 && cell(e, fr, fc) == 0) {
+                set_cell(e, fr, fc, cfg.id_tree_tap);
+                e.inv[cfg.id_tree_tap] -= 1;
+                if (next_to(e, fr, fc, cfg.id_tree_log)) o.reward = cfg.reward_intermediate;
             } else o.result = 0;
             break;
         case NGW_OP_EXTRACT_RUBBER:                                   // pogostick_v1_env.py:315-331, novelty_wrappers.py:1537-1551
             o.cost = 120.0f;
-            if (cell(e, fr, fc) == cfg->id_tree_tap && next_to(e, fr, fc, cfg->id_tree_log)) {
-                e.inv[cfg->id_rubber] += a.arg;
-                o.reward = cfg->reward_intermediate; o.cost = 50000.0f;
+            if (cell(e, fr, fc) == cfg.id_tree_tap && next_to(e, fr, fc, cfg.id_tree_log)) {
+                e.inv[cfg.id_rubber] += a.arg;
+                o.reward = cfg.reward_intermediate; o.cost = 50000.0f;
             } else o.result = 0;
             break;
         case NGW_OP_EXTRACT_STRING:                                   // bow_v1_env.py:293-304, novelty_wrappers.py:1524-1536
             o.cost = 120.0f;
-            if (cell(e, fr, fc) == cfg->id_wool) {
-                e.inv[cfg->id_string] += a.arg;
+            if (cell(e, fr, fc) == cfg.id_wool) {
+                e.inv[cfg.id_string] += a.arg;
                 set_cell(e, fr, fc, 0);
-                o.reward = cfg->reward_intermediate; o.cost = 5000.0f;
+                o.reward = cfg.reward_intermediate; o.cost = 5000.0f;
             } else o.result = 0;
             break;
         case NGW_OP_CRAFT:
-            craft(e, cfg->recipes[a.arg], o);
+            craft(e, cfg, cfg.recipes[a.arg], o);
             break;
         case NGW_OP_SELECT:                                           // pogostick_v1_env.py:338-347
             o.cost = 120.0f;
@@ -217,10 +215,10 @@ __device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_action_entry a,
         case NGW_OP_CHOP: {                                           // novelty_wrappers.py:1291-1307
             int front = cell(e, fr, fc);
             o.cost = 3600.0f * 1.2f;
-            if (!in_mask(cfg->unbreakable_mask, front)) {
+            if (!in_mask(cfg.unbreakable_mask, front)) {
                 set_cell(e, fr, fc, 0);
                 e.inv[front] += 2;
-                o.reward = cfg->reward_intermediate;
+                o.reward = cfg.reward_intermediate;
             } else o.result = 0;
             break;
         }
@@ -236,24 +234,23 @@ __device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_action_entry a,
 }
 
 // "Update after each step" (pogostick_v1_env.py:349-357 and its copies in every intercepting novelty)
-__device__ __forceinline__ void post_step(EnvRow& e, StepOut& o) {
-    grab_entities(e);
+__device__ __forceinline__ void post_step(EnvRow& e, const ngw_config& cfg, StepOut& o) {
+    grab_entities(e, cfg);
     o.done = 0;
-    if (e.inv[e.cfg->id_goal] >= 1) { o.reward = e.cfg->reward_done; o.done = 1; }
+    if (e.inv[cfg.id_goal] >= 1) { o.reward = cfg.reward_done; o.done = 1; }
 }
 
 // One full reference step() through the flattened wrapper chain.  Layers are walked outermost-first
 // (what each wrapper does before calling self.env.step), the terminal opcode runs if every
 // FenceRestriction on the way let it through, then the layers' post blocks run innermost-first.
-__device__ __forceinline__ void step_env(EnvRow& e, const ngw_action_entry a, StepOut& o) {
+__device__ __forceinline__ void step_env(EnvRow& e, const ngw_config& cfg, const ngw_action_entry a, StepOut& o) {
     uint32_t layers = (uint32_t)a.layers[0] | ((uint32_t)a.layers[1] << 8) | ((uint32_t)a.layers[2] << 16) |
                       ((uint32_t)a.layers[3] << 24);
     if (layers == 0) {                       // the common case: no pass-through novelty around this action
-        terminal_op(e, a, o);
-        post_step(e, o);
+        terminal_op(e, cfg, a, o);
+        post_step(e, cfg, o);
         return;
     }
-    const ngw_config* cfg = e.cfg;
     int fr, fc;
     front_of(e, fr, fc);
     int front = cell(e, fr, fc);             // nothing before the terminal opcode changes the grid
@@ -262,12 +259,12 @@ __device__ __forceinline__ void step_env(EnvRow& e, const ngw_action_entry a, St
         int layer = (layers >> (8 * n)) & 0xFF;
         if (layer == NGW_LAYER_END) break;
         if (layer == NGW_LAYER_CRATE) {                               // novelty_wrappers.py:1085-1088
-            if (front == cfg->id_crate)
-                for (int it = 0; it < cfg->n_items; it++) e.inv[it] += (int)cfg->crate_add[it];
+            if (front == cfg.id_crate)
+                for (int it = 0; it < cfg.n_items; it++) e.inv[it] += (int)cfg.crate_add[it];
         } else if (layer == NGW_LAYER_FENCE_MEDIUM || layer == NGW_LAYER_FENCE_HARD) {   // novelty_wrappers.py:926-958
             bool pass;
-            int fence = cfg->id_fence;
-            if (in_mask(cfg->unbreakable_mask, front)) pass = false;
+            int fence = cfg.id_fence;
+            if (in_mask(cfg.unbreakable_mask, front)) pass = false;
             else if (front == fence) pass = true;
             else if (layer == NGW_LAYER_FENCE_MEDIUM) {
                 bool ns = e.facing == NGW_NORTH || e.facing == NGW_SOUTH;
@@ -286,8 +283,8 @@ __device__ __forceinline__ void step_env(EnvRow& e, const ngw_action_entry a, St
     }
     int first_post;                           // innermost layer whose post block runs
     if (stop < 0) {
-        terminal_op(e, a, o);
-        post_step(e, o);
+        terminal_op(e, cfg, a, o);
+        post_step(e, cfg, o);
         first_post = n - 1;
     } else {
         o.reward = -1; o.result = 0; o.cost = 3600.0f; o.done = 0;
@@ -296,11 +293,11 @@ __device__ __forceinline__ void step_env(EnvRow& e, const ngw_action_entry a, St
     for (int i = first_post; i >= 0; i--) {
         int layer = (layers >> (8 * i)) & 0xFF;
         if (layer == NGW_LAYER_FIREWALL) {                            // novelty_wrappers.py:1171-1189
-            if (next_to(e, e.r, e.c, cfg->id_fire_wall)) { o.reward = cfg->reward_firewall; o.done = 1; }
+            if (next_to(e, e.r, e.c, cfg.id_fire_wall)) { o.reward = cfg.reward_firewall; o.done = 1; }
         } else if (layer == NGW_LAYER_FENCE_MEDIUM || layer == NGW_LAYER_FENCE_HARD) {
             // outer post block re-runs and overwrites info (Q5, novelty_wrappers.py:960-973); reward is the inner one
             int reward = o.reward;
-            post_step(e, o);                  // sets done / reward_done from the goal test, done = 0 otherwise
+            post_step(e, cfg, o);             // sets done / reward_done from the goal test, done = 0 otherwise
             if (!o.done) o.reward = reward;
             o.result = (i == stop) ? 0 : 1;
             o.cost = 3600.0f;
@@ -309,29 +306,78 @@ __device__ __forceinline__ void step_env(EnvRow& e, const ngw_action_entry a, St
 }
 
 // ------------------------------------------------------------------ LidarInFront (observation_wrappers.py:32-80)
-// lut: int16 [4][B][K] linear offsets d_row * ms + d_col of sample k+1 (built on the host with the reference's
-// NumPy expression).  obs row must be zero-filled for the lidar part by the caller.
-__device__ __forceinline__ void lidar_observe(const EnvRow& e, const int16_t* lut, int32_t* obs) {
-    const ngw_config* cfg = e.cfg;
-    int B = cfg->n_beams, K = cfg->max_range, L = cfg->n_lidar_items;
-    int cells = e.ms * e.ms;
-    int pos = e.r * e.ms + e.c;
-    const int16_t* row = lut + e.facing * B * K;
-    for (int b = 0; b < B; b++, row += K) {
-        for (int k = 0; k < K; k++) {
-            int idx = pos + row[k];
-            if ((unsigned)idx >= (unsigned)cells) break;              // unreachable on a walled grid
-            int id = e.m[idx];
-            if (id != 0) {
-                int slot = cfg->lidar_slot[id];
-                if (slot >= 0) obs[b * L + slot] = k + 1;
-                break;
+// Device-side companion of an ngw_config, built by ngw_create from the host beam LUT.
+//   fast path (8 beams, the reference default): the LUT factorises into a unit step per (facing, beam) times a
+//   displacement per (beam parity, sample) — axis beams advance k cells, diagonal beams round(0.71 k) cells — so
+//   the 8 beams are cast together, sample by sample, with 8 independent shared-memory reads in flight.
+//   generic path (any other beam count): int16 linear-offset LUT [4][B][K] in global memory.
+#define NGW_MAX_RANGE 96
+struct LidarDev {
+    int32_t fast;                       // 1 => unit/disp tables are valid
+    int16_t unit[4][8];                 // linear offset d_row * ms + d_col of one step of beam b when facing f
+    uint8_t disp[2][NGW_MAX_RANGE];     // cells travelled at sample k (0-based) by even / odd beams
+    const int16_t* lut;                 // generic path: device int16 [4][B][K]
+};
+
+struct DevConfig {
+    ngw_config c;
+    LidarDev lidar;
+};
+
+// obs row must be zero-filled for the lidar part by the caller.
+__device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& dc, int32_t* obs) {
+    const ngw_config& cfg = dc.c;
+    const int B = cfg.n_beams, K = cfg.max_range, L = cfg.n_lidar_items;
+    const int cells = e.ms * e.ms;
+    const int pos = e.r * e.ms + e.c;
+    if (dc.lidar.fast) {
+        int u[8];
+        uint32_t hit[8];                                              // (sample index << 8) | item id, 0 = still flying
+#pragma unroll
+        for (int b = 0; b < 8; b++) { u[b] = dc.lidar.unit[e.facing][b]; hit[b] = 0; }
+        uint32_t flying = 0xFF;
+        for (int k = 0; k < K && flying; k++) {
+            const int d0 = dc.lidar.disp[0][k], d1 = dc.lidar.disp[1][k];
+            int id[8];
+#pragma unroll
+            for (int b = 0; b < 8; b++) {                             // 8 independent reads; a landed beam re-reads the agent cell
+                int off = ((flying >> b) & 1) ? u[b] * ((b & 1) ? d1 : d0) : 0;
+                int idx = pos + off;
+                idx = (unsigned)idx < (unsigned)cells ? idx : pos;    // unreachable on a walled grid
+                id[b] = e.m[idx];
+            }
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                bool lands = ((flying >> b) & 1) && id[b] != 0;       // first non-air cell ends the beam (obsw:58-66)
+                hit[b] = lands ? (uint32_t)(((k + 1) << 8) | (id[b] & 0xFF)) : hit[b];
+                flying = lands ? (flying & ~(1u << b)) : flying;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            if (hit[b]) {
+                int slot = cfg.lidar_slot[hit[b] & 0xFF];             // -1: occludes but is not a lidar item (Q2)
+                if (slot >= 0) obs[b * L + slot] = (int)(hit[b] >> 8);
+            }
+        }
+    } else {
+        const int16_t* row = dc.lidar.lut + e.facing * B * K;
+        for (int b = 0; b < B; b++, row += K) {
+            for (int k = 0; k < K; k++) {
+                int idx = pos + row[k];
+                if ((unsigned)idx >= (unsigned)cells) break;
+                int id = e.m[idx];
+                if (id != 0) {
+                    int slot = cfg.lidar_slot[id];
+                    if (slot >= 0) obs[b * L + slot] = k + 1;
+                    break;
+                }
             }
         }
     }
-    int n_tail = cfg->n_inv_obs;
+    const int n_tail = cfg.n_inv_obs;
     int32_t* tail = obs + L * B;
-    for (int i = 0; i < n_tail; i++) tail[i] = e.inv[cfg->inv_obs_item[i]];   // sorted-name order (Q7)
+    for (int i = 0; i < n_tail; i++) tail[i] = e.inv[cfg.inv_obs_item[i]];    // sorted-name order (Q7)
 }
 
 // ------------------------------------------------------------------ reset (pogostick_v1_env.py:86-181 + novelty resets)
@@ -344,8 +390,7 @@ __device__ __forceinline__ bool placeable(const EnvRow& e, int r, int c) {
            cell(e, r, c + 1) == 0;
 }
 
-__device__ __noinline__ uint32_t reset_base(EnvRow& e, int inv_stride, uint64_t seed, uint64_t gid, uint32_t episode) {
-    const ngw_config* cfg = e.cfg;
+__device__ __noinline__ uint32_t reset_base(EnvRow& e, const ngw_config* cfg, int inv_stride, uint64_t seed, uint64_t gid, uint32_t episode) {
     int ms = e.ms;
     uint32_t err = 0;
     for (int i = 0; i < inv_stride; i++) e.inv[i] = 0;                // pogostick_v1_env.py:119-120
@@ -392,8 +437,7 @@ __device__ __noinline__ uint32_t reset_base(EnvRow& e, int inv_stride, uint64_t 
 // Post-ops [op_begin, op_end).  A uniformly random m-subset of the candidate cells (what "shuffle, take the
 // first m" selects) is drawn by selection sampling in row-major order: candidate j of n is taken with
 // probability (m - taken) / (n - j).  m = ceil(n * (pct / 100)) in IEEE doubles exactly as NumPy computes it.
-__device__ __noinline__ void reset_ops(EnvRow& e, int op_begin, int op_end, uint64_t seed, uint64_t gid, uint32_t episode) {
-    const ngw_config* cfg = e.cfg;
+__device__ __noinline__ void reset_ops(EnvRow& e, const ngw_config* cfg, int op_begin, int op_end, uint64_t seed, uint64_t gid, uint32_t episode) {
     int ms = e.ms, cells = ms * ms;
     int agent = e.r * ms + e.c;
     if (op_end > cfg->n_reset_ops) op_end = cfg->n_reset_ops;

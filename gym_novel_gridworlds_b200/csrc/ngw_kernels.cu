@@ -68,7 +68,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // ------------------------------------------------------------------ parameters
 struct StepParams {
-    const ngw_config* cfgs;
+    const DevConfig* dcfgs;     // global-memory copy of the configs (cold paths, and the hot path when NC == 0)
     int8_t* map;
     uchar4* pose;
     int32_t* inv;
@@ -87,8 +87,16 @@ struct StepParams {
     long long first_gid;
     unsigned long long seed;
     int ms, cells, inv_stride, obs_dim;
-    int map_bytes, inv_bytes, obs_bytes, lut_bytes, region_bytes;   // per-warp shared-memory carve-up
+    int map_bytes, inv_bytes, obs_bytes, region_bytes;   // per-warp shared-memory carve-up
     int auto_reset, max_episode_steps;
+};
+
+// Kernel argument block: the parameters plus up to NC configs INLINE, so that every config read in the hot path
+// is a constant-bank operand (c[0x0][..]) instead of a global load.  NC == 0 falls back to global memory.
+template <int NC>
+struct StepArgs {
+    StepParams p;
+    DevConfig cfg[NC > 0 ? NC : 1];
 };
 
 #define NGW_STAT_SLOTS 32
@@ -105,10 +113,27 @@ __device__ __forceinline__ void warp_copy16(void* dst, const void* src, int byte
     for (int i = lane; i < (bytes >> 4); i += 32) d[i] = s[i];
 }
 
+// Cold: Philox auto-reset of one env on its shared-memory rows, then the whole grid row back to HBM.
+__device__ __noinline__ uint32_t auto_reset_env(const StepParams& p, const ngw_config* cfg, int8_t* m, int32_t* inv,
+                                                long long e, uchar4& ps) {
+    uint32_t ep = p.episode[e] + 1;
+    p.episode[e] = ep;
+    EnvRow cold;
+    cold.m = m; cold.gm = nullptr; cold.inv = inv; cold.ms = p.ms;
+    cold.r = ps.x; cold.c = ps.y; cold.facing = ps.z; cold.sel = ps.w;
+    uint32_t err = reset_base(cold, cfg, p.inv_stride, p.seed, (uint64_t)(p.first_gid + e), ep);
+    reset_ops(cold, cfg, 0, NGW_MAX_RESET_OPS, p.seed, (uint64_t)(p.first_gid + e), ep);
+    int8_t* grow = p.map + e * p.cells;
+    for (int i = 0; i < p.cells; i++) grow[i] = m[i];
+    ps = make_uchar4((unsigned char)cold.r, (unsigned char)cold.c, (unsigned char)cold.facing, (unsigned char)cold.sel);
+    return err;
+}
+
 // ------------------------------------------------------------------ the fused step + LidarInFront kernel
-template <bool kTma>
-__global__ void __launch_bounds__(128) step_kernel(const StepParams p) {
+template <bool kTma, int NC>
+__global__ void __launch_bounds__(128, 4) step_kernel(const __grid_constant__ StepArgs<NC> args) {
     extern __shared__ __align__(128) unsigned char smem[];
+    const StepParams& p = args.p;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     const long long e0 = p.env_begin + ((long long)blockIdx.x * warps + warp) * 32;
     if (e0 >= p.env_end) return;                                     // whole warp leaves together
@@ -121,7 +146,6 @@ __global__ void __launch_bounds__(128) step_kernel(const StepParams p) {
     int8_t* smap = reinterpret_cast<int8_t*>(region + 16);
     int32_t* sinv = reinterpret_cast<int32_t*>(region + 16 + p.map_bytes);
     int32_t* sobs = reinterpret_cast<int32_t*>(region + 16 + p.map_bytes + p.inv_bytes);
-    int16_t* slut = reinterpret_cast<int16_t*>(region + 16 + p.map_bytes + p.inv_bytes + p.obs_bytes);
 
     // ---- stage the tile: grid rows + inventory rows (state arrays are padded, a full tile is always readable)
     const int8_t* gmap = p.map + e0 * p.cells;
@@ -139,33 +163,23 @@ __global__ void __launch_bounds__(128) step_kernel(const StepParams p) {
     }
     __syncwarp();                                                    // barrier init visible before anyone waits on it
 
-    // ---- while the copies fly: per-lane scalars, config, beam LUT, zero the observation tile
+    // ---- while the copies fly: per-lane scalars and zeroing of the observation tile
     uchar4 ps = p.pose[e];
-    const int cfg_i = p.cfg_id[e];
-    const ngw_config* cfg = p.cfgs + cfg_i;
-    const int cfg_first = __shfl_sync(0xFFFFFFFFu, cfg_i, 0);
-    const bool uniform = __all_sync(0xFFFFFFFFu, !valid || cfg_i == cfg_first);
-    const int16_t* lut = reinterpret_cast<const int16_t*>(cfg->beam_lut);
+    const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[e];
+    const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
+    const ngw_config& cfg = dc.c;
+    int action = 0;
+    if (p.actions != nullptr && valid) action = p.actions[e];
     if (p.obs != nullptr) {
-        const ngw_config* c0 = p.cfgs + cfg_first;
-        const int16_t* glut = reinterpret_cast<const int16_t*>(c0->beam_lut);
-        if (uniform && glut != nullptr) {                            // config-homogeneous warp: LUT into shared memory
-            int n = 4 * c0->n_beams * c0->max_range;
-            for (int i = lane; i < n; i += 32) slut[i] = glut[i];
-            lut = slut;
-        }
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4* o4 = reinterpret_cast<uint4*>(sobs);
         for (int i = lane; i < (p.obs_bytes >> 4); i += 32) o4[i] = z;
     }
-    int action = 0;
-    if (p.actions != nullptr && valid) action = p.actions[e];
 
     if (kTma) mbar_wait(bar, 0);
     __syncwarp();
 
     EnvRow env;
-    env.cfg = cfg;
     env.m = smap + lane * p.cells;
     env.gm = p.map + e * p.cells;
     env.inv = sinv + lane * p.inv_stride;
@@ -179,16 +193,16 @@ __global__ void __launch_bounds__(128) step_kernel(const StepParams p) {
         if (valid) {
             ngw_action_entry a;
             a.op = NGW_OP_INVALID;
-            if (action >= 0 && action < cfg->n_actions) {
-                uint2 raw = *reinterpret_cast<const uint2*>(&cfg->actions[action]);
+            if (action >= 0 && action < cfg.n_actions) {
+                uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
                 memcpy(&a, &raw, sizeof(a));
             }
             if (a.op == NGW_OP_INVALID) {                             // wrappers.py:76 / pogostick_v1_env.py:236 would raise
                 invalid = 1;
                 p.err[e] |= NGW_ERR_INVALID_ACTION;
             } else {
-                step_env(env, a, o);
-                success = o.done && env.inv[cfg->id_goal] >= 1;
+                step_env(env, cfg, a, o);
+                success = o.done && env.inv[cfg.id_goal] >= 1;
                 int finished = o.done;
                 if (p.max_episode_steps > 0) {
                     int len = p.ep_len[e] + 1;
@@ -197,14 +211,11 @@ __global__ void __launch_bounds__(128) step_kernel(const StepParams p) {
                 }
                 if (finished && p.auto_reset) {                       // fused auto-reset (rare lanes only)
                     did_reset = 1;
-                    uint32_t ep = p.episode[e] + 1;
-                    p.episode[e] = ep;
-                    env.gm = nullptr;
-                    uint32_t err = reset_base(env, p.inv_stride, p.seed, (uint64_t)(p.first_gid + e), ep);
-                    reset_ops(env, 0, NGW_MAX_RESET_OPS, p.seed, (uint64_t)(p.first_gid + e), ep);
+                    uchar4 np = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
+                                            (unsigned char)env.sel);
+                    uint32_t err = auto_reset_env(p, &p.dcfgs[cfg_i].c, env.m, env.inv, e, np);
                     if (err) p.err[e] |= err;
-                    int8_t* grow = p.map + e * p.cells;
-                    for (int i = 0; i < p.cells; i++) grow[i] = env.m[i];
+                    env.r = np.x; env.c = np.y; env.facing = np.z; env.sel = np.w;
                 }
             }
             p.pose[e] = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
@@ -236,7 +247,7 @@ __global__ void __launch_bounds__(128) step_kernel(const StepParams p) {
     }
 
     // ---- LidarInFront observation of the (possibly auto-reset) state into the shared-memory tile
-    if (p.obs != nullptr && valid && cfg->n_beams > 0) lidar_observe(env, lut, sobs + lane * p.obs_dim);
+    if (p.obs != nullptr && valid && cfg.n_beams > 0) lidar_observe(env, dc, sobs + lane * p.obs_dim);
 
     // ---- write back: inventory tile (only when stepping) and observation tile
     __syncwarp();
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(128) step_kernel(const StepParams p) {
 
 // ------------------------------------------------------------------ cold-path kernels (one thread per env, global memory)
 struct ResetParams {
-    const ngw_config* cfgs;
+    const DevConfig* dcfgs;
     int8_t* map;
     uchar4* pose;
     int32_t* inv;
@@ -281,9 +292,8 @@ __global__ void reset_kernel(const ResetParams p) {
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.n_envs) return;
     if (p.mask != nullptr && p.mask[e] == 0) return;
-    const ngw_config* cfg = p.cfgs + p.cfg_id[e];
+    const ngw_config* cfg = &p.dcfgs[p.cfg_id[e]].c;
     EnvRow env;
-    env.cfg = cfg;
     env.m = p.map + e * p.cells;
     env.gm = nullptr;
     env.inv = p.inv + e * p.inv_stride;
@@ -297,12 +307,12 @@ __global__ void reset_kernel(const ResetParams p) {
         ep = p.episode[e] + 1;
         p.episode[e] = ep;
         p.ep_len[e] = 0;
-        uint32_t err = reset_base(env, p.inv_stride, p.seed, gid, ep);
+        uint32_t err = reset_base(env, cfg, p.inv_stride, p.seed, gid, ep);
         p.err[e] = err;
-        reset_ops(env, 0, p.phase == 0 ? k : NGW_MAX_RESET_OPS, p.seed, gid, ep);
+        reset_ops(env, cfg, 0, p.phase == 0 ? k : NGW_MAX_RESET_OPS, p.seed, gid, ep);
     } else {
         ep = p.episode[e];
-        reset_ops(env, k, NGW_MAX_RESET_OPS, p.seed, gid, ep);
+        reset_ops(env, cfg, k, NGW_MAX_RESET_OPS, p.seed, gid, ep);
     }
     p.pose[e] = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing, (unsigned char)env.sel);
 }
@@ -311,9 +321,8 @@ __global__ void observe_masked_kernel(const ResetParams p, int32_t* obs, int obs
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.n_envs) return;
     if (p.mask != nullptr && p.mask[e] == 0) return;
-    const ngw_config* cfg = p.cfgs + p.cfg_id[e];
+    const DevConfig& dc = p.dcfgs[p.cfg_id[e]];
     EnvRow env;
-    env.cfg = cfg;
     env.m = p.map + e * p.cells;
     env.gm = nullptr;
     env.inv = p.inv + e * p.inv_stride;
@@ -322,7 +331,7 @@ __global__ void observe_masked_kernel(const ResetParams p, int32_t* obs, int obs
     env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
     int32_t* row = obs + e * obs_dim;
     for (int i = 0; i < obs_dim; i++) row[i] = 0;
-    if (cfg->n_beams > 0) lidar_observe(env, reinterpret_cast<const int16_t*>(cfg->beam_lut), row);
+    if (dc.c.n_beams > 0) lidar_observe(env, dc, row);
 }
 
 __global__ void set_cfg_kernel(const int32_t* src, uint8_t* dst, long long n, int n_cfgs, uint32_t* err) {
@@ -364,11 +373,11 @@ struct ngw_handle {
     long long n = 0, np = 0, first_gid = 0;
     unsigned long long seed = 0;
     int ms = 0, cells = 0, inv_stride = 0, obs_dim = 0, n_cfgs = 0;
-    int map_bytes = 0, inv_bytes = 0, obs_bytes = 0, lut_bytes = 0, region_bytes = 0, warps = 4;
-    bool use_tma = true, collect_stats = true;
-    ngw_config* d_cfgs = nullptr;
+    int map_bytes = 0, inv_bytes = 0, obs_bytes = 0, region_bytes = 0, warps = 4;
+    bool use_tma = true, collect_stats = true, force_global_cfg = false;
+    DevConfig* d_cfgs = nullptr;
     std::vector<int16_t*> d_luts;
-    std::vector<ngw_config> h_cfgs;
+    std::vector<DevConfig> h_cfgs;
     int8_t* map = nullptr; uchar4* pose = nullptr; int32_t* inv = nullptr; uint8_t* cfg_id = nullptr;
     uint32_t* episode = nullptr; int32_t* ep_len = nullptr; uint32_t* err = nullptr; double* stats = nullptr;
     long long launches = 0;
@@ -412,7 +421,7 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
     h->ms = map_size; h->cells = map_size * map_size; h->n_cfgs = n_cfgs;
     h->use_tma = getenv("NGW_NO_TMA") == nullptr;
     h->collect_stats = getenv("NGW_NO_STATS") == nullptr;
-    int max_lut = 0;
+    h->force_global_cfg = getenv("NGW_GLOBAL_CFG") != nullptr;
     for (int i = 0; i < n_cfgs; i++) {
         const ngw_config& c = cfgs[i];
         if (c.n_items < 1 || c.n_items > NGW_MAX_ITEMS || c.n_actions < 0 || c.n_actions > NGW_MAX_ACTIONS ||
@@ -425,26 +434,53 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
         int d = c.n_beams > 0 ? c.n_lidar_items * c.n_beams + c.n_inv_obs : 0;
         if (d > h->obs_dim) h->obs_dim = d;
         if (c.n_beams > 0 && c.beam_lut == nullptr) { delete h; return fail("ngw_create: lidar config without beam_lut"); }
-        int l = 4 * c.n_beams * c.max_range * 2;
-        if (l > max_lut) max_lut = l;
     }
-    // device copies of the configs, beam LUTs converted to linear int16 offsets for this map size
-    h->h_cfgs.assign(cfgs, cfgs + n_cfgs);
+    // device configs: the host beam LUT (d_row, d_col) becomes either the factorised 8-beam tables or an int16
+    // linear-offset LUT for this map size
+    h->h_cfgs.resize(n_cfgs);
     for (int i = 0; i < n_cfgs; i++) {
-        ngw_config& c = h->h_cfgs[i];
+        DevConfig& dc = h->h_cfgs[i];
+        memset(&dc, 0, sizeof(dc));
+        dc.c = cfgs[i];
+        const ngw_config& c = cfgs[i];
+        const int B = c.n_beams, K = c.max_range;
+        auto at = [&](int f, int b, int k, int j) { return (int)c.beam_lut[((f * B + b) * K + k) * 2 + j]; };
+        bool fast = (B == 8 && K >= 1 && K <= NGW_MAX_RANGE);
+        if (fast) {
+            for (int par = 0; par < 2 && fast; par++)
+                for (int k = 0; k < K && fast; k++) {
+                    int dr = abs(at(0, par, k, 0)), dcol = abs(at(0, par, k, 1));
+                    int d = dr > dcol ? dr : dcol;
+                    if (d > 255) fast = false;
+                    dc.lidar.disp[par][k] = (uint8_t)d;
+                }
+            for (int f = 0; f < 4 && fast; f++)
+                for (int b = 0; b < 8 && fast; b++) {
+                    int ur = at(f, b, 0, 0), uc = at(f, b, 0, 1);
+                    if (abs(ur) > 1 || abs(uc) > 1 || (ur == 0 && uc == 0)) { fast = false; break; }
+                    dc.lidar.unit[f][b] = (int16_t)(ur * map_size + uc);
+                    for (int k = 0; k < K; k++) {
+                        int d = dc.lidar.disp[b & 1][k];
+                        if (at(f, b, k, 0) != ur * d || at(f, b, k, 1) != uc * d) { fast = false; break; }
+                    }
+                }
+        }
+        if (getenv("NGW_NO_FAST_LIDAR")) fast = false;
+        dc.lidar.fast = fast ? 1 : 0;
         int16_t* d_lut = nullptr;
-        if (c.n_beams > 0) {
-            int n = 4 * c.n_beams * c.max_range;
+        if (B > 0 && !fast) {
+            int n = 4 * B * K;
             std::vector<int16_t> lin(n);
             for (int j = 0; j < n; j++) lin[j] = (int16_t)(c.beam_lut[2 * j] * map_size + c.beam_lut[2 * j + 1]);
             CK(cudaMalloc(&d_lut, n * sizeof(int16_t)));
             CK(cudaMemcpy(d_lut, lin.data(), n * sizeof(int16_t), cudaMemcpyHostToDevice));
             h->d_luts.push_back(d_lut);
         }
-        c.beam_lut = reinterpret_cast<const int8_t*>(d_lut);
+        dc.lidar.lut = d_lut;
+        dc.c.beam_lut = nullptr;
     }
-    CK(cudaMalloc(&h->d_cfgs, sizeof(ngw_config) * n_cfgs));
-    CK(cudaMemcpy(h->d_cfgs, h->h_cfgs.data(), sizeof(ngw_config) * n_cfgs, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_cfgs, sizeof(DevConfig) * n_cfgs));
+    CK(cudaMemcpy(h->d_cfgs, h->h_cfgs.data(), sizeof(DevConfig) * n_cfgs, cudaMemcpyHostToDevice));
     // state
     CK(cudaMalloc(&h->map, (size_t)h->np * h->cells));
     CK(cudaMalloc(&h->pose, (size_t)h->np * 4));
@@ -466,15 +502,24 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
     h->map_bytes = 32 * h->cells;                       // multiple of 32
     h->inv_bytes = 128 * h->inv_stride;
     h->obs_bytes = 128 * (h->obs_dim > 0 ? h->obs_dim : 0);
-    h->lut_bytes = align16(max_lut);
-    h->region_bytes = 16 + h->map_bytes + h->inv_bytes + h->obs_bytes + h->lut_bytes;
+    h->region_bytes = 16 + h->map_bytes + h->inv_bytes + h->obs_bytes;
     h->region_bytes = (h->region_bytes + 127) & ~127;
     int warps = 4;
     while (warps > 1 && warps * h->region_bytes > 56 * 1024) warps >>= 1;
     if (warps * h->region_bytes > 227 * 1024) { ngw_destroy(h); return fail("ngw_create: map too large for shared memory"); }
+    if (const char* w = getenv("NGW_WARPS")) {                      // tuning knob: warps (tiles) per CTA, 1..4
+        int v = atoi(w);
+        if (v >= 1 && v <= 4 && v * h->region_bytes <= 227 * 1024) warps = v;
+    }
     h->warps = warps;
-    CK(cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     *out = h;
     return 0;
 }
@@ -515,7 +560,7 @@ int ngw_load_state(ngw_handle* h, const int8_t* map, const uint8_t* pose, const 
 
 static ResetParams reset_params(ngw_handle* h, const uint8_t* mask, int phase) {
     ResetParams p;
-    p.cfgs = h->d_cfgs; p.map = h->map; p.pose = h->pose; p.inv = h->inv; p.cfg_id = h->cfg_id; p.episode = h->episode;
+    p.dcfgs = h->d_cfgs; p.map = h->map; p.pose = h->pose; p.inv = h->inv; p.cfg_id = h->cfg_id; p.episode = h->episode;
     p.ep_len = h->ep_len; p.err = h->err; p.mask = mask; p.n_envs = h->n; p.first_gid = h->first_gid; p.seed = h->seed;
     p.ms = h->ms; p.cells = h->cells; p.inv_stride = h->inv_stride; p.phase = phase;
     return p;
@@ -527,7 +572,7 @@ int ngw_reset(ngw_handle* h, const uint8_t* mask, int32_t* obs, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     int blocks = (int)((h->n + 127) / 128);
     bool split = false;
-    for (auto& c : h->h_cfgs) split |= c.reset_obs_after_ops < c.n_reset_ops;
+    for (auto& c : h->h_cfgs) split |= c.c.reset_obs_after_ops < c.c.n_reset_ops;
     if (obs == nullptr || h->obs_dim == 0 || !split) {
         reset_kernel<<<blocks, 128, 0, s>>>(reset_params(h, mask, 2));
         h->launches++;
@@ -549,14 +594,25 @@ static StepParams step_params(ngw_handle* h, const int32_t* actions, int32_t* ob
                               float* cost, uint8_t* result, int auto_reset, int max_episode_steps, long long begin,
                               long long end) {
     StepParams p;
-    p.cfgs = h->d_cfgs; p.map = h->map; p.pose = h->pose; p.inv = h->inv; p.cfg_id = h->cfg_id; p.episode = h->episode;
+    p.dcfgs = h->d_cfgs; p.map = h->map; p.pose = h->pose; p.inv = h->inv; p.cfg_id = h->cfg_id; p.episode = h->episode;
     p.ep_len = h->ep_len; p.err = h->err; p.actions = actions; p.obs = h->obs_dim > 0 ? obs : nullptr; p.reward = reward;
     p.done = done; p.cost = cost; p.result = result; p.stats = h->collect_stats ? h->stats : nullptr;
     p.env_begin = begin; p.env_end = end; p.first_gid = h->first_gid; p.seed = h->seed;
     p.ms = h->ms; p.cells = h->cells; p.inv_stride = h->inv_stride; p.obs_dim = h->obs_dim;
-    p.map_bytes = h->map_bytes; p.inv_bytes = h->inv_bytes; p.obs_bytes = h->obs_bytes; p.lut_bytes = h->lut_bytes;
+    p.map_bytes = h->map_bytes; p.inv_bytes = h->inv_bytes; p.obs_bytes = h->obs_bytes;
     p.region_bytes = h->region_bytes; p.auto_reset = auto_reset; p.max_episode_steps = max_episode_steps;
     return p;
+}
+
+}  // extern "C" (templates need C++ linkage)
+
+template <int NC>
+static void launch_step_nc(ngw_handle* h, const StepParams& p, int blocks, size_t smem, cudaStream_t s) {
+    static StepArgs<NC> args;                       // host staging of the argument block (copied by the launch)
+    args.p = p;
+    for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
+    if (h->use_tma) step_kernel<true, NC><<<blocks, 32 * h->warps, smem, s>>>(args);
+    else step_kernel<false, NC><<<blocks, 32 * h->warps, smem, s>>>(args);
 }
 
 static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
@@ -564,12 +620,17 @@ static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
     if (tiles <= 0) return 0;
     int blocks = (int)((tiles + h->warps - 1) / h->warps);
     size_t smem = (size_t)h->warps * h->region_bytes;
-    if (h->use_tma) step_kernel<true><<<blocks, 32 * h->warps, smem, s>>>(p);
-    else step_kernel<false><<<blocks, 32 * h->warps, smem, s>>>(p);
+    int nc = h->force_global_cfg ? 0 : h->n_cfgs;
+    if (nc == 0 || nc > 16) launch_step_nc<0>(h, p, blocks, smem, s);
+    else if (nc == 1) launch_step_nc<1>(h, p, blocks, smem, s);
+    else if (nc <= 4) launch_step_nc<4>(h, p, blocks, smem, s);
+    else launch_step_nc<16>(h, p, blocks, smem, s);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
 }
+
+extern "C" {
 
 int ngw_step(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done, float* step_cost,
              uint8_t* result, int32_t auto_reset, int32_t max_episode_steps, void* stream) {

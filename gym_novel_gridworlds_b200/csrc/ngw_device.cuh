@@ -324,33 +324,41 @@ struct DevConfig {
     LidarDev lidar;
 };
 
-// obs row must be zero-filled for the lidar part by the caller.
-__device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& dc, int32_t* obs) {
+// obs row must be zero-filled for the lidar part by the caller; `zero` points at a byte that always reads 0 and lives in
+// the same address space as the grid row.
+__device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& dc, int32_t* obs, const int8_t* zero) {
     const ngw_config& cfg = dc.c;
     const int B = cfg.n_beams, K = cfg.max_range, L = cfg.n_lidar_items;
     const int cells = e.ms * e.ms;
     const int pos = e.r * e.ms + e.c;
     if (dc.lidar.fast) {
+        // Each beam keeps a running cell pointer; axis beams advance one unit step per sample, diagonal beams advance
+        // when round(0.71 k) grows (disp[1][k] - disp[1][k-1] is 0 or 1).  A beam that lands parks on `zero`, a cell
+        // that always reads air, so no per-beam "still flying" test is needed in the loop.
         int u[8];
+        const int8_t* at[8];
         uint32_t hit[8];                                              // (sample index << 8) | item id, 0 = still flying
+        const int8_t* base = e.m + pos;
 #pragma unroll
-        for (int b = 0; b < 8; b++) { u[b] = dc.lidar.unit[e.facing][b]; hit[b] = 0; }
-        uint32_t flying = 0xFF;
-        for (int k = 0; k < K && flying; k++) {
+        for (int b = 0; b < 8; b++) { u[b] = dc.lidar.unit[e.facing][b]; at[b] = base; hit[b] = 0; }
+        int prev0 = 0, prev1 = 0, flying = 8;
+        for (int k = 0; k < K && flying > 0; k++) {
             const int d0 = dc.lidar.disp[0][k], d1 = dc.lidar.disp[1][k];
+            const int s0 = d0 - prev0, s1 = d1 - prev1;               // warp-uniform step counts (0 or 1 for 8 beams)
+            prev0 = d0; prev1 = d1;
             int id[8];
 #pragma unroll
-            for (int b = 0; b < 8; b++) {                             // 8 independent reads; a landed beam re-reads the agent cell
-                int off = ((flying >> b) & 1) ? u[b] * ((b & 1) ? d1 : d0) : 0;
-                int idx = pos + off;
-                idx = (unsigned)idx < (unsigned)cells ? idx : pos;    // unreachable on a walled grid
-                id[b] = e.m[idx];
+            for (int b = 0; b < 8; b++) {                             // 8 independent shared-memory reads in flight
+                at[b] += u[b] * ((b & 1) ? s1 : s0);
+                id[b] = *at[b];
             }
 #pragma unroll
             for (int b = 0; b < 8; b++) {
-                bool lands = ((flying >> b) & 1) && id[b] != 0;       // first non-air cell ends the beam (obsw:58-66)
+                bool lands = id[b] != 0;                              // first non-air cell ends the beam (obsw:58-66)
                 hit[b] = lands ? (uint32_t)(((k + 1) << 8) | (id[b] & 0xFF)) : hit[b];
-                flying = lands ? (flying & ~(1u << b)) : flying;
+                u[b] = lands ? 0 : u[b];
+                at[b] = lands ? zero : at[b];
+                flying -= lands ? 1 : 0;
             }
         }
 #pragma unroll

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(128, 4) step_kernel(const __grid_constant__ St
 
     unsigned char* region = smem + (size_t)warp * p.region_bytes;
     uint64_t* bar = reinterpret_cast<uint64_t*>(region);
+    int8_t* szero = reinterpret_cast<int8_t*>(region + 8);           // 8 bytes that always read 0 (landed lidar beams park here)
     int8_t* smap = reinterpret_cast<int8_t*>(region + 16);
     int32_t* sinv = reinterpret_cast<int32_t*>(region + 16 + p.map_bytes);
     int32_t* sobs = reinterpret_cast<int32_t*>(region + 16 + p.map_bytes + p.inv_bytes);
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(128, 4) step_kernel(const __grid_constant__ St
         warp_copy16(smap, gmap, p.map_bytes, lane);
         warp_copy16(sinv, ginv, p.inv_bytes, lane);
     }
+    if (lane == 0) *reinterpret_cast<uint64_t*>(szero) = 0ull;
     __syncwarp();                                                    // barrier init visible before anyone waits on it
 
     // ---- while the copies fly: per-lane scalars and zeroing of the observation tile
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(128, 4) step_kernel(const __grid_constant__ St
     }
 
     // ---- LidarInFront observation of the (possibly auto-reset) state into the shared-memory tile
-    if (p.obs != nullptr && valid && cfg.n_beams > 0) lidar_observe(env, dc, sobs + lane * p.obs_dim);
+    if (p.obs != nullptr && valid && cfg.n_beams > 0) lidar_observe(env, dc, sobs + lane * p.obs_dim, szero);
 
     // ---- write back: inventory tile (only when stepping) and observation tile
     __syncwarp();
@@ -286,6 +288,7 @@ struct ResetParams {
     unsigned long long seed;
     int ms, cells, inv_stride;
     int phase;   // 0: base + ops before the reset observation, 1: ops after it, 2: everything
+    const uint8_t* zero_byte;   // a global byte that always reads 0 (see lidar_observe)
 };
 
 __global__ void reset_kernel(const ResetParams p) {
@@ -331,7 +334,7 @@ __global__ void observe_masked_kernel(const ResetParams p, int32_t* obs, int obs
     env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
     int32_t* row = obs + e * obs_dim;
     for (int i = 0; i < obs_dim; i++) row[i] = 0;
-    if (dc.c.n_beams > 0) lidar_observe(env, dc, row);
+    if (dc.c.n_beams > 0) lidar_observe(env, dc, row, reinterpret_cast<const int8_t*>(p.zero_byte));
 }
 
 __global__ void set_cfg_kernel(const int32_t* src, uint8_t* dst, long long n, int n_cfgs, uint32_t* err) {
@@ -380,6 +383,7 @@ struct ngw_handle {
     std::vector<DevConfig> h_cfgs;
     int8_t* map = nullptr; uchar4* pose = nullptr; int32_t* inv = nullptr; uint8_t* cfg_id = nullptr;
     uint32_t* episode = nullptr; int32_t* ep_len = nullptr; uint32_t* err = nullptr; double* stats = nullptr;
+    uint8_t* zero_byte = nullptr;
     long long launches = 0;
     // host-buffer path
     cudaStream_t hs[HOST_STREAMS] = {nullptr, nullptr, nullptr};
@@ -399,7 +403,7 @@ void ngw_destroy(ngw_handle* h) {
     cudaSetDevice(h->device);
     for (auto p : h->d_luts) cudaFree(p);
     cudaFree(h->d_cfgs); cudaFree(h->map); cudaFree(h->pose); cudaFree(h->inv); cudaFree(h->cfg_id);
-    cudaFree(h->episode); cudaFree(h->ep_len); cudaFree(h->err); cudaFree(h->stats);
+    cudaFree(h->episode); cudaFree(h->ep_len); cudaFree(h->err); cudaFree(h->stats); cudaFree(h->zero_byte);
     cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_done); cudaFree(h->h_cost);
     cudaFree(h->h_result);
     for (int i = 0; i < HOST_STREAMS; i++)
@@ -490,6 +494,8 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
     CK(cudaMalloc(&h->ep_len, (size_t)h->np * 4));
     CK(cudaMalloc(&h->err, (size_t)h->np * 4));
     CK(cudaMalloc(&h->stats, sizeof(double) * NGW_STAT_SLOTS * NGW_STAT_COUNT));
+    CK(cudaMalloc(&h->zero_byte, 16));
+    CK(cudaMemset(h->zero_byte, 0, 16));
     CK(cudaMemset(h->map, 0, (size_t)h->np * h->cells));
     CK(cudaMemset(h->pose, 0, (size_t)h->np * 4));
     CK(cudaMemset(h->inv, 0, (size_t)h->np * h->inv_stride * 4));
@@ -504,7 +510,7 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
     h->obs_bytes = 128 * (h->obs_dim > 0 ? h->obs_dim : 0);
     h->region_bytes = 16 + h->map_bytes + h->inv_bytes + h->obs_bytes;
     h->region_bytes = (h->region_bytes + 127) & ~127;
-    int warps = 4;
+    int warps = 2;                                     // 2 tiles per CTA balances 65536-env batches best over 148 SMs
     while (warps > 1 && warps * h->region_bytes > 56 * 1024) warps >>= 1;
     if (warps * h->region_bytes > 227 * 1024) { ngw_destroy(h); return fail("ngw_create: map too large for shared memory"); }
     if (const char* w = getenv("NGW_WARPS")) {                      // tuning knob: warps (tiles) per CTA, 1..4
@@ -562,7 +568,7 @@ static ResetParams reset_params(ngw_handle* h, const uint8_t* mask, int phase) {
     ResetParams p;
     p.dcfgs = h->d_cfgs; p.map = h->map; p.pose = h->pose; p.inv = h->inv; p.cfg_id = h->cfg_id; p.episode = h->episode;
     p.ep_len = h->ep_len; p.err = h->err; p.mask = mask; p.n_envs = h->n; p.first_gid = h->first_gid; p.seed = h->seed;
-    p.ms = h->ms; p.cells = h->cells; p.inv_stride = h->inv_stride; p.phase = phase;
+    p.ms = h->ms; p.cells = h->cells; p.inv_stride = h->inv_stride; p.phase = phase; p.zero_byte = h->zero_byte;
     return p;
 }
 

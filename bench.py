@@ -200,12 +200,24 @@ def run_ours(args, rank, world, local_rank):
     g_steps = max(g_steps, 1)
     stream = torch.cuda.Stream(dev)
 
+    n_streams = int(os.environ.get('BENCH_STREAMS', '1'))
+    side = [torch.cuda.Stream(dev) for _ in range(n_streams)] if n_streams > 1 else []
+
     def capture(n):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.stream(stream):
             with torch.cuda.graph(g, stream=stream):
-                for i in range(n):
-                    one_step(i)
+                if not side:
+                    for i in range(n):
+                        one_step(i)
+                else:                                   # independent batches on parallel branches of the graph
+                    for s_ in side:
+                        s_.wait_stream(stream)
+                    for i in range(n):
+                        with torch.cuda.stream(side[(i % n_batches) % n_streams]):
+                            one_step(i)
+                    for s_ in side:
+                        stream.wait_stream(s_)
         return g
 
     graph = capture(g_steps)

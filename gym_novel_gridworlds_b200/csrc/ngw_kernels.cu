@@ -89,6 +89,7 @@ struct StepParams {
     int ms, cells, inv_stride, obs_dim;
     int map_bytes, inv_bytes, obs_bytes, region_bytes;   // per-warp shared-memory carve-up
     int auto_reset, max_episode_steps;
+    int plain_store;            // 1 => write tiles back with ordinary coalesced stores instead of TMA bulk stores
 };
 
 // Kernel argument block: the parameters plus up to NC configs INLINE, so that every config read in the hot path
@@ -133,6 +134,9 @@ __device__ __noinline__ uint32_t auto_reset_env(const StepParams& p, const ngw_c
 template <bool kTma, int NC>
 __global__ void __launch_bounds__(128, 4) step_kernel(const __grid_constant__ StepArgs<NC> args) {
     extern __shared__ __align__(128) unsigned char smem[];
+    // Programmatic dependent launch: let the next kernel of the stream start scheduling its CTAs now; everything up
+    // to griddepcontrol.wait below touches no global memory, so it overlaps the previous kernel's tail.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const StepParams& p = args.p;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     const long long e0 = p.env_begin + ((long long)blockIdx.x * warps + warp) * 32;
@@ -148,12 +152,24 @@ __global__ void __launch_bounds__(128, 4) step_kernel(const __grid_constant__ St
     int32_t* sinv = reinterpret_cast<int32_t*>(region + 16 + p.map_bytes);
     int32_t* sobs = reinterpret_cast<int32_t*>(region + 16 + p.map_bytes + p.inv_bytes);
 
-    // ---- stage the tile: grid rows + inventory rows (state arrays are padded, a full tile is always readable)
+    // ---- prologue without global memory: barrier, zero pad, zeroed observation tile
     const int8_t* gmap = p.map + e0 * p.cells;
     int32_t* ginv = p.inv + e0 * p.inv_stride;
+    if (lane == 0) {
+        if (kTma) mbar_init(bar, 1);
+        *reinterpret_cast<uint64_t*>(szero) = 0ull;
+    }
+    if (p.obs != nullptr) {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* o4 = reinterpret_cast<uint4*>(sobs);
+        for (int i = lane; i < (p.obs_bytes >> 4); i += 32) o4[i] = z;
+    }
+    __syncwarp();                                                    // barrier init visible before anyone waits on it
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // previous kernel of the stream done + visible
+
+    // ---- stage the tile: grid rows + inventory rows (state arrays are padded, a full tile is always readable)
     if (kTma) {
         if (lane == 0) {
-            mbar_init(bar, 1);
             mbar_expect_tx(bar, (uint32_t)(p.map_bytes + p.inv_bytes));
             bulk_g2s(smap, gmap, (uint32_t)p.map_bytes, bar);
             bulk_g2s(sinv, ginv, (uint32_t)p.inv_bytes, bar);
@@ -162,21 +178,14 @@ __global__ void __launch_bounds__(128, 4) step_kernel(const __grid_constant__ St
         warp_copy16(smap, gmap, p.map_bytes, lane);
         warp_copy16(sinv, ginv, p.inv_bytes, lane);
     }
-    if (lane == 0) *reinterpret_cast<uint64_t*>(szero) = 0ull;
-    __syncwarp();                                                    // barrier init visible before anyone waits on it
 
-    // ---- while the copies fly: per-lane scalars and zeroing of the observation tile
+    // ---- while the copies fly: per-lane scalars
     uchar4 ps = p.pose[e];
     const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[e];
     const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
     const ngw_config& cfg = dc.c;
     int action = 0;
     if (p.actions != nullptr && valid) action = p.actions[e];
-    if (p.obs != nullptr) {
-        uint4 z = make_uint4(0, 0, 0, 0);
-        uint4* o4 = reinterpret_cast<uint4*>(sobs);
-        for (int i = lane; i < (p.obs_bytes >> 4); i += 32) o4[i] = z;
-    }
 
     if (kTma) mbar_wait(bar, 0);
     __syncwarp();
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(128, 4) step_kernel(const __grid_constant__ St
 
     // ---- write back: inventory tile (only when stepping) and observation tile
     __syncwarp();
-    if (kTma && full_tile) {
+    if (kTma && full_tile && !p.plain_store) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -377,7 +386,7 @@ struct ngw_handle {
     unsigned long long seed = 0;
     int ms = 0, cells = 0, inv_stride = 0, obs_dim = 0, n_cfgs = 0;
     int map_bytes = 0, inv_bytes = 0, obs_bytes = 0, region_bytes = 0, warps = 4;
-    bool use_tma = true, collect_stats = true, force_global_cfg = false;
+    bool use_tma = true, collect_stats = true, force_global_cfg = false, plain_store = false, use_pdl = true;
     DevConfig* d_cfgs = nullptr;
     std::vector<int16_t*> d_luts;
     std::vector<DevConfig> h_cfgs;
@@ -426,6 +435,8 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
     h->use_tma = getenv("NGW_NO_TMA") == nullptr;
     h->collect_stats = getenv("NGW_NO_STATS") == nullptr;
     h->force_global_cfg = getenv("NGW_GLOBAL_CFG") != nullptr;
+    h->plain_store = getenv("NGW_PLAIN_STORE") != nullptr;
+    h->use_pdl = getenv("NGW_NO_PDL") == nullptr;
     for (int i = 0; i < n_cfgs; i++) {
         const ngw_config& c = cfgs[i];
         if (c.n_items < 1 || c.n_items > NGW_MAX_ITEMS || c.n_actions < 0 || c.n_actions > NGW_MAX_ACTIONS ||
@@ -607,6 +618,7 @@ static StepParams step_params(ngw_handle* h, const int32_t* actions, int32_t* ob
     p.ms = h->ms; p.cells = h->cells; p.inv_stride = h->inv_stride; p.obs_dim = h->obs_dim;
     p.map_bytes = h->map_bytes; p.inv_bytes = h->inv_bytes; p.obs_bytes = h->obs_bytes;
     p.region_bytes = h->region_bytes; p.auto_reset = auto_reset; p.max_episode_steps = max_episode_steps;
+    p.plain_store = h->plain_store ? 1 : 0;
     return p;
 }
 
@@ -617,8 +629,19 @@ static void launch_step_nc(ngw_handle* h, const StepParams& p, int blocks, size_
     static StepArgs<NC> args;                       // host staging of the argument block (copied by the launch)
     args.p = p;
     for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
-    if (h->use_tma) step_kernel<true, NC><<<blocks, 32 * h->warps, smem, s>>>(args);
-    else step_kernel<false, NC><<<blocks, 32 * h->warps, smem, s>>>(args);
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(blocks); lc.blockDim = dim3(32 * h->warps); lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    // PDL pays off for eager launches (launch latency hidden behind the previous kernel's tail); inside a CUDA graph
+    // the kernels are already back to back and early-resident dependents only take shared memory away.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cap);
+    lc.attrs = attr; lc.numAttrs = (h->use_pdl && cap == cudaStreamCaptureStatusNone) ? 1 : 0;
+    if (h->use_tma) cudaLaunchKernelEx(&lc, step_kernel<true, NC>, args);
+    else cudaLaunchKernelEx(&lc, step_kernel<false, NC>, args);
 }
 
 static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {

@@ -42,6 +42,46 @@ def build_c2_chain(num_envs=1, device=None):
     return gym.LidarInFront(env, num_beams=8)
 
 
+def build_workload(name):
+    """BASELINE.json configs -> (description, [compiled configs], envs per batch per GPU, cfg-id rule, step kwargs).
+    C2 is the headline (default); C3-C5 are extra measurements (`--workload`)."""
+    import numpy as np
+    import gym_novel_gridworlds_b200 as gym
+    from gym_novel_gridworlds_b200.compiler import compile_chain
+
+    def pogo(extra_actions=(), map_size=10):
+        env = gym.make('NovelGridworld-Pogostick-v1')
+        env.map_size = map_size
+        env = gym.LimitActions(env, set(C2_SET) | set(extra_actions))
+        return gym.LidarInFront(env, num_beams=8)
+
+    if name == 'C2':
+        return ("C2: NovelGridworld-Pogostick-v1 + LimitActions(10) + LidarInFront(8), 65536 envs/batch, "
+                "uniform random actions", [compile_chain(pogo())], 65536, None, {})
+    if name == 'C3':
+        env = gym.make('NovelGridworld-Bow-v1')
+        env = gym.LidarInFront(env, num_beams=8)
+        env = gym.inject_novelty(env, 'axe', 'medium', 'wooden', '')
+        env = gym.inject_novelty(env, 'fence', 'hard', 'oak', '')
+        return ("C3: NovelGridworld-Bow-v1 + LidarInFront(8) + axe(medium, wooden) + fence(hard, oak), 262144 envs/batch",
+                [compile_chain(env)], 262144, None, {})
+    if name in ('C4', 'C4-blocked'):
+        np.random.seed(4)
+        chains = [gym.inject_novelty(pogo(['Chop']), 'addchop'), gym.inject_novelty(pogo(['Jump']), 'addjump'),
+                  gym.inject_novelty(pogo(), 'additem', 'medium', 'spring'),
+                  gym.inject_novelty(pogo(), 'remapaction', 'hard')]
+        rule = 'interleaved' if name == 'C4' else 'blocked'
+        return ("C4: Pogostick-v1 + LimitActions + LidarInFront(8), per-env novelty addchop / addjump / additem(medium) / "
+                "remapaction(hard), config ids %s, 1048576 envs/batch, one launch per step" % rule,
+                [compile_chain(c) for c in chains], 1048576, rule, {})
+    if name == 'C5':
+        env = gym.inject_novelty(pogo(map_size=40), 'additem', 'hard', 'spring')
+        return ("C5: Pogostick-v1 map_size 40 + additem(hard) + LidarInFront(8), 524288 envs/batch per GPU, fused "
+                "auto-reset, max_episode_steps 256 (harness truncation knob)",
+                [compile_chain(env)], 524288, None, {'auto_reset': True, 'max_episode_steps': 256})
+    raise ValueError(name)
+
+
 def algorithmic_bytes_per_env_step(cc):
     """read ms^2 + 4 (pose) + 4 I (inventory) + 4 (action); write 4 (pose) + 4 I + 4 (L B + I_obs)
     + 4 (reward) + 4 (step_cost) + 1 (done) + 1 (result); grid write-back counted as 0."""
@@ -160,7 +200,6 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from gym_novel_gridworlds_b200.compiler import compile_chain
     from gym_novel_gridworlds_b200.runtime import BatchHandle
 
     torch.cuda.set_device(local_rank)
@@ -168,23 +207,37 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    cc = compile_chain(build_c2_chain())
-    bytes_step = algorithmic_bytes_per_env_step(cc)
-    per_batch_ws = ENVS_PER_BATCH * bytes_step
-    n_batches = max(2, int(np.ceil(1.6 * 126e6 / per_batch_ws)))       # combined working set ~1.6x L2
-    batches = []
-    for b in range(n_batches):
-        gid0 = (rank * n_batches + b) * ENVS_PER_BATCH
-        h = BatchHandle([cc], ENVS_PER_BATCH, device=dev, seed=0, first_env_gid=gid0)
-        h.reset()
-        batches.append(h)
+    desc, compiled, envs, cfg_rule, step_kw = build_workload(args.workload)
+    n_cfg = len(compiled)
+    # algorithmic bytes: mean over the configs of the batch (+1 byte config id per env when mixed)
+    bytes_step = float(np.mean([algorithmic_bytes_per_env_step(cc) for cc in compiled])) + (1 if n_cfg > 1 else 0)
+    per_batch_ws = envs * bytes_step
+    n_batches = max(2, int(np.ceil(1.6 * 126e6 / per_batch_ws)))       # combined working set >= 1.6x L2
+    batches, act_sets = [], []
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    acts = [torch.randint(0, cc.c.n_actions, (ENVS_PER_BATCH,), generator=gen, device=dev, dtype=torch.int32)
-            for _ in range(N_ACTION_SETS)]
+    for b in range(n_batches):
+        gid0 = (rank * n_batches + b) * envs
+        cfg_id = None
+        if n_cfg > 1:
+            idx = np.arange(envs, dtype=np.int64)
+            cfg_id = (idx % n_cfg) if cfg_rule == 'interleaved' else np.minimum(idx * n_cfg // envs, n_cfg - 1)
+        h = BatchHandle(compiled, envs, device=dev, seed=0, first_env_gid=gid0, cfg_id=cfg_id)
+        h.reset()
+        if step_kw.get('max_episode_steps', 0) > 0:                     # stagger episode ages so truncation-resets spread evenly
+            h.ep_len.copy_(torch.randint(0, step_kw['max_episode_steps'], (envs,), generator=gen, device=dev,
+                                         dtype=torch.int32))
+        batches.append(h)
+    n_act = torch.tensor([cc.c.n_actions for cc in compiled], device=dev, dtype=torch.int64)
+    per_env_n = n_act[batches[0].cfg_id.long()]
+    n_sets = N_ACTION_SETS if envs <= 262144 else 4
+    for _ in range(n_sets):
+        r = torch.randint(0, 1 << 30, (envs,), generator=gen, device=dev, dtype=torch.int64)
+        act_sets.append((r % per_env_n).to(torch.int32))
+    flags = sum(int((h.error_flags != 0).sum().item()) for h in batches)
 
     def one_step(i):
-        batches[i % n_batches].step(acts[i % N_ACTION_SETS])
+        batches[i % n_batches].step(act_sets[i % n_sets], **step_kw)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -200,11 +253,9 @@ def run_ours(args, rank, world, local_rank):
     g_steps = max(g_steps, 1)
     stream = torch.cuda.Stream(dev)
 
-    n_streams = int(os.environ.get('BENCH_STREAMS', '1'))
-    side = [torch.cuda.Stream(dev) for _ in range(n_streams)] if n_streams > 1 else []
-
-    def capture(n):
+    def capture(n, n_streams=1):
         g = torch.cuda.CUDAGraph()
+        side = [torch.cuda.Stream(dev) for _ in range(n_streams)] if n_streams > 1 else []
         with torch.cuda.stream(stream):
             with torch.cuda.graph(g, stream=stream):
                 if not side:
@@ -220,34 +271,42 @@ def run_ours(args, rank, world, local_rank):
                         stream.wait_stream(s_)
         return g
 
+    def timed(graph, replays, graph_rem):
+        with torch.cuda.stream(stream):
+            graph.replay()                                               # graph warm-up (uploads the exec graph)
+            if graph_rem:
+                graph_rem.replay()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(replays):
+                graph.replay()
+            if graph_rem:
+                graph_rem.replay()
+            ev1.record(stream)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        return ev0.elapsed_time(ev1), t0, time.perf_counter()
+
     graph = capture(g_steps)
     launches_per_step = (sum(h.launch_count() for h in batches) - launches_before) / g_steps
     replays, rem = K // g_steps, K % g_steps
     graph_rem = capture(rem) if rem else None
-    with torch.cuda.stream(stream):
-        graph.replay()                                                   # graph warm-up (uploads the exec graph)
-        if graph_rem:
-            graph_rem.replay()
-    torch.cuda.synchronize(dev)
 
-    # ---- timed region: exactly K steps, CUDA events on the launching stream, barrier + sync on both sides
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for _ in range(replays):
-            graph.replay()
-        if graph_rem:
-            graph_rem.replay()
-        ev1.record(stream)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    t_wall1 = time.perf_counter()
-    ms_total = ev0.elapsed_time(ev1)
+    # ---- timed region: exactly K steps, one stream, CUDA events on the launching stream, barrier + sync both sides
+    ms_total, t_wall0, t_wall1 = timed(graph, replays, graph_rem)
+
+    # ---- same K steps with independent batches overlapped on 3 parallel graph branches (extra figure)
+    n_ov = min(3, n_batches)
+    graph_ov = capture(g_steps, n_ov)
+    graph_ov_rem = capture(rem, n_ov) if rem else None
+    ms_overlap, _, _ = timed(graph_ov, replays, graph_ov_rem)
 
     # ---- eager (one python call per launch) figure, for the launch-bound picture
     n_eager = min(K, 2000)
@@ -261,17 +320,17 @@ def run_ours(args, rank, world, local_rank):
     eager_ms = e0.elapsed_time(e1) / n_eager
 
     # ---- end-to-end through the host-buffer C-ABI call (ngw_step_host), pinned buffers, every step H2D + D2H
-    n_e2e = min(K, 200)
-    host_acts = [a.cpu().numpy() for a in acts]
-    for i in range(3):
-        batches[i % n_batches].step_host(host_acts[i % N_ACTION_SETS])
+    n_e2e = min(K, 200 if envs <= 65536 else 40)
+    host_acts = [a.cpu().numpy() for a in act_sets]
+    for i in range(max(3, n_batches)):                                  # every handle allocates its pinned buffers here
+        batches[i % n_batches].step_host(host_acts[i % n_sets], **step_kw)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     checksum = 0.0
     for i in range(n_e2e):
-        obs, rew, dn, cost, res = batches[i % n_batches].step_host(host_acts[i % N_ACTION_SETS])
+        obs, rew, dn, cost, res = batches[i % n_batches].step_host(host_acts[i % n_sets], **step_kw)
         checksum += float(rew[0]) + float(obs[0, 0])                    # touch the results on the host
     t_e2e = time.perf_counter() - t0
     t_timed_end = time.perf_counter()
@@ -283,54 +342,59 @@ def run_ours(args, rank, world, local_rank):
     stats = torch.zeros(8, dtype=torch.float64, device=dev)
     for h in batches:
         stats += h.stats()
-    times = torch.tensor([ms_total, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, t_e2e * 1e3, ms_overlap], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)                     # max over ranks
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)                     # episode statistics over NCCL
-    ms_total, e2e_ms_total = float(times[0].item()), float(times[1].item())
+    ms_total, e2e_ms_total, ms_overlap = [float(x) for x in times.cpu().numpy()]
 
     if rank == 0:
         ms_per_step = ms_total / K
-        value = world * ENVS_PER_BATCH * K / (ms_total * 1e-3)
+        value = world * envs * K / (ms_total * 1e-3)
         peak, peak_src = measured_hbm_peak()
-        achieved = ENVS_PER_BATCH * bytes_step / (ms_per_step * 1e-3) / 1e9
+        achieved = envs * bytes_step / (ms_per_step * 1e-3) / 1e9
+        ov_achieved = envs * bytes_step / (ms_overlap / K * 1e-3) / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')) as f:
-                traffic = json.load(f).get('dram_bytes_per_launch')
+                traffic = json.load(f).get(args.workload, {}).get('dram_bytes_per_launch')
         except Exception:
             pass
+        d_obs = batches[0].obs_dim
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "C2: NovelGridworld-Pogostick-v1 + LimitActions(10) + LidarInFront(8), "
-                                   "65536 envs/batch, uniform random actions",
-                       "envs_per_batch": ENVS_PER_BATCH, "batches_rotated": n_batches,
+            "config": {"workload": desc, "envs_per_batch": envs, "batches_rotated": n_batches,
                        "l2": "inputs larger than L2: %d rotating batches, %.0f MB combined working set vs 126 MB L2"
                              % (n_batches, n_batches * per_batch_ws / 1e6),
-                       "launch": "CUDA-graph replay of %d-step graphs; eager python loop = %.2f us/step"
-                                 % (g_steps, eager_ms * 1e3),
-                       "per_gpu_envs": n_batches * ENVS_PER_BATCH, "parallelism": "independent shards x%d" % world},
+                       "launch": "one stream, CUDA-graph replay of %d-step graphs (one kernel launch per step); eager "
+                                 "python loop = %.2f us/step" % (g_steps, eager_ms * 1e3),
+                       "per_gpu_envs": n_batches * envs, "parallelism": "independent shards x%d" % world,
+                       "reset_error_flags": flags},
             "clocks": clocks,
-            "e2e": {"value": world * ENVS_PER_BATCH * n_e2e / (e2e_ms_total * 1e-3), "unit": "env-steps/s",
-                    "h2d_bytes_per_step": 4 * ENVS_PER_BATCH,
-                    "d2h_bytes_per_step": (4 * cc.obs_dim + 4 + 4 + 1 + 1) * ENVS_PER_BATCH,
-                    "steps": n_e2e, "api": "ngw_step_host (pinned host buffers, 8 chunks over 3 streams)"},
+            "e2e": {"value": world * envs * n_e2e / (e2e_ms_total * 1e-3), "unit": "env-steps/s",
+                    "h2d_bytes_per_step": 4 * envs,
+                    "d2h_bytes_per_step": (4 * d_obs + 4 + 4 + 1 + 1) * envs,
+                    "steps": n_e2e, "api": "ngw_step_host (pinned host buffers: H2D actions, one launch, D2H obs/reward/done/step_cost/result)"},
             "gpu_launches": int(round(launches_per_step * K)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "ngw::step_kernel<true>", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "ngw::step_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": bytes_step,
-                         "algorithmic_bytes_per_launch": ENVS_PER_BATCH * bytes_step,
+                         "algorithmic_bytes_per_launch": envs * bytes_step,
                          "avg_launch_us": ms_per_step * 1e3},
-            "eager": {"value": ENVS_PER_BATCH / (eager_ms * 1e-3), "unit": "env-steps/s", "us_per_step": eager_ms * 1e3},
+            "overlapped": {"note": "same K steps, independent batches on %d parallel graph branches (launches overlap)"
+                                   % n_ov, "value": world * envs * K / (ms_overlap * 1e-3), "unit": "env-steps/s",
+                           "us_per_step": ms_overlap / K * 1e3, "achieved_gbs": ov_achieved,
+                           "frac_of_hbm_peak": ov_achieved / peak},
+            "eager": {"value": envs / (eager_ms * 1e-3), "unit": "env-steps/s", "us_per_step": eager_ms * 1e3},
             "episode_stats": dict(zip(('steps', 'episodes', 'successes', 'reward_sum', 'cost_sum', 'resets',
                                        'invalid'), [float(x) for x in stats.cpu().numpy()[:7]])),
             "wall_ms_timed_region": (t_wall1 - t_wall0) * 1e3,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == 'C2':
             threads = os.cpu_count() or 1
-            steps_cpu, dt = cpu_port_run(cc, ENVS_PER_BATCH, 10 ** 9, 16, threads, time_budget_s=3.0)
+            steps_cpu, dt = cpu_port_run(compiled[0], ENVS_PER_BATCH, 10 ** 9, 16, threads, time_budget_s=3.0)
             line["cpu_baseline"] = {
                 "value": steps_cpu * ENVS_PER_BATCH / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
                 "sample": "%d steps x %d envs (%.1f s wall, ~%.0f s of CPU work), C port of the reference path "
@@ -348,6 +412,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=64)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='C2', choices=['C2', 'C3', 'C4', 'C4-blocked', 'C5'])
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

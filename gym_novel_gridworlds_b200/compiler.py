@@ -173,6 +173,15 @@ def compile_chain(top):
     if len(prog.ops) > oc.MAX_RESET_OPS:
         raise ValueError("more than %d reset post-ops" % oc.MAX_RESET_OPS)
     cfg.n_reset_ops = len(prog.ops)
+    replaced_wall = False
+    for kind, a, b, lo, hi in prog.ops:
+        if kind == oc.RESET_REPLACE and a == cfg.id_wall:
+            replaced_wall = True
+        if kind == oc.RESET_FENCE and replaced_wall:
+            # the reference's Fence.reset then fences around BORDER cells and add_fence_around indexes outside the
+            # grid (IndexError, or a silent wrap to the opposite border) — pogostick_v1_env.py:533
+            raise NotImplementedError("fence / fencerestriction outside a wall-replacing novelty: the reference "
+                                      "raises IndexError in add_fence_around for this chain")
     for i, (kind, a, b, lo, hi) in enumerate(prog.ops):
         op = cfg.reset_ops[i]
         op.kind, op.a, op.b, op.lo, op.hi = kind, a, b, lo, hi

@@ -325,52 +325,64 @@ struct DevConfig {
 };
 
 // obs row must be zero-filled for the lidar part by the caller; `zero` points at a byte that always reads 0 and lives in
-// the same address space as the grid row.
-__device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& dc, int32_t* obs, const int8_t* zero) {
+// the same address space as the grid row.  A tile can be shared by G warps: warp `g` of `G` casts beams
+// [g*NB, (g+1)*NB) with NB = 8/G (fast path) or beams g, g+G, ... (generic path).
+template <int NB>
+__device__ __forceinline__ void lidar_fast(const EnvRow& e, const DevConfig& dc, int32_t* obs, const int8_t* zero, int b0) {
+    // Each beam keeps a running cell pointer; axis beams advance one unit step per sample, diagonal beams advance
+    // when round(0.71 k) grows (disp[1][k] - disp[1][k-1] is 0 or 1).  A beam that lands parks on `zero`, a cell
+    // that always reads air, so no per-beam "still flying" test is needed in the loop.
+    const ngw_config& cfg = dc.c;
+    const int K = cfg.max_range, L = cfg.n_lidar_items;
+    int u[NB];
+    const int8_t* at[NB];
+    uint32_t hit[NB];                                                 // (sample index << 8) | item id, 0 = still flying
+    const int8_t* base = e.m + e.r * e.ms + e.c;
+#pragma unroll
+    for (int j = 0; j < NB; j++) { u[j] = dc.lidar.unit[e.facing][b0 + j]; at[j] = base; hit[j] = 0; }
+    int prev0 = 0, prev1 = 0, flying = NB;
+    for (int k = 0; k < K && flying > 0; k++) {
+        const int d0 = dc.lidar.disp[0][k], d1 = dc.lidar.disp[1][k];
+        const int s0 = d0 - prev0, s1 = d1 - prev1;                   // warp-uniform step counts (0 or 1 for 8 beams)
+        prev0 = d0; prev1 = d1;
+        int id[NB];
+#pragma unroll
+        for (int j = 0; j < NB; j++) {                                // NB independent shared-memory reads in flight
+            at[j] += u[j] * (((b0 + j) & 1) ? s1 : s0);
+            id[j] = *at[j];
+        }
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            bool lands = id[j] != 0;                                  // first non-air cell ends the beam (obsw:58-66)
+            hit[j] = lands ? (uint32_t)(((k + 1) << 8) | (id[j] & 0xFF)) : hit[j];
+            u[j] = lands ? 0 : u[j];
+            at[j] = lands ? zero : at[j];
+            flying -= lands ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        if (hit[j]) {
+            int slot = cfg.lidar_slot[hit[j] & 0xFF];                 // -1: occludes but is not a lidar item (Q2)
+            if (slot >= 0) obs[(b0 + j) * L + slot] = (int)(hit[j] >> 8);
+        }
+    }
+}
+
+__device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& dc, int32_t* obs, const int8_t* zero,
+                                              int g, int G, bool with_tail) {
     const ngw_config& cfg = dc.c;
     const int B = cfg.n_beams, K = cfg.max_range, L = cfg.n_lidar_items;
-    const int cells = e.ms * e.ms;
-    const int pos = e.r * e.ms + e.c;
     if (dc.lidar.fast) {
-        // Each beam keeps a running cell pointer; axis beams advance one unit step per sample, diagonal beams advance
-        // when round(0.71 k) grows (disp[1][k] - disp[1][k-1] is 0 or 1).  A beam that lands parks on `zero`, a cell
-        // that always reads air, so no per-beam "still flying" test is needed in the loop.
-        int u[8];
-        const int8_t* at[8];
-        uint32_t hit[8];                                              // (sample index << 8) | item id, 0 = still flying
-        const int8_t* base = e.m + pos;
-#pragma unroll
-        for (int b = 0; b < 8; b++) { u[b] = dc.lidar.unit[e.facing][b]; at[b] = base; hit[b] = 0; }
-        int prev0 = 0, prev1 = 0, flying = 8;
-        for (int k = 0; k < K && flying > 0; k++) {
-            const int d0 = dc.lidar.disp[0][k], d1 = dc.lidar.disp[1][k];
-            const int s0 = d0 - prev0, s1 = d1 - prev1;               // warp-uniform step counts (0 or 1 for 8 beams)
-            prev0 = d0; prev1 = d1;
-            int id[8];
-#pragma unroll
-            for (int b = 0; b < 8; b++) {                             // 8 independent shared-memory reads in flight
-                at[b] += u[b] * ((b & 1) ? s1 : s0);
-                id[b] = *at[b];
-            }
-#pragma unroll
-            for (int b = 0; b < 8; b++) {
-                bool lands = id[b] != 0;                              // first non-air cell ends the beam (obsw:58-66)
-                hit[b] = lands ? (uint32_t)(((k + 1) << 8) | (id[b] & 0xFF)) : hit[b];
-                u[b] = lands ? 0 : u[b];
-                at[b] = lands ? zero : at[b];
-                flying -= lands ? 1 : 0;
-            }
-        }
-#pragma unroll
-        for (int b = 0; b < 8; b++) {
-            if (hit[b]) {
-                int slot = cfg.lidar_slot[hit[b] & 0xFF];             // -1: occludes but is not a lidar item (Q2)
-                if (slot >= 0) obs[b * L + slot] = (int)(hit[b] >> 8);
-            }
-        }
+        if (G == 1) lidar_fast<8>(e, dc, obs, zero, 0);
+        else if (G == 2) lidar_fast<4>(e, dc, obs, zero, g * 4);
+        else if (G == 4) lidar_fast<2>(e, dc, obs, zero, g * 2);
+        else lidar_fast<1>(e, dc, obs, zero, g);
     } else {
-        const int16_t* row = dc.lidar.lut + e.facing * B * K;
-        for (int b = 0; b < B; b++, row += K) {
+        const int cells = e.ms * e.ms;
+        const int pos = e.r * e.ms + e.c;
+        for (int b = g; b < B; b += G) {
+            const int16_t* row = dc.lidar.lut + (e.facing * B + b) * K;
             for (int k = 0; k < K; k++) {
                 int idx = pos + row[k];
                 if ((unsigned)idx >= (unsigned)cells) break;
@@ -383,115 +395,216 @@ __device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& 
             }
         }
     }
-    const int n_tail = cfg.n_inv_obs;
-    int32_t* tail = obs + L * B;
-    for (int i = 0; i < n_tail; i++) tail[i] = e.inv[cfg.inv_obs_item[i]];    // sorted-name order (Q7)
+    if (with_tail) {
+        const int n_tail = cfg.n_inv_obs;
+        int32_t* tail = obs + L * B;
+        for (int i = 0; i < n_tail; i++) tail[i] = e.inv[cfg.inv_obs_item[i]];   // sorted-name order (Q7)
+    }
 }
 
 // ------------------------------------------------------------------ reset (pogostick_v1_env.py:86-181 + novelty resets)
-// Same DISTRIBUTION as the reference, not the same stream: the reference draws uniformly from a list it
-// shrinks by popping every drawn cell; a popped cell is either the agent cell, a placed item or a cell that
-// can never become placeable again, so "first placeable cell in a uniformly random order" == uniform over
-// the currently placeable cells == draw-with-replacement-until-placeable, which needs no list.
-__device__ __forceinline__ bool placeable(const EnvRow& e, int r, int c) {
-    return cell(e, r, c) == 0 && cell(e, r - 1, c) == 0 && cell(e, r + 1, c) == 0 && cell(e, r, c - 1) == 0 &&
-           cell(e, r, c + 1) == 0;
+// WARP-COOPERATIVE: the 32 lanes of one warp regenerate ONE environment (rows in shared or global memory).
+//
+// Same DISTRIBUTION as the reference, not the same stream:
+//  * placement: the reference draws uniformly from a list it shrinks by popping every drawn cell; a popped cell is the
+//    agent cell, a placed item or a cell that can never become placeable again, so "first placeable cell in a uniformly
+//    random order" == uniform over the currently placeable cells == draw-with-replacement-until-placeable (no list).
+//    These few draws are computed redundantly by all lanes (identical Philox counters), lane 0 writes.
+//  * post-ops ("shuffle the candidate cells, take the first m", m = ceil(n * (pct / 100)) in IEEE doubles as NumPy does):
+//    a uniformly random m-subset.  Every candidate cell gets an independent 32-bit Philox key (counter = cell index) and
+//    the m smallest keys win — found with a warp radix-select (256-bin histogram in shared memory) and, inside the
+//    boundary bin, an exact rank by (key, cell index).  Key ties (probability ~ n^2 / 2^33) fall back to index order.
+__device__ __forceinline__ bool placeable(const int8_t* m, int ms, int r, int c) {
+    const int8_t* p = m + r * ms + c;
+    return p[0] == 0 && p[-ms] == 0 && p[ms] == 0 && p[-1] == 0 && p[1] == 0;
 }
 
-__device__ __noinline__ uint32_t reset_base(EnvRow& e, const ngw_config* cfg, int inv_stride, uint64_t seed, uint64_t gid, uint32_t episode) {
-    int ms = e.ms;
-    uint32_t err = 0;
-    for (int i = 0; i < inv_stride; i++) e.inv[i] = 0;                // pogostick_v1_env.py:119-120
-    e.sel = 0;
-    int wall = cfg->id_wall;
-    for (int r = 0; r < ms; r++)                                      // pogostick_v1_env.py:129-130
-        for (int c = 0; c < ms; c++)
-            e.m[r * ms + c] = (r == 0 || c == 0 || r == ms - 1 || c == ms - 1) ? (int8_t)wall : (int8_t)0;
+__device__ __forceinline__ uint32_t philox_key(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t stream, uint32_t i) {
     Philox rng;
-    rng.init(seed, gid, episode, 0);
-    int side = ms - 4;                                                // rows/cols 2 .. ms-3 (pogostick_v1_env.py:136-138)
-    uint32_t n_av = (uint32_t)(side * side);
-    uint32_t a = rng.below(n_av);
-    e.r = 2 + (int)(a / side); e.c = 2 + (int)(a % side);             // pogostick_v1_env.py:141-142
-    e.facing = (int)rng.below(4);                                     // pogostick_v1_env.py:145
-    int agent = e.r * ms + e.c;
-    for (int i = 0; i < cfg->n_place; i++) {                          // pogostick_v1_env.py:147-148,159-181
-        int item = cfg->place_item[i], qty = cfg->place_qty[i];
-        for (int count = 0; count < qty; count++) {
-            bool placed = false;
-            for (uint32_t attempt = 0; attempt < 8 * n_av && !placed; attempt++) {
-                uint32_t d = rng.below(n_av);
-                int r = 2 + (int)(d / side), c = 2 + (int)(d % side);
-                if (r * ms + c != agent && placeable(e, r, c)) { e.m[r * ms + c] = (int8_t)item; placed = true; }
-            }
-            if (!placed) {                                            // rare: count the placeable cells exactly
-                uint32_t good = 0;
-                for (int r = 2; r <= ms - 3; r++)
-                    for (int c = 2; c <= ms - 3; c++) good += (r * ms + c != agent && placeable(e, r, c));
-                if (good == 0) { err |= NGW_ERR_PLACEMENT; i = cfg->n_place; break; }   // pogostick_v1_env.py:167
-                uint32_t pick = rng.below(good);
-                for (int r = 2; r <= ms - 3 && !placed; r++)
-                    for (int c = 2; c <= ms - 3 && !placed; c++)
-                        if (r * ms + c != agent && placeable(e, r, c)) {
-                            if (pick == 0) { e.m[r * ms + c] = (int8_t)item; placed = true; }
-                            pick--;
-                        }
+    rng.init(seed, gid, episode, stream);
+    rng.blk = 1 + i;                                                   // block 0 of the stream draws the percentage
+    rng.refill();
+    return rng.buf[0];
+}
+
+__device__ __forceinline__ bool reset_candidate(int kind, int id, int wall, int a) {
+    return kind == NGW_RESET_FENCE ? (id != 0 && id != wall)           // novelty_wrappers.py:872
+         : kind == NGW_RESET_ADDITEM ? (id == 0)                       // novelty_wrappers.py:1017
+         : (id == a);                                                  // novelty_wrappers.py:1130
+}
+
+// hist: 256 uint32 of shared memory owned by the calling warp.  Returns error flags; pose in/out (uniform over lanes).
+__device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m, int32_t* inv, int ms, int inv_stride,
+                                                uint64_t seed, uint64_t gid, uint32_t episode, bool do_base,
+                                                int op_begin, int op_end, uint32_t* hist, int& pr, int& pc, int& pf,
+                                                int& psel) {
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int cells = ms * ms;
+    const int wall = cfg->id_wall;
+    uint32_t err = 0;
+    if (do_base) {
+        for (int i = lane; i < inv_stride; i += 32) inv[i] = 0;        // pogostick_v1_env.py:119-120
+        psel = 0;
+        for (int i = lane; i < cells; i += 32) {                      // pogostick_v1_env.py:129-130
+            int r = i / ms, c = i - r * ms;
+            m[i] = (r == 0 || c == 0 || r == ms - 1 || c == ms - 1) ? (int8_t)wall : (int8_t)0;
+        }
+        __syncwarp();
+        Philox rng;
+        rng.init(seed, gid, episode, 0);
+        const int side = ms - 4;                                      // rows/cols 2 .. ms-3 (pogostick_v1_env.py:136-138)
+        const uint32_t n_av = (uint32_t)(side * side);
+        uint32_t a = rng.below(n_av);
+        pr = 2 + (int)(a / side); pc = 2 + (int)(a % side);           // pogostick_v1_env.py:141-142
+        pf = (int)rng.below(4);                                       // pogostick_v1_env.py:145
+        const int agent = pr * ms + pc;
+        for (int i = 0; i < cfg->n_place; i++) {                      // pogostick_v1_env.py:147-148,159-181
+            const int item = cfg->place_item[i], qty = cfg->place_qty[i];
+            for (int count = 0; count < qty; count++) {
+                int where = -1;
+                for (uint32_t attempt = 0; attempt < 8 * n_av && where < 0; attempt++) {
+                    uint32_t d = rng.below(n_av);
+                    int r = 2 + (int)(d / side), c = 2 + (int)(d % side);
+                    if (r * ms + c != agent && placeable(m, ms, r, c)) where = r * ms + c;
+                }
+                if (where < 0) {                                      // rare: enumerate the placeable cells exactly
+                    uint32_t good = 0;
+                    for (int r = 2; r <= ms - 3; r++)
+                        for (int c = 2; c <= ms - 3; c++) good += (r * ms + c != agent && placeable(m, ms, r, c));
+                    if (good == 0) { err |= NGW_ERR_PLACEMENT; i = cfg->n_place; break; }   // pogostick_v1_env.py:167
+                    uint32_t pick = rng.below(good);
+                    for (int r = 2; r <= ms - 3 && where < 0; r++)
+                        for (int c = 2; c <= ms - 3 && where < 0; c++)
+                            if (r * ms + c != agent && placeable(m, ms, r, c)) {
+                                if (pick == 0) where = r * ms + c;
+                                pick--;
+                            }
+                }
+                if (lane == 0) m[where] = (int8_t)item;
+                __syncwarp();
             }
         }
     }
-    return err;
-}
-
-// Post-ops [op_begin, op_end).  A uniformly random m-subset of the candidate cells (what "shuffle, take the
-// first m" selects) is drawn by selection sampling in row-major order: candidate j of n is taken with
-// probability (m - taken) / (n - j).  m = ceil(n * (pct / 100)) in IEEE doubles exactly as NumPy computes it.
-__device__ __noinline__ void reset_ops(EnvRow& e, const ngw_config* cfg, int op_begin, int op_end, uint64_t seed, uint64_t gid, uint32_t episode) {
-    int ms = e.ms, cells = ms * ms;
-    int agent = e.r * ms + e.c;
+    const int agent = pr * ms + pc;
     if (op_end > cfg->n_reset_ops) op_end = cfg->n_reset_ops;
     for (int k = op_begin; k < op_end; k++) {
         const ngw_reset_op op = cfg->reset_ops[k];
-        if (op.kind == NGW_RESET_INVSET) { e.inv[op.a] = op.lo; continue; }          // novelty_wrappers.py:33,460,668-671
-        Philox rng;
-        rng.init(seed, gid, episode, 1 + k);
-        int wall = cfg->id_wall;
+        if (op.kind == NGW_RESET_INVSET) {                            // novelty_wrappers.py:33,460,668-671
+            if (lane == 0) inv[op.a] = op.lo;
+            __syncwarp();
+            continue;
+        }
+        const uint32_t stream = 1 + k;
+        // ---- n candidates, percentage, m
         int n = 0;
-        for (int i = 0; i < cells; i++) {
-            int id = e.m[i];
-            bool cand = op.kind == NGW_RESET_FENCE ? (id != 0 && id != wall)          // novelty_wrappers.py:872
-                      : op.kind == NGW_RESET_ADDITEM ? (id == 0)                      // novelty_wrappers.py:1017
-                      : (id == op.a);                                                 // novelty_wrappers.py:1130
-            n += cand;
+        for (int i = lane; i < cells; i += 32) n += reset_candidate(op.kind, m[i], wall, op.a);
+        n = __reduce_add_sync(FULL, n);
+        Philox rng;
+        rng.init(seed, gid, episode, stream);
+        const int pct = op.lo + (int)rng.below((uint32_t)(op.hi - op.lo));            // randint(low, high), high exclusive
+        int take = (int)ceil((double)n * ((double)pct / 100.0));                      // novelty_wrappers.py:881,1025,1139
+        if (take > n) take = n;
+        if (take <= 0) continue;
+        // ---- radix-select the `take` smallest keys: after the loop, keys whose top `bits` bits are < prefix win outright,
+        //      keys whose top bits == prefix compete for the `remaining` last places
+        uint32_t prefix = 0;
+        int bits = 0, remaining = take, bin_count = n;
+        while (remaining < bin_count && bin_count > 32 && bits < 32) {
+            for (int i = lane; i < 256; i += 32) hist[i] = 0;
+            __syncwarp();
+            for (int i = lane; i < cells; i += 32) {
+                if (!reset_candidate(op.kind, m[i], wall, op.a)) continue;
+                uint32_t key = philox_key(seed, gid, episode, stream, (uint32_t)i);
+                if (bits == 0 || (key >> (32 - bits)) == prefix) atomicAdd(&hist[(key >> (24 - bits)) & 0xFF], 1u);
+            }
+            __syncwarp();
+            uint32_t mine[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { mine[j] = hist[lane * 8 + j]; sum += mine[j]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            uint32_t excl = incl - sum;
+            bool owner = (uint32_t)remaining > excl && (uint32_t)remaining <= incl;   // the bin holding the remaining-th key
+            int bin = 0; uint32_t below = excl, cnt = 0;
+            if (owner) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (cnt == 0) {
+                        if ((uint32_t)remaining <= below + mine[j]) { bin = lane * 8 + j; cnt = mine[j]; }
+                        else below += mine[j];
+                    }
+                }
+            }
+            int src = __ffs(__ballot_sync(FULL, owner)) - 1;
+            bin = __shfl_sync(FULL, bin, src);
+            below = __shfl_sync(FULL, below, src);
+            cnt = __shfl_sync(FULL, cnt, src);
+            prefix = (prefix << 8) | (uint32_t)bin;
+            bits += 8;
+            remaining -= (int)below;
+            bin_count = (int)cnt;
+            __syncwarp();
         }
-        int pct = op.lo + (int)rng.below((uint32_t)(op.hi - op.lo));                  // randint(low, high), high exclusive
-        int m = (int)ceil((double)n * ((double)pct / 100.0));                         // novelty_wrappers.py:881,1025,1139
-        if (m > n) m = n;
-        int seen = 0, taken = 0;
-        for (int i = 0; i < cells && taken < m; i++) {
-            int id = e.m[i] & 0x7F;
-            bool marked = e.m[i] & 0x80;
-            bool cand = !marked && (op.kind == NGW_RESET_FENCE ? (id != 0 && id != wall)
-                                  : op.kind == NGW_RESET_ADDITEM ? (id == 0) : (id == op.a));
-            if (!cand) continue;
-            bool take = rng.below((uint32_t)(n - seen)) < (uint32_t)(m - taken);
-            seen++;
-            if (!take) continue;
-            taken++;
-            if (op.kind == NGW_RESET_FENCE) e.m[i] = (int8_t)(id | 0x80);             // mark; fences go in afterwards
-            else if (i != agent) e.m[i] = (int8_t)(op.kind == NGW_RESET_ADDITEM ? op.a : op.b);
+        // ---- apply: one chunked pass in cell order; boundary-bin cells are collected (<= 32, or all of them win)
+        const bool all_in_bin_win = remaining >= bin_count;
+        int n_list = 0;
+        uint32_t my_key = 0; int my_idx = -1;
+        const int value = op.kind == NGW_RESET_ADDITEM ? op.a : op.b;
+        for (int base = 0; base < cells; base += 32) {
+            const int i = base + lane;
+            int id = i < cells ? (int)m[i] : 0;
+            bool cand = i < cells && reset_candidate(op.kind, id, wall, op.a);
+            uint32_t key = cand ? philox_key(seed, gid, episode, stream, (uint32_t)i) : 0;
+            uint32_t top = bits == 0 ? 0 : (key >> (32 - bits));
+            bool wins = cand && (bits == 0 ? all_in_bin_win : (top < prefix || (top == prefix && all_in_bin_win)));
+            bool boundary = cand && !all_in_bin_win && top == prefix;
+            if (wins) {
+                if (op.kind == NGW_RESET_FENCE) m[i] = (int8_t)(id | 0x80);       // mark; fences go in afterwards
+                else if (i != agent) m[i] = (int8_t)value;                        // novelty_wrappers.py:1027,1141
+            }
+            uint32_t bal = __ballot_sync(FULL, boundary);
+            if (boundary) {
+                int slot = n_list + __popc(bal & ((1u << lane) - 1u));
+                if (slot < 32) { hist[slot] = key; hist[32 + slot] = (uint32_t)i; }
+            }
+            n_list += __popc(bal);
         }
-        if (op.kind == NGW_RESET_FENCE) {                                             // add_fence_around, pogostick_v1_env.py:524-536
-            for (int i = 0; i < cells; i++) {
-                if (!(e.m[i] & 0x80)) continue;
-                e.m[i] = (int8_t)(e.m[i] & 0x7F);
-                int r = i / ms, c = i % ms;
-                for (int rr = r - 1; rr <= r + 1; rr++)
-                    for (int cc = c - 1; cc <= c + 1; cc++)
-                        if (rr >= 0 && rr < ms && cc >= 0 && cc < ms && e.m[rr * ms + cc] == 0 && rr * ms + cc != agent)
-                            e.m[rr * ms + cc] = (int8_t)op.a;
+        __syncwarp();
+        if (n_list > 0) {
+            if (n_list > 32) n_list = 32;                             // > 32 equal 32-bit prefixes: cannot happen in practice
+            if (lane < n_list) { my_key = hist[lane]; my_idx = (int)hist[32 + lane]; }
+            int rank = 0;
+            for (int j = 0; j < n_list; j++) {
+                uint32_t kj = __shfl_sync(FULL, my_key, j);
+                int ij = __shfl_sync(FULL, my_idx, j);
+                rank += (kj < my_key) || (kj == my_key && ij < my_idx);
+            }
+            if (lane < n_list && rank < remaining) {
+                if (op.kind == NGW_RESET_FENCE) m[my_idx] = (int8_t)(m[my_idx] | 0x80);
+                else if (my_idx != agent) m[my_idx] = (int8_t)value;
             }
         }
+        __syncwarp();
+        if (op.kind == NGW_RESET_FENCE) {                             // add_fence_around, pogostick_v1_env.py:524-536
+            for (int i = lane; i < cells; i += 32) {
+                int v = m[i];
+                if (!(v & 0x80)) continue;
+                m[i] = (int8_t)(v & 0x7F);
+                int r = i / ms, c = i - r * ms;
+                for (int rr = r - 1; rr <= r + 1; rr++)
+                    for (int cc = c - 1; cc <= c + 1; cc++)
+                        if (rr >= 0 && rr < ms && cc >= 0 && cc < ms && m[rr * ms + cc] == 0 && rr * ms + cc != agent)
+                            m[rr * ms + cc] = (int8_t)op.a;
+            }
+            __syncwarp();
+        }
     }
+    return err;
 }
 
 }  // namespace ngw

@@ -114,170 +114,209 @@ __device__ __forceinline__ void warp_copy16(void* dst, const void* src, int byte
     for (int i = lane; i < (bytes >> 4); i += 32) d[i] = s[i];
 }
 
-// Cold: Philox auto-reset of one env on its shared-memory rows, then the whole grid row back to HBM.
-__device__ __noinline__ uint32_t auto_reset_env(const StepParams& p, const ngw_config* cfg, int8_t* m, int32_t* inv,
-                                                long long e, uchar4& ps) {
-    uint32_t ep = p.episode[e] + 1;
-    p.episode[e] = ep;
-    EnvRow cold;
-    cold.m = m; cold.gm = nullptr; cold.inv = inv; cold.ms = p.ms;
-    cold.r = ps.x; cold.c = ps.y; cold.facing = ps.z; cold.sel = ps.w;
-    uint32_t err = reset_base(cold, cfg, p.inv_stride, p.seed, (uint64_t)(p.first_gid + e), ep);
-    reset_ops(cold, cfg, 0, NGW_MAX_RESET_OPS, p.seed, (uint64_t)(p.first_gid + e), ep);
-    int8_t* grow = p.map + e * p.cells;
-    for (int i = 0; i < p.cells; i++) grow[i] = m[i];
-    ps = make_uchar4((unsigned char)cold.r, (unsigned char)cold.c, (unsigned char)cold.facing, (unsigned char)cold.sel);
-    return err;
+// Cold: fused auto-reset.  Called by the whole step warp; every lane that finished an episode is regenerated in turn by
+// all 32 lanes (reset_env_warp), then its grid row goes back to HBM with coalesced stores.
+__device__ __noinline__ void auto_reset_warp(const StepParams& p, const DevConfig* dcfgs, int cfg_i, bool need,
+                                             int8_t* smap, int32_t* sinv, uint32_t* hist, long long e0, uchar4& ps) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();                                                    // every lane's step writes to the tile are visible
+    uint32_t pending = __ballot_sync(0xFFFFFFFFu, need);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const long long e = e0 + src;
+        const int ci = __shfl_sync(0xFFFFFFFFu, cfg_i, src);
+        uint32_t ep = p.episode[e] + 1;
+        __syncwarp();
+        if (lane == 0) p.episode[e] = ep;
+        int8_t* m = smap + src * p.cells;
+        int32_t* inv = sinv + src * p.inv_stride;
+        int r = 0, c = 0, f = 0, sel = 0;
+        uint32_t err = reset_env_warp(&dcfgs[ci].c, m, inv, p.ms, p.inv_stride, p.seed, (uint64_t)(p.first_gid + e), ep,
+                                      true, 0, NGW_MAX_RESET_OPS, hist, r, c, f, sel);
+        int8_t* grow = p.map + e * p.cells;
+        for (int i = lane; i < p.cells; i += 32) grow[i] = m[i];
+        if (lane == src) {
+            ps = make_uchar4((unsigned char)r, (unsigned char)c, (unsigned char)f, (unsigned char)sel);
+            if (err) p.err[e] |= err;
+        }
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------ the fused step + LidarInFront kernel
+// One CTA = one tile of 32 consecutive envs, G = blockDim.x / 32 warps.  Lane l of every warp owns env l of the tile.
+// Warp 0 runs the flattened step; then all G warps cast 8/G lidar beams each for their lane's env.  G = 1 is the plain
+// one-warp-per-tile kernel; G > 1 shortens the per-tile latency where shared memory limits the tiles per SM.
 template <bool kTma, int NC>
-__global__ void __launch_bounds__(128, 4) step_kernel(const __grid_constant__ StepArgs<NC> args) {
+__global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepArgs<NC> args) {
     extern __shared__ __align__(128) unsigned char smem[];
     // Programmatic dependent launch: let the next kernel of the stream start scheduling its CTAs now; everything up
     // to griddepcontrol.wait below touches no global memory, so it overlaps the previous kernel's tail.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const StepParams& p = args.p;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-    const long long e0 = p.env_begin + ((long long)blockIdx.x * warps + warp) * 32;
-    if (e0 >= p.env_end) return;                                     // whole warp leaves together
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, G = blockDim.x >> 5;
+    const long long e0 = p.env_begin + (long long)blockIdx.x * 32;
     const long long e = e0 + lane;
     const bool valid = e < p.env_end;
     const bool full_tile = e0 + 32 <= p.env_end;
+    const bool stepping = p.actions != nullptr;
 
-    unsigned char* region = smem + (size_t)warp * p.region_bytes;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(region);
-    int8_t* szero = reinterpret_cast<int8_t*>(region + 8);           // 8 bytes that always read 0 (landed lidar beams park here)
-    int8_t* smap = reinterpret_cast<int8_t*>(region + 16);
-    int32_t* sinv = reinterpret_cast<int32_t*>(region + 16 + p.map_bytes);
-    int32_t* sobs = reinterpret_cast<int32_t*>(region + 16 + p.map_bytes + p.inv_bytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    int8_t* szero = reinterpret_cast<int8_t*>(smem + 8);             // 8 bytes that always read 0 (landed lidar beams park here)
+    uchar4* spose = reinterpret_cast<uchar4*>(smem + 16);            // pose after the step, for the other warps
+    uint32_t* sscratch = reinterpret_cast<uint32_t*>(smem + 16 + 128);   // 1 KB: radix-select histogram of the auto-reset
+    int8_t* smap = reinterpret_cast<int8_t*>(smem + 16 + 128 + 1024);
+    int32_t* sinv = reinterpret_cast<int32_t*>(smem + 16 + 128 + 1024 + p.map_bytes);
+    int32_t* sobs = reinterpret_cast<int32_t*>(smem + 16 + 128 + 1024 + p.map_bytes + p.inv_bytes);
 
     // ---- prologue without global memory: barrier, zero pad, zeroed observation tile
     const int8_t* gmap = p.map + e0 * p.cells;
     int32_t* ginv = p.inv + e0 * p.inv_stride;
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         if (kTma) mbar_init(bar, 1);
         *reinterpret_cast<uint64_t*>(szero) = 0ull;
     }
     if (p.obs != nullptr) {
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4* o4 = reinterpret_cast<uint4*>(sobs);
-        for (int i = lane; i < (p.obs_bytes >> 4); i += 32) o4[i] = z;
+        for (int i = threadIdx.x; i < (p.obs_bytes >> 4); i += blockDim.x) o4[i] = z;
     }
-    __syncwarp();                                                    // barrier init visible before anyone waits on it
+    __syncthreads();                                                 // barrier init visible before anyone waits on it
     asm volatile("griddepcontrol.wait;" ::: "memory");               // previous kernel of the stream done + visible
 
     // ---- stage the tile: grid rows + inventory rows (state arrays are padded, a full tile is always readable)
     if (kTma) {
-        if (lane == 0) {
+        if (threadIdx.x == 0) {
             mbar_expect_tx(bar, (uint32_t)(p.map_bytes + p.inv_bytes));
             bulk_g2s(smap, gmap, (uint32_t)p.map_bytes, bar);
             bulk_g2s(sinv, ginv, (uint32_t)p.inv_bytes, bar);
         }
     } else {
-        warp_copy16(smap, gmap, p.map_bytes, lane);
-        warp_copy16(sinv, ginv, p.inv_bytes, lane);
+        const uint4* s4 = reinterpret_cast<const uint4*>(gmap);
+        uint4* d4 = reinterpret_cast<uint4*>(smap);
+        for (int i = threadIdx.x; i < (p.map_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
+        s4 = reinterpret_cast<const uint4*>(ginv);
+        d4 = reinterpret_cast<uint4*>(sinv);
+        for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
     }
 
     // ---- while the copies fly: per-lane scalars
-    uchar4 ps = p.pose[e];
     const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[e];
     const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
     const ngw_config& cfg = dc.c;
+    uchar4 ps = make_uchar4(0, 0, 0, 0);
     int action = 0;
-    if (p.actions != nullptr && valid) action = p.actions[e];
+    if (g == 0) {
+        ps = p.pose[e];
+        if (stepping && valid) action = p.actions[e];
+    }
 
     if (kTma) mbar_wait(bar, 0);
-    __syncwarp();
+    else __syncthreads();
 
     EnvRow env;
     env.m = smap + lane * p.cells;
     env.gm = p.map + e * p.cells;
     env.inv = sinv + lane * p.inv_stride;
     env.ms = p.ms;
-    env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
 
-    if (p.actions != nullptr) {
-        StepOut o;
-        o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f;
-        int invalid = 0, did_reset = 0, success = 0;
-        if (valid) {
-            ngw_action_entry a;
-            a.op = NGW_OP_INVALID;
-            if (action >= 0 && action < cfg.n_actions) {
-                uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
-                memcpy(&a, &raw, sizeof(a));
-            }
-            if (a.op == NGW_OP_INVALID) {                             // wrappers.py:76 / pogostick_v1_env.py:236 would raise
-                invalid = 1;
-                p.err[e] |= NGW_ERR_INVALID_ACTION;
-            } else {
-                step_env(env, cfg, a, o);
-                success = o.done && env.inv[cfg.id_goal] >= 1;
-                int finished = o.done;
-                if (p.max_episode_steps > 0) {
-                    int len = p.ep_len[e] + 1;
-                    if (len >= p.max_episode_steps) { finished = 1; o.done = 1; }     // harness truncation knob
-                    p.ep_len[e] = finished && p.auto_reset ? 0 : len;
+    if (g == 0) {
+        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+        if (stepping) {
+            StepOut o;
+            o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f;
+            int invalid = 0, did_reset = 0, success = 0;
+            if (valid) {
+                ngw_action_entry a;
+                a.op = NGW_OP_INVALID;
+                if (action >= 0 && action < cfg.n_actions) {
+                    uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
+                    memcpy(&a, &raw, sizeof(a));
                 }
-                if (finished && p.auto_reset) {                       // fused auto-reset (rare lanes only)
-                    did_reset = 1;
-                    uchar4 np = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
-                                            (unsigned char)env.sel);
-                    uint32_t err = auto_reset_env(p, &p.dcfgs[cfg_i].c, env.m, env.inv, e, np);
-                    if (err) p.err[e] |= err;
-                    env.r = np.x; env.c = np.y; env.facing = np.z; env.sel = np.w;
+                if (a.op == NGW_OP_INVALID) {                         // wrappers.py:76 / pogostick_v1_env.py:236 would raise
+                    invalid = 1;
+                    p.err[e] |= NGW_ERR_INVALID_ACTION;
+                } else {
+                    step_env(env, cfg, a, o);
+                    success = o.done && env.inv[cfg.id_goal] >= 1;
+                    int finished = o.done;
+                    if (p.max_episode_steps > 0) {
+                        int len = p.ep_len[e] + 1;
+                        if (len >= p.max_episode_steps) { finished = 1; o.done = 1; }     // harness truncation knob
+                        p.ep_len[e] = finished && p.auto_reset ? 0 : len;
+                    }
+                    if (finished && p.auto_reset) { did_reset = 1; }
+                }
+                ps = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
+                                 (unsigned char)env.sel);
+            }
+            if (p.auto_reset && __any_sync(0xFFFFFFFFu, did_reset)) {     // rare: regenerate finished episodes, warp-cooperatively
+                auto_reset_warp(p, p.dcfgs, cfg_i, did_reset != 0, smap, sinv, sscratch, e0, ps);
+                env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+            }
+            if (valid) {
+                p.pose[e] = ps;
+                p.reward[e] = (float)o.reward;
+                p.done[e] = (uint8_t)o.done;
+                p.cost[e] = o.cost;
+                p.result[e] = (uint8_t)o.result;
+            }
+            if (p.stats != nullptr) {
+                int n_done = __reduce_add_sync(0xFFFFFFFFu, valid ? o.done : 0);
+                int n_succ = __reduce_add_sync(0xFFFFFFFFu, success);
+                int n_reset = __reduce_add_sync(0xFFFFFFFFu, did_reset);
+                int n_inv = __reduce_add_sync(0xFFFFFFFFu, invalid);
+                int n_valid = __reduce_add_sync(0xFFFFFFFFu, valid ? 1 : 0);
+                int r_sum = __reduce_add_sync(0xFFFFFFFFu, o.reward);
+                float c_sum = warp_sum(o.cost);
+                if (lane == 0) {
+                    double* s = p.stats + (size_t)(blockIdx.x % NGW_STAT_SLOTS) * NGW_STAT_COUNT;
+                    atomicAdd(&s[NGW_STAT_STEPS], (double)(n_valid - n_inv));
+                    atomicAdd(&s[NGW_STAT_REWARD_SUM], (double)r_sum);
+                    atomicAdd(&s[NGW_STAT_COST_SUM], (double)c_sum);
+                    if (n_done) atomicAdd(&s[NGW_STAT_EPISODES], (double)n_done);
+                    if (n_succ) atomicAdd(&s[NGW_STAT_SUCCESSES], (double)n_succ);
+                    if (n_reset) atomicAdd(&s[NGW_STAT_RESETS], (double)n_reset);
+                    if (n_inv) atomicAdd(&s[NGW_STAT_INVALID], (double)n_inv);
                 }
             }
-            p.pose[e] = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
-                                    (unsigned char)env.sel);
-            p.reward[e] = (float)o.reward;
-            p.done[e] = (uint8_t)o.done;
-            p.cost[e] = o.cost;
-            p.result[e] = (uint8_t)o.result;
         }
-        if (p.stats != nullptr) {
-            int n_done = __reduce_add_sync(0xFFFFFFFFu, valid ? o.done : 0);
-            int n_succ = __reduce_add_sync(0xFFFFFFFFu, success);
-            int n_reset = __reduce_add_sync(0xFFFFFFFFu, did_reset);
-            int n_inv = __reduce_add_sync(0xFFFFFFFFu, invalid);
-            int n_valid = __reduce_add_sync(0xFFFFFFFFu, valid ? 1 : 0);
-            int r_sum = __reduce_add_sync(0xFFFFFFFFu, o.reward);
-            float c_sum = warp_sum(o.cost);
-            if (lane == 0) {
-                double* s = p.stats + (size_t)(blockIdx.x % NGW_STAT_SLOTS) * NGW_STAT_COUNT;
-                atomicAdd(&s[NGW_STAT_STEPS], (double)(n_valid - n_inv));
-                atomicAdd(&s[NGW_STAT_REWARD_SUM], (double)r_sum);
-                atomicAdd(&s[NGW_STAT_COST_SUM], (double)c_sum);
-                if (n_done) atomicAdd(&s[NGW_STAT_EPISODES], (double)n_done);
-                if (n_succ) atomicAdd(&s[NGW_STAT_SUCCESSES], (double)n_succ);
-                if (n_reset) atomicAdd(&s[NGW_STAT_RESETS], (double)n_reset);
-                if (n_inv) atomicAdd(&s[NGW_STAT_INVALID], (double)n_inv);
-            }
-        }
+        if (G > 1) spose[lane] = ps;
+    }
+    if (G > 1) {
+        __syncthreads();                                             // step results (grid, inventory, pose) visible to all warps
+        ps = spose[lane];
+        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
     }
 
     // ---- LidarInFront observation of the (possibly auto-reset) state into the shared-memory tile
-    if (p.obs != nullptr && valid && cfg.n_beams > 0) lidar_observe(env, dc, sobs + lane * p.obs_dim, szero);
+    if (p.obs != nullptr && valid && cfg.n_beams > 0)
+        lidar_observe(env, dc, sobs + lane * p.obs_dim, szero, g, G, g == G - 1);
 
     // ---- write back: inventory tile (only when stepping) and observation tile
-    __syncwarp();
+    __syncthreads();
     if (kTma && full_tile && !p.plain_store) {
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-            if (p.actions != nullptr) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
-            if (p.obs != nullptr) bulk_s2g(p.obs + e0 * p.obs_dim, sobs, (uint32_t)p.obs_bytes);
-            bulk_commit();
-            bulk_wait_read0();                                       // shared memory must outlive the reads
+        if (threadIdx.x < 32) {
+            fence_async_smem();
+            __syncwarp();
+            if (threadIdx.x == 0) {
+                if (stepping) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
+                if (p.obs != nullptr) bulk_s2g(p.obs + e0 * p.obs_dim, sobs, (uint32_t)p.obs_bytes);
+                bulk_commit();
+                bulk_wait_read0();                                   // shared memory must outlive the reads
+            }
         }
     } else {
-        if (p.actions != nullptr) warp_copy16(ginv, sinv, p.inv_bytes, lane);
+        if (stepping) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
+            uint4* d4 = reinterpret_cast<uint4*>(ginv);
+            for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
+        }
         if (p.obs != nullptr) {
             int n = (int)((p.env_end - e0 < 32 ? p.env_end - e0 : 32)) * p.obs_dim;
             int32_t* gobs = p.obs + e0 * p.obs_dim;
-            if (full_tile) warp_copy16(gobs, sobs, p.obs_bytes, lane);
-            else for (int i = lane; i < n; i += 32) gobs[i] = sobs[i];
+            for (int i = threadIdx.x; i < n; i += blockDim.x) gobs[i] = sobs[i];
         }
     }
 }
@@ -300,33 +339,32 @@ struct ResetParams {
     const uint8_t* zero_byte;   // a global byte that always reads 0 (see lidar_observe)
 };
 
-__global__ void reset_kernel(const ResetParams p) {
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+#define NGW_RESET_WARPS 4
+__global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_kernel(const ResetParams p) {
+    __shared__ uint32_t hist[NGW_RESET_WARPS][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long e = (long long)blockIdx.x * NGW_RESET_WARPS + warp;       // one warp regenerates one env
     if (e >= p.n_envs) return;
     if (p.mask != nullptr && p.mask[e] == 0) return;
     const ngw_config* cfg = &p.dcfgs[p.cfg_id[e]].c;
-    EnvRow env;
-    env.m = p.map + e * p.cells;
-    env.gm = nullptr;
-    env.inv = p.inv + e * p.inv_stride;
-    env.ms = p.ms;
     uchar4 ps = p.pose[e];
-    env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+    int r = ps.x, c = ps.y, f = ps.z, sel = ps.w;
     uint64_t gid = (uint64_t)(p.first_gid + e);
     int k = cfg->reset_obs_after_ops;
-    uint32_t ep;
+    int8_t* m = p.map + e * p.cells;
+    int32_t* inv = p.inv + e * p.inv_stride;
     if (p.phase != 1) {
-        ep = p.episode[e] + 1;
-        p.episode[e] = ep;
-        p.ep_len[e] = 0;
-        uint32_t err = reset_base(env, cfg, p.inv_stride, p.seed, gid, ep);
-        p.err[e] = err;
-        reset_ops(env, cfg, 0, p.phase == 0 ? k : NGW_MAX_RESET_OPS, p.seed, gid, ep);
+        uint32_t ep = p.episode[e] + 1;
+        __syncwarp();
+        uint32_t err = reset_env_warp(cfg, m, inv, p.ms, p.inv_stride, p.seed, gid, ep, true, 0,
+                                      p.phase == 0 ? k : NGW_MAX_RESET_OPS, hist[warp], r, c, f, sel);
+        if (lane == 0) { p.episode[e] = ep; p.ep_len[e] = 0; p.err[e] = err; }
     } else {
-        ep = p.episode[e];
-        reset_ops(env, cfg, k, NGW_MAX_RESET_OPS, p.seed, gid, ep);
+        uint32_t ep = p.episode[e];
+        reset_env_warp(cfg, m, inv, p.ms, p.inv_stride, p.seed, gid, ep, false, k, NGW_MAX_RESET_OPS, hist[warp], r, c, f,
+                       sel);
     }
-    p.pose[e] = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing, (unsigned char)env.sel);
+    if (lane == 0) p.pose[e] = make_uchar4((unsigned char)r, (unsigned char)c, (unsigned char)f, (unsigned char)sel);
 }
 
 __global__ void observe_masked_kernel(const ResetParams p, int32_t* obs, int obs_dim) {
@@ -343,7 +381,7 @@ __global__ void observe_masked_kernel(const ResetParams p, int32_t* obs, int obs
     env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
     int32_t* row = obs + e * obs_dim;
     for (int i = 0; i < obs_dim; i++) row[i] = 0;
-    if (dc.c.n_beams > 0) lidar_observe(env, dc, row, reinterpret_cast<const int8_t*>(p.zero_byte));
+    if (dc.c.n_beams > 0) lidar_observe(env, dc, row, reinterpret_cast<const int8_t*>(p.zero_byte), 0, 1, true);
 }
 
 __global__ void set_cfg_kernel(const int32_t* src, uint8_t* dst, long long n, int n_cfgs, uint32_t* err) {
@@ -519,14 +557,15 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
     h->map_bytes = 32 * h->cells;                       // multiple of 32
     h->inv_bytes = 128 * h->inv_stride;
     h->obs_bytes = 128 * (h->obs_dim > 0 ? h->obs_dim : 0);
-    h->region_bytes = 16 + h->map_bytes + h->inv_bytes + h->obs_bytes;
+    h->region_bytes = 16 + 128 + 1024 + h->map_bytes + h->inv_bytes + h->obs_bytes;
     h->region_bytes = (h->region_bytes + 127) & ~127;
-    int warps = 2;                                     // 2 tiles per CTA balances 65536-env batches best over 148 SMs
-    while (warps > 1 && warps * h->region_bytes > 56 * 1024) warps >>= 1;
-    if (warps * h->region_bytes > 227 * 1024) { ngw_destroy(h); return fail("ngw_create: map too large for shared memory"); }
-    if (const char* w = getenv("NGW_WARPS")) {                      // tuning knob: warps (tiles) per CTA, 1..4
+    if (h->region_bytes > 227 * 1024) { ngw_destroy(h); return fail("ngw_create: map too large for shared memory"); }
+    // G warps share one tile: 1 for small grids (many tiles fit per SM), more when shared memory limits the tiles
+    int tiles_per_sm = (227 * 1024) / (h->region_bytes + 1024);
+    int warps = tiles_per_sm >= 12 ? 1 : (tiles_per_sm >= 6 ? 2 : (tiles_per_sm >= 3 ? 4 : 8));
+    if (const char* w = getenv("NGW_WARPS")) {                      // tuning knob: warps per tile, 1 / 2 / 4 / 8
         int v = atoi(w);
-        if (v >= 1 && v <= 4 && v * h->region_bytes <= 227 * 1024) warps = v;
+        if (v == 1 || v == 2 || v == 4 || v == 8) warps = v;
     }
     h->warps = warps;
     CK(cudaFuncSetAttribute(step_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -588,19 +627,20 @@ int ngw_reset(ngw_handle* h, const uint8_t* mask, int32_t* obs, void* stream) {
     CK(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     int blocks = (int)((h->n + 127) / 128);
+    int rblocks = (int)((h->n + NGW_RESET_WARPS - 1) / NGW_RESET_WARPS);
     bool split = false;
     for (auto& c : h->h_cfgs) split |= c.c.reset_obs_after_ops < c.c.n_reset_ops;
     if (obs == nullptr || h->obs_dim == 0 || !split) {
-        reset_kernel<<<blocks, 128, 0, s>>>(reset_params(h, mask, 2));
+        reset_kernel<<<rblocks, 32 * NGW_RESET_WARPS, 0, s>>>(reset_params(h, mask, 2));
         h->launches++;
         if (obs != nullptr && h->obs_dim > 0) {
             observe_masked_kernel<<<blocks, 128, 0, s>>>(reset_params(h, mask, 2), obs, h->obs_dim);
             h->launches++;
         }
     } else {
-        reset_kernel<<<blocks, 128, 0, s>>>(reset_params(h, mask, 0));
+        reset_kernel<<<rblocks, 32 * NGW_RESET_WARPS, 0, s>>>(reset_params(h, mask, 0));
         observe_masked_kernel<<<blocks, 128, 0, s>>>(reset_params(h, mask, 0), obs, h->obs_dim);
-        reset_kernel<<<blocks, 128, 0, s>>>(reset_params(h, mask, 1));
+        reset_kernel<<<rblocks, 32 * NGW_RESET_WARPS, 0, s>>>(reset_params(h, mask, 1));
         h->launches += 3;
     }
     CK(cudaGetLastError());
@@ -647,8 +687,8 @@ static void launch_step_nc(ngw_handle* h, const StepParams& p, int blocks, size_
 static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
     long long tiles = (p.env_end - p.env_begin + 31) / 32;
     if (tiles <= 0) return 0;
-    int blocks = (int)((tiles + h->warps - 1) / h->warps);
-    size_t smem = (size_t)h->warps * h->region_bytes;
+    int blocks = (int)tiles;
+    size_t smem = (size_t)h->region_bytes;
     int nc = h->force_global_cfg ? 0 : h->n_cfgs;
     if (nc == 0 || nc > 16) launch_step_nc<0>(h, p, blocks, smem, s);
     else if (nc == 1) launch_step_nc<1>(h, p, blocks, smem, s);

@@ -13,10 +13,12 @@
 from .core import make, register, registry, Env, Wrapper  # noqa: F401
 from . import envs, wrappers, observation_wrappers, novelty_wrappers, spaces  # noqa: F401
 from .wrappers import LimitActions  # noqa: F401
-from .observation_wrappers import LidarInFront  # noqa: F401
+from .observation_wrappers import LidarInFront, AgentMap  # noqa: F401
 from .novelty_wrappers import inject_novelty  # noqa: F401
 
 register(id='NovelGridworld-Pogostick-v1', entry_point=envs.PogostickV1Env)
 register(id='NovelGridworld-Bow-v1', entry_point=envs.BowV1Env)
+register(id='NovelGridworld-Pogostick-v0', entry_point=envs.PogostickV0Env)
+register(id='NovelGridworld-Bow-v0', entry_point=envs.BowV0Env)
 
 __version__ = '0.1.0'

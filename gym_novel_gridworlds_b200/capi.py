@@ -8,7 +8,7 @@ from . import opcodes as oc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libngw_b200.so')
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class ActionEntryC(C.Structure):
@@ -35,6 +35,7 @@ class ConfigC(C.Structure):
         ('n_items', C.c_int32), ('n_actions', C.c_int32),
         ('actions', ActionEntryC * oc.MAX_ACTIONS),
         ('unbreakable_mask', C.c_uint32), ('entity_mask', C.c_uint32),
+        ('break_reward_mask', C.c_uint32), ('reserved_mask', C.c_uint32),
         ('id_wall', C.c_uint8), ('id_crafting_table', C.c_uint8), ('id_tree_log', C.c_uint8),
         ('id_tree_tap', C.c_uint8), ('id_rubber', C.c_uint8), ('id_wool', C.c_uint8), ('id_string', C.c_uint8),
         ('id_goal', C.c_uint8), ('id_wooden_axe', C.c_uint8), ('id_iron_axe', C.c_uint8), ('id_fence', C.c_uint8),
@@ -80,6 +81,7 @@ EXPORTS = {
     'ngw_step_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int32, C.c_int32]),
     'ngw_observe': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ngw_agent_map': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'ngw_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'ngw_launch_count': (C.c_int64, [C.c_void_p]),
 }

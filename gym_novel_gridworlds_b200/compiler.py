@@ -114,6 +114,9 @@ def compile_chain(top):
     for name in base.entities:
         if name in items_id:
             cfg.entity_mask |= 1 << items_id[name]
+    for name in base._BREAK_REWARD_ITEMS:
+        if name in items_id:
+            cfg.break_reward_mask |= 1 << items_id[name]
     cfg.id_wall = _item_id(items_id, 'wall')
     cfg.id_crafting_table = _item_id(items_id, 'crafting_table')
     cfg.id_tree_log = _item_id(items_id, 'tree_log')

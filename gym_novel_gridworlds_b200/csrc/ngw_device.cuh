@@ -159,7 +159,7 @@ __device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_config& cfg, co
             if (variant == NGW_BRK_BASE) {                            // pogostick_v1_env.py:283-289
                 set_cell(e, fr, fc, 0);
                 e.inv[front] += 1;
-                if (front == cfg.id_tree_log) o.reward = cfg.reward_intermediate;
+                if (in_mask(cfg.break_reward_mask, front)) o.reward = cfg.reward_intermediate;
             } else if (variant == NGW_BRK_INCREASE) {                 // novelty_wrappers.py:1444-1454
                 set_cell(e, fr, fc, 0);
                 e.inv[front] += (a.arg == NGW_NONE || a.arg == front) ? 2 : 1;
@@ -496,6 +496,40 @@ __device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m
             continue;
         }
         const uint32_t stream = 1 + k;
+        if (op.kind == NGW_RESET_TREETAP) {                           // pogostick_v0_env.py:155-178
+            // uniform over (tree_log, direction) pairs until the target cell is free == the reference's retry loop;
+            // the few draws are computed redundantly by all lanes
+            int n_logs = 0;
+            for (int i = lane; i < cells; i += 32) n_logs += (m[i] == (int8_t)op.b);
+            n_logs = __reduce_add_sync(FULL, n_logs);
+            if (n_logs <= 1) { err |= NGW_ERR_PLACEMENT; continue; }
+            Philox rt;
+            rt.init(seed, gid, episode, stream);
+            int target = -1;
+            for (int attempt = 0; attempt < 4096 && target < 0; attempt++) {
+                int direction = (int)rt.below(4);
+                int which = (int)rt.below((uint32_t)n_logs);
+                int log = -1;
+                for (int base = 0; base < cells && log < 0; base += 32) {     // which-th tree_log in row-major order
+                    int i = base + lane;
+                    uint32_t bal = __ballot_sync(FULL, i < cells && m[i] == (int8_t)op.b);
+                    int c = __popc(bal);
+                    if (which < c) {
+                        int bit = __fns(bal, 0, which + 1);
+                        log = base + bit;
+                    } else which -= c;
+                }
+                int r = log / ms, c = log - r * ms;
+                int tr = r + (direction == NGW_SOUTH) - (direction == NGW_NORTH);
+                int tc = c + (direction == NGW_EAST) - (direction == NGW_WEST);
+                if (tr >= 0 && tr < ms && tc >= 0 && tc < ms && m[tr * ms + tc] == 0 && tr * ms + tc != agent)
+                    target = tr * ms + tc;
+            }
+            if (target < 0) { err |= NGW_ERR_PLACEMENT; continue; }
+            if (lane == 0) m[target] = (int8_t)op.a;
+            __syncwarp();
+            continue;
+        }
         // ---- n candidates, percentage, m
         int n = 0;
         for (int i = lane; i < cells; i += 32) n += reset_candidate(op.kind, m[i], wall, op.a);

@@ -384,6 +384,17 @@ __global__ void observe_masked_kernel(const ResetParams p, int32_t* obs, int obs
     if (dc.c.n_beams > 0) lidar_observe(env, dc, row, reinterpret_cast<const int8_t*>(p.zero_byte), 0, 1, true);
 }
 
+// AgentMap.get_agentView (observation_wrappers.py:98-118): zero-padded (2v+1)^2 crop centred on the agent
+__global__ void agent_map_kernel(const int8_t* map, const uchar4* pose, int8_t* out, long long n, int ms, int view) {
+    const int side = 2 * view + 1;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * side * side) return;
+    long long e = idx / (side * side);
+    int k = (int)(idx - e * side * side);
+    int r = pose[e].x - view + k / side, c = pose[e].y - view + k % side;
+    out[idx] = (r >= 0 && r < ms && c >= 0 && c < ms) ? map[e * ms * ms + r * ms + c] : (int8_t)0;
+}
+
 __global__ void set_cfg_kernel(const int32_t* src, uint8_t* dst, long long n, int n_cfgs, uint32_t* err) {
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
@@ -753,6 +764,17 @@ int ngw_step_host(ngw_handle* h, const int32_t* actions, int32_t* obs, float* re
     CK(cudaMemcpyAsync(step_cost, h->h_cost, cnt * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(result, h->h_result, cnt, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int ngw_agent_map(ngw_handle* h, int8_t* out, int32_t view, void* stream) {
+    if (!h || !out || view < 1 || view > 32) return fail("ngw_agent_map: bad arguments");
+    CK(cudaSetDevice(h->device));
+    long long total = h->n * (2 * view + 1) * (2 * view + 1);
+    agent_map_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->map, h->pose, out, h->n, h->ms,
+                                                                                         view);
+    h->launches++;
+    CK(cudaGetLastError());
     return 0;
 }
 

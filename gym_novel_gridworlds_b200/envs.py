@@ -27,6 +27,8 @@ class NovelGridworldBatchEnv(Env):
     _COST_NO_TABLE = {}
     _COST_OK = {}
     _CRAFT_REWARD_IS_DONE = False      # bow_v1_env.py:424 uses reward_done, pogostick_v1_env.py:455 reward_intermediate
+    _BREAK_REWARD_ITEMS = ('tree_log',)  # base Break rewards these (pogostick_v1_env.py:288; v0: pogostick_v0_env.py:312)
+    _PLACES_TREE_TAP = False           # pogostick_v0_env.py:155-178
 
     def __init__(self, env=None, num_envs=1, device=None, seed=0, first_env_gid=0):
         self.env = env                                  # env to restore in reset (pogostick_v1_env.py:29,89-109)
@@ -159,7 +161,10 @@ class NovelGridworldBatchEnv(Env):
         return ActionEntry(oc.OP_NOOP)
 
     def _reset_program(self):
-        return ResetProgram([(self.items_id[name], qty) for name, qty in self.items_quantity.items()])
+        prog = ResetProgram([(self.items_id[name], qty) for name, qty in self.items_quantity.items()])
+        if self._PLACES_TREE_TAP:
+            prog.ops.append((oc.RESET_TREETAP, self.items_id['tree_tap'], self.items_id['tree_log'], 0, 0))
+        return prog
 
     def _lidar(self):
         return None
@@ -246,3 +251,22 @@ class BowV1Env(NovelGridworldBatchEnv):
             return ActionEntry(oc.OP_EXTRACT_STRING, arg=4)          # bow_v1_env.py:297
         return ActionEntry({'Forward': oc.OP_FORWARD, 'Left': oc.OP_LEFT, 'Right': oc.OP_RIGHT,
                             'Break': oc.OP_BREAK}[name])
+
+
+class PogostickV0Env(PogostickV1Env):
+    """Ingredients pre-placed, one tree_tap next to a random tree_log, rewards for breaking stick / plank, craft reward
+    = reward_done (pogostick_v0_env.py:44,155-178,312,479)."""
+    env_id = 'NovelGridworld-Pogostick-v0'
+    _ITEMS_QUANTITY = (('crafting_table', 1), ('stick', 4), ('plank', 2), ('tree_log', 2))
+    _BREAK_REWARD_ITEMS = ('stick', 'plank')
+    _CRAFT_REWARD_IS_DONE = True
+    _PLACES_TREE_TAP = True
+
+
+class BowV0Env(BowV1Env):
+    """Ingredients pre-placed, rewards for breaking stick / string, craft reward = reward_intermediate
+    (bow_v0_env.py:44,286,424)."""
+    env_id = 'NovelGridworld-Bow-v0'
+    _ITEMS_QUANTITY = (('crafting_table', 1), ('stick', 3), ('string', 3))
+    _BREAK_REWARD_ITEMS = ('stick', 'string')
+    _CRAFT_REWARD_IS_DONE = False

@@ -66,3 +66,39 @@ class LidarInFront(Wrapper):
 
     def observation(self, obs=None):
         return self.unwrapped._runtime_for(self.unwrapped._top).lidar_observation()
+
+
+class AgentMap(Wrapper):
+    """Agent's local view: the zero-padded (2*agent_view_size+1)^2 crop of the grid centred on the agent, plus facing id
+    and the inventory (observation_wrappers.py:83-129).  The crop is one small kernel (ngw_agent_map) over the live state."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.max_items = 20
+        self.agent_view_size = 5
+        assert not self.max_items < len(self.env.items), "Cannot have more than " + str(self.max_items) + " items"
+        assert self.agent_view_size >= 1, "Increase the agent_view_size"
+        self.observation_space = spaces.Dict({'agent_map': spaces.Box(
+            low=0, high=self.max_items, shape=(self.agent_view_size, self.agent_view_size, 1))})
+
+    def get_agentView(self):
+        return self.unwrapped._runtime_for(self.unwrapped._top).agent_map(self.agent_view_size)
+
+    def observation(self, obs=None):
+        rt = self.unwrapped._runtime_for(self.unwrapped._top)
+        d = rt.dict_observation()
+        return {'agent_map': rt.agent_map(self.agent_view_size), 'agent_facing_id': d['agent_facing_id'],
+                'inventory_items_quantity': d['inventory_items_quantity']}
+
+    def _reset_program(self):
+        prog = self.env._reset_program()
+        prog.returns = 'agent_map'
+        return prog
+
+    def reset(self, **kwargs):
+        self.unwrapped._runtime_for(self).reset(**kwargs)
+        return self.observation()
+
+    def step(self, action):
+        _, reward, done, info = self.unwrapped._runtime_for(self).step(action)
+        return self.observation(), reward, done, info

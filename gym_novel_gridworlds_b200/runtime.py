@@ -238,6 +238,13 @@ class ChainRuntime(object):
         return {'map': h.map, 'agent_location': h.pose[:, 0:2], 'agent_facing_id': h.pose[:, 2],
                 'inventory_items_quantity': {n: h.inventory[:, i] for i, n in enumerate(names) if n in self.base.items}}
 
+    def agent_map(self, view):
+        h = self.handle
+        side = 2 * view + 1
+        out = torch.empty((h.n, side, side), dtype=torch.int8, device=h.device)
+        capi.check(h.lib, h.lib.ngw_agent_map(h._h, _ptr(out), int(view), h._stream()))
+        return out[0].cpu().numpy().astype(np.int64) if self.single else out
+
     def lidar_observation(self):
         obs = self.handle.observe()[:, :self.compiled.obs_dim]
         return obs[0].cpu().numpy().astype(np.int64) if self.single else obs

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define NGW_ABI_VERSION 3
+#define NGW_ABI_VERSION 4
 
 #define NGW_MAX_ITEMS 24          /* reference asserts len(items) <= 20 (pogostick_v1_env.py:75,220) */
 #define NGW_MAX_ACTIONS 48
@@ -92,7 +92,8 @@ enum ngw_reset_kind {
     NGW_RESET_FENCE = 1,       /* novelty_wrappers.py:868-889: a = fence id, percent in [lo, hi) of non-air non-wall cells */
     NGW_RESET_ADDITEM = 2,     /* novelty_wrappers.py:1013-1034: a = new item id, percent of air cells */
     NGW_RESET_REPLACE = 3,     /* novelty_wrappers.py:1126-1148: a = item to replace, b = replacement */
-    NGW_RESET_INVSET = 4       /* novelty_wrappers.py:33,460,668-671: inventory[a] = lo */
+    NGW_RESET_INVSET = 4,      /* novelty_wrappers.py:33,460,668-671: inventory[a] = lo */
+    NGW_RESET_TREETAP = 5      /* pogostick_v0_env.py:155-178: a = tree_tap id, b = tree_log id; one tap next to a random log */
 };
 
 typedef struct {
@@ -132,6 +133,10 @@ typedef struct {
     ngw_action_entry actions[NGW_MAX_ACTIONS];
     uint32_t unbreakable_mask;         /* bit i: item id i in unbreakable_items (pogostick_v1_env.py:41, novelty_wrappers.py:1116) */
     uint32_t entity_mask;              /* bit i: item id i in entities (pogostick_v1_env.py:47,538-554) */
+    uint32_t break_reward_mask;        /* bit i: base Break of item i earns reward_intermediate: tree_log in the v1 envs
+                                          (pogostick_v1_env.py:288), stick/plank resp. stick/string in v0
+                                          (pogostick_v0_env.py:312, bow_v0_env.py:286) */
+    uint32_t reserved_mask;
     uint8_t id_wall, id_crafting_table, id_tree_log, id_tree_tap, id_rubber, id_wool, id_string, id_goal;
     uint8_t id_wooden_axe, id_iron_axe; /* ids of the literal names compared at novelty_wrappers.py:56,67 */
     uint8_t id_fence;                  /* FenceRestriction.env2.fence_name (novelty_wrappers.py:928) */
@@ -229,6 +234,10 @@ int ngw_step_host(ngw_handle* h, const int32_t* actions, int32_t* obs, float* re
 
 /* LidarInFront.observation of the current state into DEVICE int32[n_envs][obs_dim]. */
 int ngw_observe(ngw_handle* h, int32_t* obs, void* stream);
+
+/* AgentMap.get_agentView (observation_wrappers.py:98-118): the (2*view+1)^2 zero-padded crop of the grid centred on the
+ * agent, DEVICE int8[n_envs][2*view+1][2*view+1]. */
+int ngw_agent_map(ngw_handle* h, int8_t* out, int32_t view, void* stream);
 
 /* Copy the NGW_STAT_COUNT accumulated counters (doubles) to DEVICE out8; reset_after != 0 zeroes them. */
 int ngw_stats(ngw_handle* h, double* out8_dev, int32_t reset_after, void* stream);

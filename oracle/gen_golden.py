@@ -81,7 +81,10 @@ def run_scenario(ns, desc, out):
         obs0 = env.reset()
         m, p, v = snapshot(base)
         rec['reset_map'].append(m); rec['reset_pose'].append(p); rec['reset_inv'].append(v)
-        if isinstance(obs0, dict):
+        if isinstance(obs0, dict) and 'agent_map' in obs0:
+            reset_kind = 'agent_map'
+            rec['reset_obs'].append(np.asarray(obs0['agent_map'], np.int64).ravel())
+        elif isinstance(obs0, dict):
             reset_kind = 'dict'
             assert obs0['map'] is base.map and obs0['inventory_items_quantity'] is base.inventory_items_quantity
             rec['reset_obs'].append(np.zeros(0, np.int64))
@@ -99,7 +102,11 @@ def run_scenario(ns, desc, out):
             obs, reward, done, info = env.step(a)
             A.append(a); R.append(reward); D.append(bool(done)); Cst.append(float(info['step_cost']))
             Res.append(bool(info['result']))
-            O.append(np.zeros(0, np.int64) if isinstance(obs, dict) else np.asarray(obs, np.int64))
+            if isinstance(obs, dict) and 'agent_map' in obs:
+                assert obs['agent_facing_id'] == base.agent_facing_id
+                O.append(np.asarray(obs['agent_map'], np.int64).ravel())
+            else:
+                O.append(np.zeros(0, np.int64) if isinstance(obs, dict) else np.asarray(obs, np.int64))
             m, p, v = snapshot(base)
             M.append(m); P.append(p); V.append(v)
         rec['actions'].append(np.array(A, np.int32)); rec['obs'].append(np.stack(O))

@@ -196,7 +196,7 @@ static void do_break(env_t* e, const ngw_action_entry* a, out_t* o) {
         case NGW_BRK_BASE:                       /* pogostick_v1_env.py:283-289 */
             CELL(e, fr, fc) = 0;
             e->inv[front] += 1;
-            if (front == cfg->id_tree_log) o->reward = cfg->reward_intermediate;
+            if (in_mask(cfg->break_reward_mask, front)) o->reward = cfg->reward_intermediate;
             break;
         case NGW_BRK_AXE:
         case NGW_BRK_AXE_INC: {                  /* novelty_wrappers.py:55-81 */
@@ -490,6 +490,23 @@ int ngo_reset_legacy(const ngw_config* cfg, int ms, ngo_mt* mt, int8_t* map, uin
     for (int k = op_begin; k < op_end && k < cfg->n_reset_ops && rc == 0; k++) {
         const ngw_reset_op* op = &cfg->reset_ops[k];
         if (op->kind == NGW_RESET_INVSET) { inv[op->a] = op->lo; continue; }
+        if (op->kind == NGW_RESET_TREETAP) {                           /* pogostick_v0_env.py:155-178 */
+            int n_logs = 0, agent = pose[0] * ms + pose[1];
+            for (int i = 0; i < n_cells; i++) if (map[i] == op->b) cells[n_logs++] = i;   /* np.where, row-major */
+            if (n_logs <= 1) { rc = NGW_ERR_PLACEMENT; break; }        /* assert len(result[0]) > 1 */
+            for (;;) {
+                int direction = (int)ngo_randint(mt, 0, 4);            /* np.random.choice(['NORTH','SOUTH','WEST','EAST']) */
+                int log = cells[ngo_randint(mt, 0, (uint32_t)n_logs)]; /* np.random.choice(len(result[0])) */
+                int r = log / ms, c = log % ms;
+                int tr = r + (direction == NGW_SOUTH) - (direction == NGW_NORTH);
+                int tc = c + (direction == NGW_EAST) - (direction == NGW_WEST);
+                if (tr >= 0 && tr <= ms - 1 && tc >= 0 && tc <= ms - 1 && map[tr * ms + tc] == 0 && tr * ms + tc != agent) {
+                    map[tr * ms + tc] = (int8_t)op->a;
+                    break;                                             /* a tree_tap now exists */
+                }
+            }
+            continue;
+        }
         int n = 0;                                                     /* np.where(...) is row-major */
         for (int i = 0; i < n_cells; i++) {
             int id = map[i], take;

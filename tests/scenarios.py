@@ -12,6 +12,8 @@ import numpy as np
 
 POGO = 'NovelGridworld-Pogostick-v1'
 BOW = 'NovelGridworld-Bow-v1'
+POGO0 = 'NovelGridworld-Pogostick-v0'
+BOW0 = 'NovelGridworld-Bow-v0'
 
 C2_SET = ['Forward', 'Left', 'Right', 'Break', 'Place_tree_tap', 'Extract_rubber',
           'Craft_plank', 'Craft_stick', 'Craft_tree_tap', 'Craft_pogo_stick']
@@ -29,6 +31,8 @@ def build_chain(ns, desc, **make_kwargs):
             env = ns['LimitActions'](env, set(step[1]))
         elif kind == 'lidar':
             env = ns['LidarInFront'](env, num_beams=step[1])
+        elif kind == 'agentmap':
+            env = ns['AgentMap'](env)
         elif kind == 'novelty':
             env = ns['inject_novelty'](env, step[1], step[2], step[3], step[4])
         else:
@@ -48,15 +52,15 @@ def reference_namespace():
     import gym
     import gym_novel_gridworlds  # noqa: F401  (registers the ids)
     from gym_novel_gridworlds.wrappers import LimitActions
-    from gym_novel_gridworlds.observation_wrappers import LidarInFront
+    from gym_novel_gridworlds.observation_wrappers import LidarInFront, AgentMap
     from gym_novel_gridworlds.novelty_wrappers import inject_novelty
-    return {'make': gym.make, 'LimitActions': LimitActions, 'LidarInFront': LidarInFront,
+    return {'make': gym.make, 'LimitActions': LimitActions, 'LidarInFront': LidarInFront, 'AgentMap': AgentMap,
             'inject_novelty': inject_novelty}
 
 
 def b200_namespace():
     import gym_novel_gridworlds_b200 as g
-    return {'make': g.make, 'LimitActions': g.LimitActions, 'LidarInFront': g.LidarInFront,
+    return {'make': g.make, 'LimitActions': g.LimitActions, 'LidarInFront': g.LidarInFront, 'AgentMap': g.AgentMap,
             'inject_novelty': g.inject_novelty}
 
 
@@ -133,4 +137,19 @@ def all_scenarios():
     add('pogo_addchop_addjump', POGO, [['limit', C2_SET + ['Chop', 'Jump']], ['lidar', 8], _nov('addchop'), _nov('addjump')])
     add('bow_axehard_wooden_limit', BOW, [['limit', BOW_SET + ['Craft_wooden_axe', 'Select_wooden_axe']], ['lidar', 8], _nov('axe', 'hard', 'wooden', 'true')])
     add('bow_extractdec_over_firewall', BOW, [['lidar', 8], _nov('firewall', 'easy'), _nov('extractincdec', 'hard', 'decrease')])
+    # the v0 envs (ingredients pre-placed, tree_tap placed at reset, other reward items) and AgentMap
+    add('pogo0_bare', POGO0, [])
+    add('pogo0_lidar', POGO0, [['lidar', 8]])
+    add('pogo0_limit_lidar', POGO0, [['limit', C2_SET], ['lidar', 8]])
+    add('pogo0_A_axe_easy', POGO0, [['limit', C2_SET + ['Select_wooden_axe']], ['lidar', 8], _nov('axe', 'easy', 'wooden', '')])
+    add('pogo0_C_fence_hard', POGO0, [['lidar', 8], _nov('fence', 'hard', 'oak')])
+    add('pogo0_ms16_lidar', POGO0, [['lidar', 8]], map_size=16)
+    add('bow0_bare', BOW0, [])
+    add('bow0_limit_lidar', BOW0, [['limit', BOW_SET], ['lidar', 8]])
+    add('bow0_C_firewall_hard', BOW0, [['lidar', 8], _nov('firewall', 'hard')])
+    add('bow0_B_additem_medium', BOW0, [_nov('additem', 'medium', 'spring'), ['lidar', 8]])
+    add('pogo_agentmap', POGO, [['limit', C2_SET], ['agentmap']])
+    add('bow_agentmap', BOW, [['agentmap']])
+    add('pogo0_agentmap_additem', POGO0, [_nov('additem', 'hard', 'spring'), ['agentmap']])
+    add('pogo_ms20_agentmap', POGO, [['agentmap']], map_size=20)
     return S

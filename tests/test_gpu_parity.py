@@ -30,9 +30,16 @@ def test_gpu_replays_reference_golden_trace(name):
     n_items = g['init_inv'].shape[1]
     h = BatchHandle([cc], E, seed=1)
     h.load_state(g['init_map'], g['init_pose'], g['init_inv'])
-    has_obs = g['obs'].shape[2] > 0
+    kind = g['meta']['reset_kind']
+    has_obs = g['obs'].shape[2] > 0 and kind != 'agent_map'
+    amap = torch.empty((E, 11, 11), dtype=torch.int8, device='cuda')
     for t in range(T):
         obs, reward, done, cost, result = h.step(torch.from_numpy(g['actions'][:, t].copy()).cuda())
+        if kind == 'agent_map':
+            from gym_novel_gridworlds_b200 import capi
+            import ctypes as C
+            capi.check(h.lib, h.lib.ngw_agent_map(h._h, C.c_void_p(amap.data_ptr()), 5, h._stream()))
+            assert np.array_equal(amap.cpu().numpy().reshape(E, -1), g['obs'][:, t]), "%s step %d" % (name, t)
         where = "%s step %d" % (name, t)
         assert np.array_equal(reward.cpu().numpy(), g['reward'][:, t].astype(np.float32)), where
         assert np.array_equal(done.cpu().numpy(), g['done'][:, t]), where

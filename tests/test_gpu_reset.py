@@ -93,7 +93,8 @@ def test_sharded_reset_is_independent_of_sharding():
 
 @pytest.mark.parametrize('name', ['bow_C3_axe_medium_fence_hard', 'pogo_A_additem_hard', 'pogo_A_firewall_hard',
                                   'pogo_A_axetobreak_hard_iron', 'pogo_A_replaceitem_medium_log',
-                                  'pogo_ms40_additem_hard', 'pogo_A_axe_easy_wooden', 'pogo_A_crate_hard'])
+                                  'pogo_ms40_additem_hard', 'pogo_A_axe_easy_wooden', 'pogo_A_crate_hard',
+                                  'pogo0_lidar', 'pogo0_C_fence_hard', 'bow0_C_firewall_hard'])
 def test_novelty_reset_statistics_match_reference_generator(name):
     cc = _compiled(golden_util.get(name)['meta'])
     n = 2048 if cc.map_size > 20 else 8192
@@ -151,3 +152,38 @@ def test_sticky_done_without_auto_reset():
     for _ in range(3):
         obs, rew, done, cost, res = h.step(torch.zeros(32, dtype=torch.int32, device='cuda') + 7)
         assert done.all() and (rew == 50).all()
+
+
+def test_v0_tree_tap_is_next_to_a_tree_log():
+    cc = _compiled(golden_util.get('pogo0_lidar')['meta'])
+    n = 4096
+    h = BatchHandle([cc], n, seed=4)
+    h.reset()
+    m = h.map.cpu().numpy().astype(int)
+    pose = h.pose.cpu().numpy()
+    tap, log = cc.c.id_tree_tap, cc.c.id_tree_log
+    assert ((m == tap).sum(axis=(1, 2)) == 1).all()                      # pogostick_v0_env.py:176-177
+    for i in range(0, n, 37):
+        r, c = np.argwhere(m[i] == tap)[0]
+        assert log in (m[i, r - 1, c], m[i, r + 1, c], m[i, r, c - 1], m[i, r, c + 1])
+        assert (r, c) != (pose[i, 0], pose[i, 1])
+
+
+def test_agent_map_wrapper_single_and_batched():
+    import gym_novel_gridworlds_b200 as gym
+    for n in (1, 257):
+        env = gym.AgentMap(gym.make('NovelGridworld-Pogostick-v1', num_envs=n))
+        obs = env.reset()
+        am = obs['agent_map']
+        assert tuple(am.shape[-2:]) == (11, 11)
+        full = env.unwrapped._runtime.handle.map.cpu().numpy()
+        pose = env.unwrapped._runtime.handle.pose.cpu().numpy()
+        am = np.asarray(am if n == 1 else am.cpu().numpy()).reshape(n, 11, 11)
+        for i in range(0, n, 16):
+            ext = np.zeros((20, 20), int)
+            ext[5:15, 5:15] = full[i]
+            r, c = int(pose[i, 0]), int(pose[i, 1])
+            assert np.array_equal(am[i], ext[r:r + 11, c:c + 11])
+        a = 0 if n == 1 else torch.zeros(n, dtype=torch.int32, device='cuda')
+        obs, reward, done, info = env.step(a)
+        assert 'agent_map' in obs and 'agent_facing_id' in obs and 'inventory_items_quantity' in obs

@@ -10,6 +10,14 @@ from oracle.oracle_lib import OracleBatch
 NAMES = golden_util.names()
 
 
+def agent_map_of(flat_map, pose, ms, view=5):
+    """AgentMap.get_agentView (observation_wrappers.py:98-118): zero-padded 11x11 crop centred on the agent."""
+    ext = np.zeros((ms + 2 * view, ms + 2 * view), np.int64)
+    ext[view:-view, view:-view] = np.asarray(flat_map).reshape(ms, ms)
+    r, c = int(pose[0]), int(pose[1])
+    return ext[r:r + 2 * view + 1, c:c + 2 * view + 1].ravel()
+
+
 def _build(name):
     g = golden_util.get(name)
     env = scenarios.build_chain(scenarios.b200_namespace(), g['meta'])
@@ -51,6 +59,8 @@ def test_oracle_reset_reproduces_reference_stream(name):
         assert np.array_equal(ob.inv[0, :n_items], g['reset_inv'][ep])
         if g['meta']['reset_kind'] == 'lidar':
             assert np.array_equal(obs[:cc.obs_dim], g['reset_obs'][ep].astype(np.int32))
+        if g['meta']['reset_kind'] == 'agent_map':
+            assert np.array_equal(agent_map_of(ob.map[0], ob.pose[0], cc.map_size), g['reset_obs'][ep])
 
 
 @pytest.mark.parametrize('name', NAMES)
@@ -62,7 +72,8 @@ def test_oracle_replay_matches_reference(name):
     ob.map[:] = g['init_map']
     ob.pose[:] = g['init_pose']
     ob.inv[:, :n_items] = g['init_inv']
-    has_obs = g['obs'].shape[2] > 0
+    kind = g['meta']['reset_kind']
+    has_obs = g['obs'].shape[2] > 0 and kind != 'agent_map'
     if has_obs:
         assert g['obs'].shape[2] == cc.obs_dim
     for t in range(T):
@@ -78,3 +89,6 @@ def test_oracle_replay_matches_reference(name):
         assert np.array_equal(ob.inv[:, :n_items], g['inv'][:, t]), where
         if has_obs:
             assert np.array_equal(obs, g['obs'][:, t].astype(np.int32)), where
+        if kind == 'agent_map':
+            for i in range(E):
+                assert np.array_equal(agent_map_of(ob.map[i], ob.pose[i], cc.map_size), g['obs'][i, t]), where

@@ -308,6 +308,20 @@ def run_ours(args, rank, world, local_rank):
     graph_ov_rem = capture(rem, n_ov) if rem else None
     ms_overlap, _, _ = timed(graph_ov, replays, graph_ov_rem)
 
+    # ---- K-step rollout kernel: 64 steps per launch, uniform random policy drawn on the device
+    roll_T = 64
+    for h in batches:
+        h.rollout(roll_T, None, policy_seed=1, **step_kw)
+    torch.cuda.synchronize(dev)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_roll = max(2 * n_batches, 8)
+    r0.record()
+    for i in range(n_roll):
+        batches[i % n_batches].rollout(roll_T, None, policy_seed=2 + i, **step_kw)
+    r1.record()
+    torch.cuda.synchronize(dev)
+    roll_ms = r0.elapsed_time(r1)
+
     # ---- eager (one python call per launch) figure, for the launch-bound picture
     n_eager = min(K, 2000)
     torch.cuda.synchronize(dev)
@@ -387,6 +401,9 @@ def run_ours(args, rank, world, local_rank):
                                    % n_ov, "value": world * envs * K / (ms_overlap * 1e-3), "unit": "env-steps/s",
                            "us_per_step": ms_overlap / K * 1e3, "achieved_gbs": ov_achieved,
                            "frac_of_hbm_peak": ov_achieved / peak},
+            "rollout": {"note": "ngw_rollout: %d steps per launch, on-device uniform random policy, tile resident in "
+                                "shared memory; outputs are per-env sums + final observation" % roll_T,
+                        "value": world * envs * roll_T * n_roll / (roll_ms * 1e-3), "unit": "env-steps/s"},
             "eager": {"value": envs / (eager_ms * 1e-3), "unit": "env-steps/s", "us_per_step": eager_ms * 1e3},
             "episode_stats": dict(zip(('steps', 'episodes', 'successes', 'reward_sum', 'cost_sum', 'resets',
                                        'invalid'), [float(x) for x in stats.cpu().numpy()[:7]])),

@@ -90,6 +90,13 @@ struct StepParams {
     int map_bytes, inv_bytes, obs_bytes, region_bytes;   // per-warp shared-memory carve-up
     int auto_reset, max_episode_steps;
     int plain_store;            // 1 => write tiles back with ordinary coalesced stores instead of TMA bulk stores
+    // K-step rollout (n_steps > 1 or random policy): the tile stays in shared memory across the steps
+    int n_steps;                // steps per launch (1 for ngw_step)
+    int random_policy;          // 1 => actions drawn on the device (Philox), `actions` is only a non-null marker
+    long long act_stride;       // elements between consecutive steps in `actions` / `actions_out`
+    unsigned long long policy_seed;
+    int32_t* done_count;        // optional: episodes finished per env during the launch
+    int32_t* actions_out;       // optional: actions taken
 };
 
 // Kernel argument block: the parameters plus up to NC configs INLINE, so that every config read in the hot path
@@ -148,7 +155,7 @@ __device__ __noinline__ void auto_reset_warp(const StepParams& p, const DevConfi
 // One CTA = one tile of 32 consecutive envs, G = blockDim.x / 32 warps.  Lane l of every warp owns env l of the tile.
 // Warp 0 runs the flattened step; then all G warps cast 8/G lidar beams each for their lane's env.  G = 1 is the plain
 // one-warp-per-tile kernel; G > 1 shortens the per-tile latency where shared memory limits the tiles per SM.
-template <bool kTma, int NC>
+template <bool kTma, int NC, bool kMulti>
 __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepArgs<NC> args) {
     extern __shared__ __align__(128) unsigned char smem[];
     // Programmatic dependent launch: let the next kernel of the stream start scheduling its CTAs now; everything up
@@ -226,60 +233,78 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
         if (stepping) {
             StepOut o;
             o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f;
-            int invalid = 0, did_reset = 0, success = 0;
-            if (valid) {
-                ngw_action_entry a;
-                a.op = NGW_OP_INVALID;
-                if (action >= 0 && action < cfg.n_actions) {
-                    uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
-                    memcpy(&a, &raw, sizeof(a));
+            float reward_sum = 0.0f, cost_sum = 0.0f;
+            int done_count = 0;
+            const int n_steps = kMulti ? p.n_steps : 1;               // kMulti == false: the plain one-step kernel
+            const bool random_policy = kMulti && p.random_policy;
+            for (int t = 0; t < n_steps; t++) {
+                int next_action = 0;                                  // prefetch the next step's action behind this step
+                if (!random_policy && t + 1 < n_steps && valid) next_action = p.actions[(t + 1) * p.act_stride + e];
+                if (random_policy && valid) {                         // uniform over the config's action ids
+                    Philox pr;
+                    pr.init(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, 0xFFF);
+                    action = (int)pr.below((uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
                 }
-                if (a.op == NGW_OP_INVALID) {                         // wrappers.py:76 / pogostick_v1_env.py:236 would raise
-                    invalid = 1;
-                    p.err[e] |= NGW_ERR_INVALID_ACTION;
-                } else {
-                    step_env(env, cfg, a, o);
-                    success = o.done && env.inv[cfg.id_goal] >= 1;
-                    int finished = o.done;
-                    if (p.max_episode_steps > 0) {
-                        int len = p.ep_len[e] + 1;
-                        if (len >= p.max_episode_steps) { finished = 1; o.done = 1; }     // harness truncation knob
-                        p.ep_len[e] = finished && p.auto_reset ? 0 : len;
+                if (kMulti && p.actions_out != nullptr && valid) p.actions_out[t * p.act_stride + e] = action;
+                o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f;
+                int invalid = 0, did_reset = 0, success = 0;
+                if (valid) {
+                    ngw_action_entry a;
+                    a.op = NGW_OP_INVALID;
+                    if (action >= 0 && action < cfg.n_actions) {
+                        uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
+                        memcpy(&a, &raw, sizeof(a));
                     }
-                    if (finished && p.auto_reset) { did_reset = 1; }
+                    if (a.op == NGW_OP_INVALID) {                     // wrappers.py:76 / pogostick_v1_env.py:236 would raise
+                        invalid = 1;
+                        p.err[e] |= NGW_ERR_INVALID_ACTION;
+                    } else {
+                        step_env(env, cfg, a, o);
+                        success = o.done && env.inv[cfg.id_goal] >= 1;
+                        int finished = o.done;
+                        if (p.max_episode_steps > 0) {
+                            int len = p.ep_len[e] + 1;
+                            if (len >= p.max_episode_steps) { finished = 1; o.done = 1; } // harness truncation knob
+                            p.ep_len[e] = finished && p.auto_reset ? 0 : len;
+                        }
+                        if (finished && p.auto_reset) { did_reset = 1; }
+                    }
+                    ps = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
+                                     (unsigned char)env.sel);
+                    reward_sum += (float)o.reward; cost_sum += o.cost; done_count += o.done;
                 }
-                ps = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
-                                 (unsigned char)env.sel);
-            }
-            if (p.auto_reset && __any_sync(0xFFFFFFFFu, did_reset)) {     // rare: regenerate finished episodes, warp-cooperatively
-                auto_reset_warp(p, p.dcfgs, cfg_i, did_reset != 0, smap, sinv, sscratch, e0, ps);
-                env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+                if (p.auto_reset && __any_sync(0xFFFFFFFFu, did_reset)) { // rare: regenerate finished episodes, warp-cooperatively
+                    auto_reset_warp(p, p.dcfgs, cfg_i, did_reset != 0, smap, sinv, sscratch, e0, ps);
+                    env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+                }
+                if (p.stats != nullptr) {
+                    int n_done = __reduce_add_sync(0xFFFFFFFFu, valid ? o.done : 0);
+                    int n_succ = __reduce_add_sync(0xFFFFFFFFu, success);
+                    int n_reset = __reduce_add_sync(0xFFFFFFFFu, did_reset);
+                    int n_inv = __reduce_add_sync(0xFFFFFFFFu, invalid);
+                    int n_valid = __reduce_add_sync(0xFFFFFFFFu, valid ? 1 : 0);
+                    int r_sum = __reduce_add_sync(0xFFFFFFFFu, o.reward);
+                    float c_sum = warp_sum(o.cost);
+                    if (lane == 0) {
+                        double* s = p.stats + (size_t)(blockIdx.x % NGW_STAT_SLOTS) * NGW_STAT_COUNT;
+                        atomicAdd(&s[NGW_STAT_STEPS], (double)(n_valid - n_inv));
+                        atomicAdd(&s[NGW_STAT_REWARD_SUM], (double)r_sum);
+                        atomicAdd(&s[NGW_STAT_COST_SUM], (double)c_sum);
+                        if (n_done) atomicAdd(&s[NGW_STAT_EPISODES], (double)n_done);
+                        if (n_succ) atomicAdd(&s[NGW_STAT_SUCCESSES], (double)n_succ);
+                        if (n_reset) atomicAdd(&s[NGW_STAT_RESETS], (double)n_reset);
+                        if (n_inv) atomicAdd(&s[NGW_STAT_INVALID], (double)n_inv);
+                    }
+                }
+                action = next_action;
             }
             if (valid) {
                 p.pose[e] = ps;
-                p.reward[e] = (float)o.reward;
+                p.reward[e] = reward_sum;                             // == the step's reward when n_steps == 1
                 p.done[e] = (uint8_t)o.done;
-                p.cost[e] = o.cost;
+                p.cost[e] = cost_sum;
                 p.result[e] = (uint8_t)o.result;
-            }
-            if (p.stats != nullptr) {
-                int n_done = __reduce_add_sync(0xFFFFFFFFu, valid ? o.done : 0);
-                int n_succ = __reduce_add_sync(0xFFFFFFFFu, success);
-                int n_reset = __reduce_add_sync(0xFFFFFFFFu, did_reset);
-                int n_inv = __reduce_add_sync(0xFFFFFFFFu, invalid);
-                int n_valid = __reduce_add_sync(0xFFFFFFFFu, valid ? 1 : 0);
-                int r_sum = __reduce_add_sync(0xFFFFFFFFu, o.reward);
-                float c_sum = warp_sum(o.cost);
-                if (lane == 0) {
-                    double* s = p.stats + (size_t)(blockIdx.x % NGW_STAT_SLOTS) * NGW_STAT_COUNT;
-                    atomicAdd(&s[NGW_STAT_STEPS], (double)(n_valid - n_inv));
-                    atomicAdd(&s[NGW_STAT_REWARD_SUM], (double)r_sum);
-                    atomicAdd(&s[NGW_STAT_COST_SUM], (double)c_sum);
-                    if (n_done) atomicAdd(&s[NGW_STAT_EPISODES], (double)n_done);
-                    if (n_succ) atomicAdd(&s[NGW_STAT_SUCCESSES], (double)n_succ);
-                    if (n_reset) atomicAdd(&s[NGW_STAT_RESETS], (double)n_reset);
-                    if (n_inv) atomicAdd(&s[NGW_STAT_INVALID], (double)n_inv);
-                }
+                if (kMulti && p.done_count != nullptr) p.done_count[e] = done_count;
             }
         }
         if (G > 1) spose[lane] = ps;
@@ -579,14 +604,22 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
         if (v == 1 || v == 2 || v == 4 || v == 8) warps = v;
     }
     h->warps = warps;
-    CK(cudaFuncSetAttribute(step_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<true, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<true, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<true, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<false, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(step_kernel<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     *out = h;
     return 0;
 }
@@ -670,6 +703,7 @@ static StepParams step_params(ngw_handle* h, const int32_t* actions, int32_t* ob
     p.map_bytes = h->map_bytes; p.inv_bytes = h->inv_bytes; p.obs_bytes = h->obs_bytes;
     p.region_bytes = h->region_bytes; p.auto_reset = auto_reset; p.max_episode_steps = max_episode_steps;
     p.plain_store = h->plain_store ? 1 : 0;
+    p.n_steps = 1; p.random_policy = 0; p.act_stride = 0; p.policy_seed = 0; p.done_count = nullptr; p.actions_out = nullptr;
     return p;
 }
 
@@ -691,8 +725,14 @@ static void launch_step_nc(ngw_handle* h, const StepParams& p, int blocks, size_
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(s, &cap);
     lc.attrs = attr; lc.numAttrs = (h->use_pdl && cap == cudaStreamCaptureStatusNone) ? 1 : 0;
-    if (h->use_tma) cudaLaunchKernelEx(&lc, step_kernel<true, NC>, args);
-    else cudaLaunchKernelEx(&lc, step_kernel<false, NC>, args);
+    const bool multi = p.n_steps > 1 || p.random_policy || p.done_count != nullptr || p.actions_out != nullptr;
+    if (h->use_tma) {
+        if (multi) cudaLaunchKernelEx(&lc, step_kernel<true, NC, true>, args);
+        else cudaLaunchKernelEx(&lc, step_kernel<true, NC, false>, args);
+    } else {
+        if (multi) cudaLaunchKernelEx(&lc, step_kernel<false, NC, true>, args);
+        else cudaLaunchKernelEx(&lc, step_kernel<false, NC, false>, args);
+    }
 }
 
 static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
@@ -720,6 +760,23 @@ int ngw_step(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward,
     CK(cudaSetDevice(h->device));
     return launch_step(h, step_params(h, actions, obs, reward, done, step_cost, result, auto_reset, max_episode_steps,
                                       0, h->n), (cudaStream_t)stream);
+}
+
+int ngw_rollout(ngw_handle* h, const int32_t* actions, int32_t n_steps, uint64_t policy_seed, int32_t* obs,
+                float* reward_sum, float* cost_sum, int32_t* done_count, uint8_t* last_done, uint8_t* last_result,
+                int32_t* actions_out, int32_t auto_reset, int32_t max_episode_steps, void* stream) {
+    if (!h) return fail("null handle");
+    if (n_steps < 1) return fail("ngw_rollout: n_steps must be >= 1");
+    if (!reward_sum || !cost_sum || !last_done || !last_result) return fail("ngw_rollout: null output pointer");
+    if (h->obs_dim > 0 && obs && ((uintptr_t)obs & 15)) return fail("ngw_rollout: obs must be 16-byte aligned");
+    CK(cudaSetDevice(h->device));
+    // any non-null pointer marks "stepping"; with the random policy it is never dereferenced
+    const int32_t* act = actions ? actions : reinterpret_cast<const int32_t*>(h->zero_byte);
+    StepParams p = step_params(h, act, obs, reward_sum, last_done, cost_sum, last_result, auto_reset, max_episode_steps,
+                               0, h->n);
+    p.n_steps = n_steps; p.random_policy = actions ? 0 : 1; p.act_stride = h->n; p.policy_seed = policy_seed;
+    p.done_count = done_count; p.actions_out = actions_out;
+    return launch_step(h, p, (cudaStream_t)stream);
 }
 
 int ngw_observe(ngw_handle* h, int32_t* obs, void* stream) {

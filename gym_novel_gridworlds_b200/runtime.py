@@ -136,6 +136,25 @@ class BatchHandle(object):
                                                self._stream()))
         return self.obs, self.reward, self.done, self.step_cost, self.result
 
+    def rollout(self, n_steps, actions=None, policy_seed=0, auto_reset=False, max_episode_steps=0,
+                record_actions=False):
+        """n_steps consecutive steps in ONE launch (tile resident in shared memory).  actions: int32 CUDA tensor
+        [n_steps, n] or None for the on-device uniform random policy.  Returns (obs after the last step, reward sum,
+        step_cost sum, episodes finished, last done, last result[, actions taken])."""
+        if actions is not None:
+            actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+            assert actions.shape == (n_steps, self.n)
+        if not hasattr(self, '_done_count'):
+            self._done_count = torch.zeros(self.n, dtype=torch.int32, device=self.device)
+        taken = torch.empty((n_steps, self.n), dtype=torch.int32, device=self.device) if record_actions else None
+        capi.check(self.lib, self.lib.ngw_rollout(
+            self._h, _ptr(actions), int(n_steps), int(policy_seed) & (2 ** 64 - 1),
+            _ptr(self.obs) if self.obs_dim else None, _ptr(self.reward), _ptr(self.step_cost), _ptr(self._done_count),
+            _ptr(self.done), _ptr(self.result), _ptr(taken), int(bool(auto_reset)), int(max_episode_steps),
+            self._stream()))
+        out = (self.obs, self.reward, self.step_cost, self._done_count, self.done, self.result)
+        return out + (taken,) if record_actions else out
+
     def observe(self):
         if self.obs_dim:
             capi.check(self.lib, self.lib.ngw_observe(self._h, _ptr(self.obs), self._stream()))

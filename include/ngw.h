@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define NGW_ABI_VERSION 4
+#define NGW_ABI_VERSION 5
 
 #define NGW_MAX_ITEMS 24          /* reference asserts len(items) <= 20 (pogostick_v1_env.py:75,220) */
 #define NGW_MAX_ACTIONS 48
@@ -231,6 +231,15 @@ int ngw_step(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward,
  * the outputs are valid on the host. */
 int ngw_step_host(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done,
                   float* step_cost, uint8_t* result, int32_t auto_reset, int32_t max_episode_steps);
+
+/* K-step rollout in ONE launch: every tile stays in shared memory for n_steps consecutive steps.
+ * actions: DEVICE int32[n_steps][n_envs], or NULL = uniform random policy drawn on the device with Philox
+ * (policy_seed, global env id, step index) — the tests/random_action.py loop without the host.  reward_sum / cost_sum
+ * accumulate over the steps, done_count counts finished episodes, last_done / last_result are the final step's, obs is
+ * the observation after the last step; actions_out (DEVICE int32[n_steps][n_envs], NULL = skip) records the actions. */
+int ngw_rollout(ngw_handle* h, const int32_t* actions, int32_t n_steps, uint64_t policy_seed, int32_t* obs,
+                float* reward_sum, float* cost_sum, int32_t* done_count, uint8_t* last_done, uint8_t* last_result,
+                int32_t* actions_out, int32_t auto_reset, int32_t max_episode_steps, void* stream);
 
 /* LidarInFront.observation of the current state into DEVICE int32[n_envs][obs_dim]. */
 int ngw_observe(ngw_handle* h, int32_t* obs, void* stream);

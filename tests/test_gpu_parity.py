@@ -186,3 +186,36 @@ def test_single_env_api_reproduces_survey_kat():
     assert list(nz) == [6, 11, 18, 27, 34, 41, 42, 55, 57, 60] and list(obs[nz]) == [5, 4, 2, 5, 4, 4, 1, 4, 2, 4]
     with pytest.raises(AssertionError):
         env.step(10)
+
+
+def test_rollout_kernel_equals_repeated_steps():
+    """T steps in one launch == T launches (same states, observation, sums), given and random policy."""
+    cc = _compiled({'env': scenarios.POGO, 'map_size': 10, 'chain': [['limit', scenarios.C2_SET], ['lidar', 8]]})
+    n, T = 3000 + 9, 40
+    ob = OracleBatch([cc], n)
+    ob.reset_legacy(31337)
+    h1, h2, h3 = BatchHandle([cc], n), BatchHandle([cc], n), BatchHandle([cc], n)
+    for h in (h1, h2, h3):
+        h.load_state(ob.map, ob.pose, ob.inv)
+    rng = np.random.RandomState(5)
+    acts = rng.randint(0, cc.c.n_actions, size=(T, n)).astype(np.int32)
+    rew = np.zeros(n); cost = np.zeros(n); dones = np.zeros(n, int)
+    for t in range(T):
+        o, r, d, c, res = h1.step(torch.from_numpy(acts[t]).cuda())
+        rew += r.cpu().numpy(); cost += c.cpu().numpy().astype(np.float64); dones += d.cpu().numpy()
+    obs2, r2, c2, dc2, d2, res2 = h2.rollout(T, torch.from_numpy(acts).cuda())
+    assert torch.equal(h1.map, h2.map) and torch.equal(h1.pose, h2.pose) and torch.equal(h1.inventory, h2.inventory)
+    assert torch.equal(obs2, o) and torch.equal(d2, d) and torch.equal(res2, res)
+    assert np.array_equal(r2.cpu().numpy(), rew) and np.array_equal(dc2.cpu().numpy(), dones)
+    np.testing.assert_allclose(c2.cpu().numpy(), cost, rtol=1e-5)
+    # on-device random policy: replay the recorded actions through the oracle
+    out = h3.rollout(T, None, policy_seed=99, record_actions=True)
+    taken = out[-1].cpu().numpy()
+    assert taken.min() >= 0 and taken.max() < cc.c.n_actions
+    counts = np.bincount(taken.ravel(), minlength=cc.c.n_actions) / taken.size
+    assert np.abs(counts - 1.0 / cc.c.n_actions).max() < 0.01         # uniform policy
+    for t in range(T):
+        o_obs, o_rew, o_done, o_cost, o_res = ob.step(taken[t])
+    assert np.array_equal(h3.map.cpu().numpy().reshape(n, -1), ob.map)
+    assert np.array_equal(h3.inventory.cpu().numpy(), ob.inv) and np.array_equal(h3.pose.cpu().numpy(), ob.pose)
+    assert np.array_equal(out[0].cpu().numpy()[:, :cc.obs_dim], o_obs)

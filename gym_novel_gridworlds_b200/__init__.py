@@ -12,7 +12,7 @@
 """
 from .core import make, register, registry, Env, Wrapper  # noqa: F401
 from . import envs, wrappers, observation_wrappers, novelty_wrappers, spaces  # noqa: F401
-from .wrappers import LimitActions  # noqa: F401
+from .wrappers import LimitActions, SaveTrajectories  # noqa: F401
 from .observation_wrappers import LidarInFront, AgentMap  # noqa: F401
 from .novelty_wrappers import inject_novelty  # noqa: F401
 

@@ -286,10 +286,37 @@ class ChainRuntime(object):
         b.block_in_front_id = int(b.map[fr][fc])
         b.block_in_front_str = names[b.block_in_front_id]
 
-    def reset(self, **kwargs):
+    def _restore_from(self, src_env):
+        """The `env=` branch of reset (pogostick_v1_env.py:89-109, tests/test_multi_agent.py:55): tables and state are
+        copied from another env (device-to-device through ngw_load_state); selected_item is NOT copied, as there."""
+        import copy
+        b, src = self.base, src_env.unwrapped
+        src_rt = src._runtime
+        if src_rt is None or src_rt.handle is None:
+            raise RuntimeError("the env to restore from has not been reset yet")
+        b.map_size = copy.deepcopy(src.map_size)
+        b.items_id = copy.deepcopy(src.items_id)
+        b.items_quantity = copy.deepcopy(src.items_quantity)
         h = self._ensure()
-        cc = self.compiled
-        obs = h.reset(want_obs=(cc.reset_returns == 'lidar'))
+        sh = src_rt.handle
+        if sh.n != h.n:
+            raise ValueError("restore needs the same num_envs (%d vs %d)" % (sh.n, h.n))
+        pose = sh.pose.clone()
+        pose[:, 3] = h.pose[:, 3]
+        n = min(sh.inv_stride, h.inv_stride)
+        h.load_state(sh.map, pose, sh.inventory[:, :n].contiguous())
+        obs = h.observe() if self.compiled.reset_returns == 'lidar' else None
+        return h, obs
+
+    def reset(self, **kwargs):
+        if self.base.env is not None:
+            print("RESTORING " + self.base.env_id + " ...")                # pogostick_v1_env.py:90
+            h, obs = self._restore_from(self.base.env)
+            cc = self.compiled
+        else:
+            h = self._ensure()
+            cc = self.compiled
+            obs = h.reset(want_obs=(cc.reset_returns == 'lidar'))
         if self.single:
             torch.cuda.current_stream(h.device).synchronize()
             if int(h.error_flags[0].item()) & oc.ERR_PLACEMENT:

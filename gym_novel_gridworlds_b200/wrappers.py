@@ -1,6 +1,51 @@
-"""LimitActions as a config builder (reference: wrappers.py:57-85)."""
+"""LimitActions as a config builder and SaveTrajectories as a host-side logger (reference: wrappers.py:9-85)."""
+import os
+import pickle
+from datetime import datetime
+
 from . import spaces
 from .core import Wrapper, _Invalid
+
+
+class SaveTrajectories(Wrapper):
+    """Records the state after every step and pickles the list (wrappers.py:9-54), same dict schema.  With
+    num_envs == 1 the values are the reference's python objects; batched envs store CPU copies of the state tensors."""
+
+    def __init__(self, env, save_path):
+        super().__init__(env)
+        self.save_path = save_path
+        os.makedirs(self.save_path, exist_ok=True)
+        self.state_trajectories = []
+
+    def step(self, action_id):
+        obs, reward, done, info = self.unwrapped._runtime_for(self).step(action_id)
+        self.last_done = done
+        self.state_trajectories.append(self.get_state())
+        return obs, reward, done, info
+
+    def get_state(self):
+        base = self.unwrapped
+        rt = base._runtime
+        if base.num_envs == 1:
+            fields = {"map": base.map, "agent_location": base.agent_location,
+                      "agent_facing_str": base.agent_facing_str, "block_in_front_id": base.block_in_front_id,
+                      "inventory_items_quantity": base.inventory_items_quantity}
+        else:
+            m, pose, inv = [x.cpu().numpy() for x in rt.handle.export_state()]
+            names = rt.compiled.item_names
+            fields = {"map": m, "agent_location": pose[:, 0:2], "agent_facing_id": pose[:, 2],
+                      "inventory_items_quantity": {n: inv[:, i] for i, n in enumerate(names) if n in base.items}}
+        fields.update({"map_size": base.map_size, "items_id": base.items_id, "items_quantity": base.items_quantity,
+                       "action_str": base.actions_id, "last_action": base.last_action, "last_done": self.last_done})
+        return fields
+
+    def save(self):
+        path = os.path.join(self.save_path,
+                            datetime.now().strftime("%Y-%m-%d-%H-%M-%S") + "_{env}.bin".format(env=self.env.env_id))
+        with open(path, 'wb') as f:
+            pickle.dump(self.state_trajectories, f)
+        print("Trajectories saved at: ", path)
+        return path
 
 
 class LimitActions(Wrapper):

@@ -219,3 +219,31 @@ def test_rollout_kernel_equals_repeated_steps():
     assert np.array_equal(h3.map.cpu().numpy().reshape(n, -1), ob.map)
     assert np.array_equal(h3.inventory.cpu().numpy(), ob.inv) and np.array_equal(h3.pose.cpu().numpy(), ob.pose)
     assert np.array_equal(out[0].cpu().numpy()[:, :cc.obs_dim], o_obs)
+
+
+def test_env_restore_chaining_and_save_trajectories(tmp_path):
+    """the `env=` restore branch of reset (pogostick_v1_env.py:89-109) and the SaveTrajectories schema."""
+    import pickle
+    import gym_novel_gridworlds_b200 as gym
+    for n in (1, 300):
+        first = gym.LidarInFront(gym.make('NovelGridworld-Pogostick-v1', num_envs=n, seed=3))
+        first.reset()
+        a = 3 if n == 1 else torch.full((n,), 3, dtype=torch.int32, device='cuda')
+        first.step(a)
+        second = gym.LidarInFront(gym.make('NovelGridworld-Pogostick-v1', num_envs=n, env=first))
+        obs = second.reset()
+        h1, h2 = first.unwrapped._runtime.handle, second.unwrapped._runtime.handle
+        assert torch.equal(h1.map, h2.map) and torch.equal(h1.inventory, h2.inventory)
+        assert torch.equal(h1.pose[:, :3], h2.pose[:, :3])
+        o1 = first.observation()
+        assert np.array_equal(np.asarray(obs if n == 1 else obs.cpu().numpy()), np.asarray(o1 if n == 1 else o1.cpu().numpy()))
+    env = gym.SaveTrajectories(gym.make('NovelGridworld-Bow-v1'), str(tmp_path))
+    env.reset()
+    for a in (0, 1, 3):
+        env.step(a)
+    path = env.save()
+    with open(path, 'rb') as f:
+        traj = pickle.load(f)
+    assert len(traj) == 3
+    assert set(traj[0]) == {"map_size", "map", "agent_location", "agent_facing_str", "block_in_front_id", "items_id",
+                            "items_quantity", "inventory_items_quantity", "action_str", "last_action", "last_done"}

@@ -70,7 +70,10 @@ struct StepOut {
     int done;
     int result;
     float cost;
+    int msg;        // enum ngw_msg | argument << 5
 };
+
+__device__ __forceinline__ int msg_of(int code, int arg) { return code | (arg << 5); }
 
 __device__ __forceinline__ int cell(const EnvRow& e, int r, int c) { return e.m[r * e.ms + c]; }
 
@@ -115,20 +118,30 @@ __device__ __forceinline__ void grab_entities(EnvRow& e, const ngw_config& cfg) 
 }
 
 // craft (pogostick_v1_env.py:413-474, bow_v1_env.py:386-441, novelty_wrappers.py:371-436)
-__device__ __forceinline__ void craft(EnvRow& e, const ngw_config& cfg, const ngw_recipe& rc, StepOut& o) {
-    bool have_all = true;
+__device__ __forceinline__ void craft(EnvRow& e, const ngw_config& cfg, int slot, StepOut& o) {
+    const ngw_recipe& rc = cfg.recipes[slot];
+    int missing = 0;
     int n_in = rc.n_inputs;
     for (int i = 0; i < n_in; i++) {
         int item = rc.in_item[i];
-        have_all &= (item != NGW_NONE) && (e.inv[item == NGW_NONE ? 0 : item] >= (int)rc.in_qty[i]);
+        bool have = (item != NGW_NONE) && (e.inv[item == NGW_NONE ? 0 : item] >= (int)rc.in_qty[i]);
+        missing |= have ? 0 : (1 << i);
     }
-    if (!have_all) { o.result = 0; o.cost = rc.cost_missing; return; }
+    if (missing) {
+        o.result = 0; o.cost = rc.cost_missing;
+        o.msg = msg_of(NGW_MSG_MISSING, slot | (missing << 3));
+        return;
+    }
     if (rc.needs_table) {
         int fr, fc;
         front_of(e, fr, fc);
-        if (cell(e, fr, fc) != cfg.id_crafting_table) { o.result = 0; o.cost = rc.cost_no_table; return; }
+        if (cell(e, fr, fc) != cfg.id_crafting_table) {
+            o.result = 0; o.cost = rc.cost_no_table; o.msg = NGW_MSG_NEED_TABLE;
+            return;
+        }
     }
     o.reward = rc.reward_ok;
+    o.msg = msg_of(NGW_MSG_CRAFTED, rc.out_item);
     for (int i = 0; i < n_in; i++) e.inv[rc.in_item[i]] -= (int)rc.in_qty[i];
     e.inv[rc.out_item] += (int)rc.out_qty;
     o.cost = rc.cost_ok;
@@ -139,10 +152,10 @@ __device__ __forceinline__ void craft(EnvRow& e, const ngw_config& cfg, const ng
 __device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_config& cfg, const ngw_action_entry a, StepOut& o) {
     int fr, fc;
     front_of(e, fr, fc);
-    o.reward = -1; o.result = 1; o.cost = 0.0f; o.done = 0;         // pogostick_v1_env.py:239-242
+    o.reward = -1; o.result = 1; o.cost = 0.0f; o.done = 0; o.msg = 0;   // pogostick_v1_env.py:239-242
     switch (a.op) {
         case NGW_OP_FORWARD:                                          // pogostick_v1_env.py:244-257
-            if (cell(e, fr, fc) == 0) { e.r = fr; e.c = fc; } else o.result = 0;
+            if (cell(e, fr, fc) == 0) { e.r = fr; e.c = fc; } else { o.result = 0; o.msg = NGW_MSG_BLOCK_IN_PATH; }
             o.cost = 27.906975f;
             break;
         case NGW_OP_LEFT:                                             // N->W S->E W->S E->N  (0->2 1->3 2->1 3->0)
@@ -154,7 +167,7 @@ __device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_config& cfg, co
         case NGW_OP_BREAK: {
             int front = cell(e, fr, fc);
             o.cost = 3600.0f;
-            if (in_mask(cfg.unbreakable_mask, front)) { o.result = 0; break; }
+            if (in_mask(cfg.unbreakable_mask, front)) { o.result = 0; o.msg = msg_of(NGW_MSG_CANNOT_BREAK, front); break; }
             int variant = a.variant;
             if (variant == NGW_BRK_BASE) {                            // pogostick_v1_env.py:283-289
                 set_cell(e, fr, fc, 0);
@@ -174,7 +187,7 @@ __device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_config& cfg, co
                     o.reward = cfg.reward_intermediate;
                     o.cost = wooden ? 1800.0f : 900.0f;
                 } else if (variant == NGW_BRK_AXETOBREAK) {
-                    o.result = 0;
+                    o.result = 0; o.msg = msg_of(NGW_MSG_NEED_AXE, a.arg);
                 } else {                                              // breaks, but no reward even for tree_log (Q4)
                     set_cell(e, fr, fc, 0);
                     e.inv[front] += 1;
@@ -187,15 +200,22 @@ __device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_config& cfg, co
             if (e.inv[cfg.id_tree_tap] >= 1 && cell(e, fr, fc) == 0) {
                 set_cell(e, fr, fc, cfg.id_tree_tap);
                 e.inv[cfg.id_tree_tap] -= 1;
+                o.msg = NGW_MSG_TAP_PLACED;
                 if (next_to(e, fr, fc, cfg.id_tree_log)) o.reward = cfg.reward_intermediate;
-            } else o.result = 0;
+            } else {
+                o.result = 0;
+                o.msg = e.inv[cfg.id_tree_tap] >= 1 ? msg_of(NGW_MSG_BLOCK_EXISTS, cell(e, fr, fc)) : NGW_MSG_NOT_IN_INVENTORY;
+            }
             break;
         case NGW_OP_EXTRACT_RUBBER:                                   // pogostick_v1_env.py:315-331, novelty_wrappers.py:1537-1551
             o.cost = 120.0f;
             if (cell(e, fr, fc) == cfg.id_tree_tap && next_to(e, fr, fc, cfg.id_tree_log)) {
                 e.inv[cfg.id_rubber] += a.arg;
                 o.reward = cfg.reward_intermediate; o.cost = 50000.0f;
-            } else o.result = 0;
+            } else {
+                o.result = 0;
+                o.msg = cell(e, fr, fc) == cfg.id_tree_tap ? NGW_MSG_NO_LOG_NEAR_TAP : NGW_MSG_NO_TAP;
+            }
             break;
         case NGW_OP_EXTRACT_STRING:                                   // bow_v1_env.py:293-304, novelty_wrappers.py:1524-1536
             o.cost = 120.0f;
@@ -203,14 +223,14 @@ __device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_config& cfg, co
                 e.inv[cfg.id_string] += a.arg;
                 set_cell(e, fr, fc, 0);
                 o.reward = cfg.reward_intermediate; o.cost = 5000.0f;
-            } else o.result = 0;
+            } else { o.result = 0; o.msg = NGW_MSG_NO_WOOL; }
             break;
         case NGW_OP_CRAFT:
-            craft(e, cfg, cfg.recipes[a.arg], o);
+            craft(e, cfg, a.arg, o);
             break;
         case NGW_OP_SELECT:                                           // pogostick_v1_env.py:338-347
             o.cost = 120.0f;
-            if (a.arg != NGW_NONE && e.inv[a.arg] >= 1) e.sel = a.arg; else o.result = 0;
+            if (a.arg != NGW_NONE && e.inv[a.arg] >= 1) e.sel = a.arg; else { o.result = 0; o.msg = NGW_MSG_NOT_IN_INVENTORY; }
             break;
         case NGW_OP_CHOP: {                                           // novelty_wrappers.py:1291-1307
             int front = cell(e, fr, fc);
@@ -219,13 +239,13 @@ __device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_config& cfg, co
                 set_cell(e, fr, fc, 0);
                 e.inv[front] += 2;
                 o.reward = cfg.reward_intermediate;
-            } else o.result = 0;
+            } else { o.result = 0; o.msg = msg_of(NGW_MSG_CANNOT_CHOP, front); }
             break;
         }
         case NGW_OP_JUMP: {                                           // novelty_wrappers.py:1363-1382
             int tr = e.r + 2 * (fr - e.r), tc = e.c + 2 * (fc - e.c);
             if (tr >= 0 && tr <= e.ms - 1 && tc >= 0 && tc <= e.ms - 1 && cell(e, tr, tc) == 0) { e.r = tr; e.c = tc; }
-            else o.result = 0;
+            else { o.result = 0; o.msg = NGW_MSG_BLOCK_IN_PATH; }
             o.cost = 27.906975f * 2.0f;
             break;
         }
@@ -287,13 +307,13 @@ __device__ __forceinline__ void step_env(EnvRow& e, const ngw_config& cfg, const
         post_step(e, cfg, o);
         first_post = n - 1;
     } else {
-        o.reward = -1; o.result = 0; o.cost = 3600.0f; o.done = 0;
+        o.reward = -1; o.result = 0; o.cost = 3600.0f; o.done = 0; o.msg = 0;
         first_post = stop;
     }
     for (int i = first_post; i >= 0; i--) {
         int layer = (layers >> (8 * i)) & 0xFF;
         if (layer == NGW_LAYER_FIREWALL) {                            // novelty_wrappers.py:1171-1189
-            if (next_to(e, e.r, e.c, cfg.id_fire_wall)) { o.reward = cfg.reward_firewall; o.done = 1; }
+            if (next_to(e, e.r, e.c, cfg.id_fire_wall)) { o.reward = cfg.reward_firewall; o.done = 1; o.msg = NGW_MSG_FIRE_WALL; }
         } else if (layer == NGW_LAYER_FENCE_MEDIUM || layer == NGW_LAYER_FENCE_HARD) {
             // outer post block re-runs and overwrites info (Q5, novelty_wrappers.py:960-973); reward is the inner one
             int reward = o.reward;
@@ -301,6 +321,9 @@ __device__ __forceinline__ void step_env(EnvRow& e, const ngw_config& cfg, const
             if (!o.done) o.reward = reward;
             o.result = (i == stop) ? 0 : 1;
             o.cost = 3600.0f;
+            // the overwritten info carries this wrapper's own message: '' unless it refused (novelty_wrappers.py:955,958)
+            o.msg = (i != stop) ? 0 : (in_mask(cfg.unbreakable_mask, front) ? msg_of(NGW_MSG_CANNOT_BREAK, front)
+                                                                             : NGW_MSG_FENCE_RESTRICTION);
         }
     }
 }

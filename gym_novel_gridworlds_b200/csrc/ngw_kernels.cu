@@ -97,6 +97,7 @@ struct StepParams {
     unsigned long long policy_seed;
     int32_t* done_count;        // optional: episodes finished per env during the launch
     int32_t* actions_out;       // optional: actions taken
+    uint16_t* msg;              // optional: info['message'] codes (enum ngw_msg | arg << 5)
 };
 
 // Kernel argument block: the parameters plus up to NC configs INLINE, so that every config read in the hot path
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
         env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
         if (stepping) {
             StepOut o;
-            o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f;
+            o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0;
             float reward_sum = 0.0f, cost_sum = 0.0f;
             int done_count = 0;
             const int n_steps = kMulti ? p.n_steps : 1;               // kMulti == false: the plain one-step kernel
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
                     action = (int)pr.below((uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
                 }
                 if (kMulti && p.actions_out != nullptr && valid) p.actions_out[t * p.act_stride + e] = action;
-                o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f;
+                o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0;
                 int invalid = 0, did_reset = 0, success = 0;
                 if (valid) {
                     ngw_action_entry a;
@@ -305,6 +306,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
                 p.cost[e] = cost_sum;
                 p.result[e] = (uint8_t)o.result;
                 if (kMulti && p.done_count != nullptr) p.done_count[e] = done_count;
+                if (p.msg != nullptr) p.msg[e] = (uint16_t)o.msg;
             }
         }
         if (G > 1) spose[lane] = ps;
@@ -467,6 +469,7 @@ struct ngw_handle {
     int8_t* map = nullptr; uchar4* pose = nullptr; int32_t* inv = nullptr; uint8_t* cfg_id = nullptr;
     uint32_t* episode = nullptr; int32_t* ep_len = nullptr; uint32_t* err = nullptr; double* stats = nullptr;
     uint8_t* zero_byte = nullptr;
+    uint16_t* msg = nullptr;                       // caller-owned message-code buffer (ngw_set_message_buffer)
     long long launches = 0;
     // host-buffer path
     cudaStream_t hs[HOST_STREAMS] = {nullptr};
@@ -487,8 +490,7 @@ void ngw_destroy(ngw_handle* h) {
     for (auto p : h->d_luts) cudaFree(p);
     cudaFree(h->d_cfgs); cudaFree(h->map); cudaFree(h->pose); cudaFree(h->inv); cudaFree(h->cfg_id);
     cudaFree(h->episode); cudaFree(h->ep_len); cudaFree(h->err); cudaFree(h->stats); cudaFree(h->zero_byte);
-    cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_done); cudaFree(h->h_cost);
-    cudaFree(h->h_result);
+    cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward);   // h_cost / h_done / h_result live in h_reward's block
     for (int i = 0; i < HOST_STREAMS; i++)
         if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
     delete h;
@@ -703,6 +705,7 @@ static StepParams step_params(ngw_handle* h, const int32_t* actions, int32_t* ob
     p.map_bytes = h->map_bytes; p.inv_bytes = h->inv_bytes; p.obs_bytes = h->obs_bytes;
     p.region_bytes = h->region_bytes; p.auto_reset = auto_reset; p.max_episode_steps = max_episode_steps;
     p.plain_store = h->plain_store ? 1 : 0;
+    p.msg = h->msg;
     p.n_steps = 1; p.random_policy = 0; p.act_stride = 0; p.policy_seed = 0; p.done_count = nullptr; p.actions_out = nullptr;
     return p;
 }
@@ -793,10 +796,20 @@ static int ensure_host_path(ngw_handle* h) {
     for (int i = 0; i < HOST_STREAMS; i++) CK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
     CK(cudaMalloc(&h->h_actions, (size_t)h->np * 4));
     if (h->obs_dim > 0) CK(cudaMalloc(&h->h_obs, (size_t)h->np * h->obs_dim * 4));
-    CK(cudaMalloc(&h->h_reward, (size_t)h->np * 4));
-    CK(cudaMalloc(&h->h_done, (size_t)h->np));
-    CK(cudaMalloc(&h->h_cost, (size_t)h->np * 4));
-    CK(cudaMalloc(&h->h_result, (size_t)h->np));
+    // reward | step_cost | done | result share one allocation, n-element sections, so that a caller whose host buffers
+    // have the same layout gets them with ONE device-to-host copy
+    unsigned char* small = nullptr;
+    CK(cudaMalloc(&small, (size_t)h->n * 10 + 64));
+    h->h_reward = reinterpret_cast<float*>(small);
+    h->h_cost = reinterpret_cast<float*>(small + (size_t)h->n * 4);
+    h->h_done = small + (size_t)h->n * 8;
+    h->h_result = small + (size_t)h->n * 9;
+    return 0;
+}
+
+int ngw_set_message_buffer(ngw_handle* h, uint16_t* msg_dev) {
+    if (!h) return fail("null handle");
+    h->msg = msg_dev;
     return 0;
 }
 
@@ -816,10 +829,15 @@ int ngw_step_host(ngw_handle* h, const int32_t* actions, int32_t* obs, float* re
                                    auto_reset, max_episode_steps, 0, n), s)) return 1;
     if (h->obs_dim > 0 && obs)
         CK(cudaMemcpyAsync(obs, h->h_obs, cnt * h->obs_dim * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(reward, h->h_reward, cnt * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(done, h->h_done, cnt, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(step_cost, h->h_cost, cnt * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(result, h->h_result, cnt, cudaMemcpyDeviceToHost, s));
+    const unsigned char* r8 = reinterpret_cast<const unsigned char*>(reward);
+    if (reinterpret_cast<const unsigned char*>(step_cost) == r8 + cnt * 4 && done == r8 + cnt * 8 && result == r8 + cnt * 9) {
+        CK(cudaMemcpyAsync(reward, h->h_reward, cnt * 10, cudaMemcpyDeviceToHost, s));   // same layout: one copy
+    } else {
+        CK(cudaMemcpyAsync(reward, h->h_reward, cnt * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(done, h->h_done, cnt, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(step_cost, h->h_cost, cnt * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(result, h->h_result, cnt, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaStreamSynchronize(s));
     return 0;
 }

@@ -155,6 +155,15 @@ class BatchHandle(object):
         out = (self.obs, self.reward, self.step_cost, self._done_count, self.done, self.result)
         return out + (taken,) if record_actions else out
 
+    def enable_messages(self, on=True):
+        """Make every following step also write info['message'] codes (uint16 per env) into self.msg."""
+        if on and getattr(self, 'msg', None) is None:
+            self.msg = torch.zeros(self.n, dtype=torch.int16, device=self.device)
+        capi.check(self.lib, self.lib.ngw_set_message_buffer(self._h, _ptr(self.msg) if on else None))
+        if not on:
+            self.msg = None
+        return self.msg
+
     def observe(self):
         if self.obs_dim:
             capi.check(self.lib, self.lib.ngw_observe(self._h, _ptr(self.obs), self._stream()))
@@ -163,13 +172,16 @@ class BatchHandle(object):
     def _host_buffers(self):
         if self._host is None:
             d = max(self.obs_dim, 1)
+            n = self.n
+            small = torch.zeros(10 * n + 64, dtype=torch.uint8).pin_memory()   # reward | step_cost | done | result
             self._host = {
-                'actions': torch.zeros(self.n, dtype=torch.int32).pin_memory(),
-                'obs': torch.zeros((self.n, d), dtype=torch.int32).pin_memory(),
-                'reward': torch.zeros(self.n, dtype=torch.float32).pin_memory(),
-                'done': torch.zeros(self.n, dtype=torch.uint8).pin_memory(),
-                'step_cost': torch.zeros(self.n, dtype=torch.float32).pin_memory(),
-                'result': torch.zeros(self.n, dtype=torch.uint8).pin_memory(),
+                'actions': torch.zeros(n, dtype=torch.int32).pin_memory(),
+                'obs': torch.zeros((n, d), dtype=torch.int32).pin_memory(),
+                'small': small,
+                'reward': small[:4 * n].view(torch.float32),
+                'step_cost': small[4 * n:8 * n].view(torch.float32),
+                'done': small[8 * n:9 * n],
+                'result': small[9 * n:10 * n],
             }
         return self._host
 
@@ -193,11 +205,41 @@ class BatchHandle(object):
         return int(self.lib.ngw_launch_count(self._h))
 
 
+_MSG_FIXED = {0: '', 1: 'Block in path', 3: 'Block tree_tap placed', 5: 'Item not found in inventory',
+              6: 'No tree_log near tree_tap', 7: 'No tree_tap found', 8: 'No wool found',
+              10: 'Need to be in front of crafting_table', 14: 'Cannot break due to fence restriction',
+              15: 'You died due to fire_wall'}
+
+
+def decode_message(code, compiled):
+    """16-bit message code (enum ngw_msg | arg << 5) -> the reference's info['message'] string."""
+    code = int(code) & 0xFFFF
+    kind, arg = code & 31, code >> 5
+    if kind in _MSG_FIXED:
+        return _MSG_FIXED[kind]
+    names = compiled.item_names
+    if kind == 2:
+        return "Cannot break " + names[arg]                                   # pogostick_v1_env.py:292
+    if kind == 4:
+        return "Block " + names[arg] + " already exists when trying to place block"   # pogostick_v1_env.py:309
+    if kind == 9:                                                              # pogostick_v1_env.py:432-440
+        rec = compiled.c.recipes[arg & 7]
+        parts = [str(rec.in_qty[i]) + ' ' + names[rec.in_item[i]] for i in range(rec.n_inputs) if (arg >> 3) & (1 << i)]
+        return "Missing items: " + ', '.join(parts)
+    if kind == 11:
+        return "Crafted " + names[arg]                                         # pogostick_v1_env.py:472
+    if kind == 12:
+        return "Cannot break without " + names[arg] + " selected"              # novelty_wrappers.py:501
+    if kind == 13:
+        return "Cannot chop " + names[arg]                                     # novelty_wrappers.py:1307
+    return ''
+
+
 class LazyInfo(object):
     """info of a batched step: tensors, converted to the reference's dict only on demand."""
 
-    def __init__(self, result, step_cost):
-        self.result, self.step_cost = result, step_cost
+    def __init__(self, result, step_cost, msg=None, compiled=None):
+        self.result, self.step_cost, self._msg, self._compiled = result, step_cost, msg, compiled
 
     def __getitem__(self, key):
         if key == 'result':
@@ -205,8 +247,16 @@ class LazyInfo(object):
         if key == 'step_cost':
             return self.step_cost
         if key == 'message':
-            return None          # host-side string formatting is outside the accelerated path
+            if self._msg is None:
+                return None      # message codes are off unless BatchHandle.enable_messages() was called
+            codes = self._msg.cpu().numpy() if hasattr(self._msg, 'cpu') else self._msg
+            cfg_ids = None
+            return [decode_message(c, self._compiled[0]) for c in codes] if len(self._compiled) == 1 else \
+                [decode_message(c, self._compiled[int(i)]) for c, i in zip(codes, self._cfg_ids())]
         raise KeyError(key)
+
+    def _cfg_ids(self):
+        return getattr(self, 'cfg_ids', [0] * len(self._msg))
 
     def keys(self):
         return ['result', 'step_cost', 'message']
@@ -222,6 +272,7 @@ class ChainRuntime(object):
         self._fingerprint = None
         self.auto_reset = False
         self.max_episode_steps = 0
+        self.messages = False          # batched envs: set True before the first reset to get info['message']
 
     # ------------------------------------------------------------------
     def _ensure(self):
@@ -233,6 +284,8 @@ class ChainRuntime(object):
             self.compiled, self._fingerprint = cc, fp
             self.handle = BatchHandle([cc], self.base.num_envs, self.base.device, self.base.rng_seed,
                                       self.base.first_env_gid)
+            if self.single or self.messages:
+                self.handle.enable_messages()
         return self.handle
 
     def close(self):
@@ -350,13 +403,14 @@ class ChainRuntime(object):
             b.step_count += 1
             b.last_reward, b.last_done = int(reward[0].item()), bool(done[0].item())
             b.last_step_cost = float(cost[0].item())
-            info = {'result': bool(result[0].item()), 'step_cost': b.last_step_cost, 'message': ''}
+            info = {'result': bool(result[0].item()), 'step_cost': b.last_step_cost,
+                    'message': decode_message(h.msg[0].item(), cc)}
             o = (obs[0, :cc.obs_dim].cpu().numpy().astype(np.int64) if cc.obs_dim else self.dict_observation())
             return o, b.last_reward, b.last_done, info
         if isinstance(action, torch.Tensor) and action.is_cuda:
             obs, reward, done, cost, result = h.step(action, self.auto_reset, self.max_episode_steps)
             o = obs[:, :cc.obs_dim] if cc.obs_dim else self.dict_observation()
-            return o, reward, done.view(torch.bool), LazyInfo(result.view(torch.bool), cost)
+            return o, reward, done.view(torch.bool), LazyInfo(result.view(torch.bool), cost, getattr(h, 'msg', None), [cc])
         obs, reward, done, cost, result = h.step_host(action, self.auto_reset, self.max_episode_steps)
         o = obs[:, :cc.obs_dim] if cc.obs_dim else self.dict_observation()
         return o, reward, done.view(np.bool_), LazyInfo(result.view(np.bool_), cost)

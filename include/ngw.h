@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define NGW_ABI_VERSION 5
+#define NGW_ABI_VERSION 6
 
 #define NGW_MAX_ITEMS 24          /* reference asserts len(items) <= 20 (pogostick_v1_env.py:75,220) */
 #define NGW_MAX_ACTIONS 48
@@ -169,6 +169,28 @@ typedef struct {
     int32_t reset_obs_after_ops;       /* how many reset ops have run when the reset observation is taken (quirk Q3) */
 } ngw_config;
 
+/* info['message'] as a 16-bit code: low 5 bits = enum ngw_msg, high 11 bits = argument (item id, or for MISSING the
+ * recipe slot in bits 0-2 and a mask of the missing ingredients, by recipe input position, in bits 3-6).
+ * The host layer formats the reference's strings lazily (runtime.decode_message). */
+enum ngw_msg {
+    NGW_MSG_NONE = 0,
+    NGW_MSG_BLOCK_IN_PATH = 1,        /* pogostick_v1_env.py:255, novelty_wrappers.py:1380 */
+    NGW_MSG_CANNOT_BREAK = 2,         /* "Cannot break <item>" pogostick_v1_env.py:292, novelty_wrappers.py:84,958 */
+    NGW_MSG_TAP_PLACED = 3,           /* pogostick_v1_env.py:301 */
+    NGW_MSG_BLOCK_EXISTS = 4,         /* "Block <item> already exists when trying to place block" pogostick_v1_env.py:309 */
+    NGW_MSG_NOT_IN_INVENTORY = 5,     /* pogostick_v1_env.py:312,347 */
+    NGW_MSG_NO_LOG_NEAR_TAP = 6,      /* pogostick_v1_env.py:328 */
+    NGW_MSG_NO_TAP = 7,               /* pogostick_v1_env.py:331 */
+    NGW_MSG_NO_WOOL = 8,              /* bow_v1_env.py:304 */
+    NGW_MSG_MISSING = 9,              /* "Missing items: 2 plank, 1 stick" pogostick_v1_env.py:432-440 */
+    NGW_MSG_NEED_TABLE = 10,          /* pogostick_v1_env.py:452 */
+    NGW_MSG_CRAFTED = 11,             /* "Crafted <item>" pogostick_v1_env.py:472 */
+    NGW_MSG_NEED_AXE = 12,            /* "Cannot break without <axe> selected" novelty_wrappers.py:501 */
+    NGW_MSG_CANNOT_CHOP = 13,         /* novelty_wrappers.py:1307 */
+    NGW_MSG_FENCE_RESTRICTION = 14,   /* novelty_wrappers.py:955 */
+    NGW_MSG_FIRE_WALL = 15            /* novelty_wrappers.py:1189 */
+};
+
 /* per-env error flags (ngw_error_flags) */
 #define NGW_ERR_INVALID_ACTION 1u      /* AssertionError wrappers.py:76 / ValueError pogostick_v1_env.py:236 */
 #define NGW_ERR_PLACEMENT 2u           /* AssertionError "Cannot place items, increase map size!" pogostick_v1_env.py:167 */
@@ -225,6 +247,10 @@ int ngw_reset(ngw_handle* h, const uint8_t* mask, int32_t* obs, void* stream);
  * max_episode_steps > 0).  All pointers are DEVICE pointers; obs may be NULL when obs_dim == 0. */
 int ngw_step(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done,
              float* step_cost, uint8_t* result, int32_t auto_reset, int32_t max_episode_steps, void* stream);
+
+/* Optional: DEVICE uint16[n_envs] that every following ngw_step / ngw_rollout fills with the step's message code
+ * (NULL switches it off again; off by default — the hot path then writes nothing). */
+int ngw_set_message_buffer(ngw_handle* h, uint16_t* msg_dev);
 
 /* Same call with HOST buffers (the reference-facing path): copies actions in, steps, copies
  * obs/reward/done/step_cost/result out, chunk-pipelined over internal pinned staging; returns after

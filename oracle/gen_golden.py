@@ -71,7 +71,7 @@ def run_scenario(ns, desc, out):
            else sorted(set(env.actions_id.values())))
     meta = dict(desc)
     rec = {k: [] for k in ('reset_map', 'reset_pose', 'reset_inv', 'reset_obs', 'init_map', 'init_pose', 'init_inv',
-                           'actions', 'obs', 'reward', 'done', 'cost', 'result', 'map', 'pose', 'inv')}
+                           'actions', 'obs', 'reward', 'done', 'cost', 'result', 'map', 'pose', 'inv', 'message')}
     seeds = []
     reset_kind = None
     for ep in range(EPISODES):
@@ -96,12 +96,12 @@ def run_scenario(ns, desc, out):
             perturb(base, rng)
         m, p, v = snapshot(base)
         rec['init_map'].append(m); rec['init_pose'].append(p); rec['init_inv'].append(v)
-        A, O, R, D, Cst, Res, M, P, V = [], [], [], [], [], [], [], [], []
+        A, O, R, D, Cst, Res, M, P, V, Msg = [], [], [], [], [], [], [], [], [], []
         for t in range(STEPS):
             a = int(ext[rng.randint(len(ext))])
             obs, reward, done, info = env.step(a)
             A.append(a); R.append(reward); D.append(bool(done)); Cst.append(float(info['step_cost']))
-            Res.append(bool(info['result']))
+            Res.append(bool(info['result'])); Msg.append(str(info['message']))
             if isinstance(obs, dict) and 'agent_map' in obs:
                 assert obs['agent_facing_id'] == base.agent_facing_id
                 O.append(np.asarray(obs['agent_map'], np.int64).ravel())
@@ -113,6 +113,7 @@ def run_scenario(ns, desc, out):
         rec['reward'].append(np.array(R, np.int32)); rec['done'].append(np.array(D, np.uint8))
         rec['cost'].append(np.array(Cst, np.float64)); rec['result'].append(np.array(Res, np.uint8))
         rec['map'].append(np.stack(M)); rec['pose'].append(np.stack(P)); rec['inv'].append(np.stack(V))
+        rec['message'].append(np.array(Msg, dtype='U96'))
     # tables the host layer must reproduce
     meta.update({
         'seeds': seeds, 'reset_kind': reset_kind, 'external_ids': ext,

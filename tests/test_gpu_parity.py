@@ -30,6 +30,8 @@ def test_gpu_replays_reference_golden_trace(name):
     n_items = g['init_inv'].shape[1]
     h = BatchHandle([cc], E, seed=1)
     h.load_state(g['init_map'], g['init_pose'], g['init_inv'])
+    h.enable_messages()
+    from gym_novel_gridworlds_b200.runtime import decode_message
     kind = g['meta']['reset_kind']
     has_obs = g['obs'].shape[2] > 0 and kind != 'agent_map'
     amap = torch.empty((E, 11, 11), dtype=torch.int8, device='cuda')
@@ -45,6 +47,7 @@ def test_gpu_replays_reference_golden_trace(name):
         assert np.array_equal(done.cpu().numpy(), g['done'][:, t]), where
         assert np.array_equal(result.cpu().numpy(), g['result'][:, t]), where
         np.testing.assert_allclose(cost.cpu().numpy(), g['cost'][:, t], rtol=1e-6, err_msg=where)
+        assert [decode_message(c, cc) for c in h.msg.cpu().numpy()] == list(g['message'][:, t]), where   # info['message']
         assert np.array_equal(h.map.cpu().numpy().reshape(E, -1), g['map'][:, t]), where
         assert np.array_equal(h.pose.cpu().numpy(), g['pose'][:, t]), where
         assert np.array_equal(h.inventory.cpu().numpy()[:, :n_items], g['inv'][:, t]), where

@@ -89,7 +89,7 @@ class Wrapper(Env):
         return self.unwrapped._runtime_for(self).step(action)
 
     def render(self, mode='human', **kwargs):
-        raise NotImplementedError("render() is host visualisation, outside the accelerated path (SURVEY §8f N4)")
+        return self.env.render(mode, **kwargs)
 
     def close(self):
         return self.env.close()

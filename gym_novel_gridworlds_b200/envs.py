@@ -200,8 +200,37 @@ class NovelGridworldBatchEnv(Env):
         """Dict of LIVE views of the state tensors (pogostick_v1_env.py:214-228)."""
         return self._runtime_for(self._top).dict_observation()
 
-    def render(self, mode='human', title=None):
-        raise NotImplementedError("render() is host visualisation, outside the accelerated path (SURVEY §8f N4)")
+    def render(self, mode='human', title=None, env_index=0):
+        """Host visualisation of ONE env of the batch from the exported state (pogostick_v1_env.py:556-620 draws the
+        same picture with matplotlib).  matplotlib is optional; without it (or with mode='ansi') the grid is printed /
+        returned as text: item ids, the agent as ^ v < >."""
+        rt = self._runtime_for(self._top)
+        if rt.handle is None:
+            raise RuntimeError("render() before reset()")
+        grid = rt.handle.map[env_index].cpu().numpy()
+        r, c, facing, sel = [int(x) for x in rt.handle.pose[env_index].cpu().numpy()]
+        if mode != 'ansi':
+            try:
+                import matplotlib.pyplot as plt
+            except ImportError:
+                mode = 'ansi'
+        if mode == 'ansi':
+            rows = []
+            for i in range(grid.shape[0]):
+                rows.append(' '.join('^v<>'[facing] if (i, j) == (r, c) else ('.' if grid[i, j] == 0 else '%x' % grid[i, j])
+                                     for j in range(grid.shape[1])))
+            text = '\n'.join(rows)
+            print(text)
+            return text
+        plt.figure(title or self.env_id, figsize=(9, 5))
+        plt.imshow(grid, cmap="gist_ncar", vmin=0, vmax=len(self.items_id))
+        dx, dy = {0: (0, -0.01), 1: (0, 0.01), 2: (-0.01, 0), 3: (0.01, 0)}[facing]
+        plt.arrow(c, r, dx, dy, head_width=0.7, head_length=0.7, color='white')
+        plt.title('NORTH', fontsize=10)
+        plt.xlabel('SOUTH')
+        plt.ylabel('WEST')
+        plt.pause(0.01)
+        plt.clf()
 
     def close(self):
         if self._runtime is not None:

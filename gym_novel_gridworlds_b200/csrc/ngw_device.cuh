@@ -442,12 +442,14 @@ __device__ __forceinline__ bool placeable(const int8_t* m, int ms, int r, int c)
     return p[0] == 0 && p[-ms] == 0 && p[ms] == 0 && p[-1] == 0 && p[1] == 0;
 }
 
-__device__ __forceinline__ uint32_t philox_key(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t stream, uint32_t i) {
+// keys of the four cells 4q .. 4q+3: one Philox block (block 0 of the stream draws the percentage)
+__device__ __forceinline__ void philox_keys4(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t stream, uint32_t q,
+                                             uint32_t key[4]) {
     Philox rng;
     rng.init(seed, gid, episode, stream);
-    rng.blk = 1 + i;                                                   // block 0 of the stream draws the percentage
+    rng.blk = 1 + q;
     rng.refill();
-    return rng.buf[0];
+    key[0] = rng.buf[0]; key[1] = rng.buf[1]; key[2] = rng.buf[2]; key[3] = rng.buf[3];
 }
 
 __device__ __forceinline__ bool reset_candidate(int kind, int id, int wall, int a) {
@@ -567,13 +569,25 @@ __device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m
         //      keys whose top bits == prefix compete for the `remaining` last places
         uint32_t prefix = 0;
         int bits = 0, remaining = take, bin_count = n;
+        const int quads = (cells + 3) >> 2;                           // a lane handles 4 consecutive cells per Philox block
         while (remaining < bin_count && bin_count > 32 && bits < 32) {
             for (int i = lane; i < 256; i += 32) hist[i] = 0;
             __syncwarp();
-            for (int i = lane; i < cells; i += 32) {
-                if (!reset_candidate(op.kind, m[i], wall, op.a)) continue;
-                uint32_t key = philox_key(seed, gid, episode, stream, (uint32_t)i);
-                if (bits == 0 || (key >> (32 - bits)) == prefix) atomicAdd(&hist[(key >> (24 - bits)) & 0xFF], 1u);
+            for (int q = lane; q < quads; q += 32) {
+                bool cand[4], any = false;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    int i = 4 * q + j;
+                    cand[j] = i < cells && reset_candidate(op.kind, m[i < cells ? i : 0], wall, op.a);
+                    any |= cand[j];
+                }
+                if (!any) continue;
+                uint32_t key[4];
+                philox_keys4(seed, gid, episode, stream, (uint32_t)q, key);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (cand[j] && (bits == 0 || (key[j] >> (32 - bits)) == prefix))
+                        atomicAdd(&hist[(key[j] >> (24 - bits)) & 0xFF], 1u);
             }
             __syncwarp();
             uint32_t mine[8], sum = 0;
@@ -607,29 +621,40 @@ __device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m
             bin_count = (int)cnt;
             __syncwarp();
         }
-        // ---- apply: one chunked pass in cell order; boundary-bin cells are collected (<= 32, or all of them win)
+        // ---- apply: one pass; winners are written at once, boundary-bin cells (<= 32, unless all of them win) are listed
         const bool all_in_bin_win = remaining >= bin_count;
         int n_list = 0;
         uint32_t my_key = 0; int my_idx = -1;
         const int value = op.kind == NGW_RESET_ADDITEM ? op.a : op.b;
-        for (int base = 0; base < cells; base += 32) {
-            const int i = base + lane;
-            int id = i < cells ? (int)m[i] : 0;
-            bool cand = i < cells && reset_candidate(op.kind, id, wall, op.a);
-            uint32_t key = cand ? philox_key(seed, gid, episode, stream, (uint32_t)i) : 0;
-            uint32_t top = bits == 0 ? 0 : (key >> (32 - bits));
-            bool wins = cand && (bits == 0 ? all_in_bin_win : (top < prefix || (top == prefix && all_in_bin_win)));
-            bool boundary = cand && !all_in_bin_win && top == prefix;
-            if (wins) {
-                if (op.kind == NGW_RESET_FENCE) m[i] = (int8_t)(id | 0x80);       // mark; fences go in afterwards
-                else if (i != agent) m[i] = (int8_t)value;                        // novelty_wrappers.py:1027,1141
+        for (int qb = 0; qb < quads; qb += 32) {
+            const int q = qb + lane;
+            uint32_t key[4] = {0, 0, 0, 0};
+            int id[4]; bool cand[4], any = false;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int i = 4 * q + j;
+                id[j] = (q < quads && i < cells) ? (int)m[i] : 0;
+                cand[j] = q < quads && i < cells && reset_candidate(op.kind, id[j], wall, op.a);
+                any |= cand[j];
             }
-            uint32_t bal = __ballot_sync(FULL, boundary);
-            if (boundary) {
-                int slot = n_list + __popc(bal & ((1u << lane) - 1u));
-                if (slot < 32) { hist[slot] = key; hist[32 + slot] = (uint32_t)i; }
+            if (any) philox_keys4(seed, gid, episode, stream, (uint32_t)q, key);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = 4 * q + j;
+                uint32_t top = bits == 0 ? 0 : (key[j] >> (32 - bits));
+                bool wins = cand[j] && (bits == 0 ? all_in_bin_win : (top < prefix || (top == prefix && all_in_bin_win)));
+                bool boundary = cand[j] && !all_in_bin_win && top == prefix;
+                if (wins) {
+                    if (op.kind == NGW_RESET_FENCE) m[i] = (int8_t)(id[j] | 0x80);    // mark; fences go in afterwards
+                    else if (i != agent) m[i] = (int8_t)value;                        // novelty_wrappers.py:1027,1141
+                }
+                uint32_t bal = __ballot_sync(FULL, boundary);
+                if (boundary) {
+                    int slot = n_list + __popc(bal & ((1u << lane) - 1u));
+                    if (slot < 32) { hist[slot] = key[j]; hist[32 + slot] = (uint32_t)i; }
+                }
+                n_list += __popc(bal);
             }
-            n_list += __popc(bal);
         }
         __syncwarp();
         if (n_list > 0) {

@@ -98,6 +98,8 @@ struct StepParams {
     int32_t* done_count;        // optional: episodes finished per env during the launch
     int32_t* actions_out;       // optional: actions taken
     uint16_t* msg;              // optional: info['message'] codes (enum ngw_msg | arg << 5)
+    int32_t* reset_list;        // single-step auto-reset: finished envs are queued here ...
+    int32_t* reset_count;       // ... and regenerated by reset_list_kernel right after this launch
 };
 
 // Kernel argument block: the parameters plus up to NC configs INLINE, so that every config read in the hot path
@@ -274,9 +276,20 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
                                      (unsigned char)env.sel);
                     reward_sum += (float)o.reward; cost_sum += o.cost; done_count += o.done;
                 }
-                if (p.auto_reset && __any_sync(0xFFFFFFFFu, did_reset)) { // rare: regenerate finished episodes, warp-cooperatively
-                    auto_reset_warp(p, p.dcfgs, cfg_i, did_reset != 0, smap, sinv, sscratch, e0, ps);
-                    env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+                if (p.auto_reset) {
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, did_reset);
+                    if (bal != 0 && !kMulti) {
+                        // single step: queue the finished envs; reset_list_kernel (next in the stream, one warp per env at
+                        // full occupancy) regenerates them and overwrites their observation rows
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(p.reset_count, __popc(bal));
+                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                        if (did_reset) p.reset_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)e;
+                    } else if (bal != 0) {
+                        // rollout: the next step needs the new episode now -> regenerate in place, warp-cooperatively
+                        auto_reset_warp(p, p.dcfgs, cfg_i, did_reset != 0, smap, sinv, sscratch, e0, ps);
+                        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+                    }
                 }
                 if (p.stats != nullptr) {
                     int n_done = __reduce_add_sync(0xFFFFFFFFu, valid ? o.done : 0);
@@ -364,15 +377,42 @@ struct ResetParams {
     int ms, cells, inv_stride;
     int phase;   // 0: base + ops before the reset observation, 1: ops after it, 2: everything
     const uint8_t* zero_byte;   // a global byte that always reads 0 (see lidar_observe)
+    const int32_t* reset_list;  // reset_list_kernel: queue written by the step kernel
+    int32_t* reset_count;
+    int32_t* done_ctas;
+    int32_t* obs;
+    int obs_dim;
 };
 
 #define NGW_RESET_WARPS 4
+// The cold kernels regenerate an env on a shared-memory copy of its rows (every pass of reset_env_warp would otherwise
+// pay HBM latency) and write the rows back with coalesced stores.
+struct ResetScratch {
+    uint32_t hist[256];
+    int32_t inv[NGW_MAX_ITEMS];
+    int8_t row[NGW_MAX_MAP_SIZE * NGW_MAX_MAP_SIZE];
+};
+
+__device__ __forceinline__ void rows_to_smem(ResetScratch& sc, const int8_t* m, const int32_t* inv, int cells, int inv_stride,
+                                             int lane) {
+    for (int i = lane; i < cells; i += 32) sc.row[i] = m[i];
+    for (int i = lane; i < inv_stride; i += 32) sc.inv[i] = inv[i];
+    __syncwarp();
+}
+__device__ __forceinline__ void rows_from_smem(const ResetScratch& sc, int8_t* m, int32_t* inv, int cells, int inv_stride,
+                                               int lane) {
+    __syncwarp();
+    for (int i = lane; i < cells; i += 32) m[i] = sc.row[i];
+    for (int i = lane; i < inv_stride; i += 32) inv[i] = sc.inv[i];
+}
+
 __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_kernel(const ResetParams p) {
-    __shared__ uint32_t hist[NGW_RESET_WARPS][256];
+    __shared__ ResetScratch scratch[NGW_RESET_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long e = (long long)blockIdx.x * NGW_RESET_WARPS + warp;       // one warp regenerates one env
     if (e >= p.n_envs) return;
     if (p.mask != nullptr && p.mask[e] == 0) return;
+    ResetScratch& sc = scratch[warp];
     const ngw_config* cfg = &p.dcfgs[p.cfg_id[e]].c;
     uchar4 ps = p.pose[e];
     int r = ps.x, c = ps.y, f = ps.z, sel = ps.w;
@@ -383,15 +423,66 @@ __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_kernel(const Reset
     if (p.phase != 1) {
         uint32_t ep = p.episode[e] + 1;
         __syncwarp();
-        uint32_t err = reset_env_warp(cfg, m, inv, p.ms, p.inv_stride, p.seed, gid, ep, true, 0,
-                                      p.phase == 0 ? k : NGW_MAX_RESET_OPS, hist[warp], r, c, f, sel);
+        uint32_t err = reset_env_warp(cfg, sc.row, sc.inv, p.ms, p.inv_stride, p.seed, gid, ep, true, 0,
+                                      p.phase == 0 ? k : NGW_MAX_RESET_OPS, sc.hist, r, c, f, sel);
         if (lane == 0) { p.episode[e] = ep; p.ep_len[e] = 0; p.err[e] = err; }
     } else {
         uint32_t ep = p.episode[e];
-        reset_env_warp(cfg, m, inv, p.ms, p.inv_stride, p.seed, gid, ep, false, k, NGW_MAX_RESET_OPS, hist[warp], r, c, f,
-                       sel);
+        rows_to_smem(sc, m, inv, p.cells, p.inv_stride, lane);
+        reset_env_warp(cfg, sc.row, sc.inv, p.ms, p.inv_stride, p.seed, gid, ep, false, k, NGW_MAX_RESET_OPS, sc.hist, r, c,
+                       f, sel);
     }
+    rows_from_smem(sc, m, inv, p.cells, p.inv_stride, lane);
     if (lane == 0) p.pose[e] = make_uchar4((unsigned char)r, (unsigned char)c, (unsigned char)f, (unsigned char)sel);
+}
+
+// Second half of the single-step auto-reset: a grid-stride loop of warps over the queue the step kernel filled.  Each
+// warp regenerates one env in HBM (reset_env_warp), then 8 lanes cast its LidarInFront beams into its observation row.
+// The last CTA to finish empties the queue for the next step.
+__global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_list_kernel(const ResetParams p) {
+    __shared__ ResetScratch scratch[NGW_RESET_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ResetScratch& sc = scratch[warp];
+    const int count = *reinterpret_cast<volatile int32_t*>(p.reset_count);
+    for (int i = blockIdx.x * NGW_RESET_WARPS + warp; i < count; i += gridDim.x * NGW_RESET_WARPS) {
+        const long long e = p.reset_list[i];
+        const DevConfig& dc = p.dcfgs[p.cfg_id[e]];
+        uchar4 ps = p.pose[e];
+        int r = ps.x, c = ps.y, f = ps.z, sel = ps.w;
+        int8_t* m = p.map + e * p.cells;
+        int32_t* inv = p.inv + e * p.inv_stride;
+        uint32_t ep = p.episode[e] + 1;
+        __syncwarp();
+        uint32_t err = reset_env_warp(&dc.c, sc.row, sc.inv, p.ms, p.inv_stride, p.seed, (uint64_t)(p.first_gid + e), ep,
+                                      true, 0, NGW_MAX_RESET_OPS, sc.hist, r, c, f, sel);
+        rows_from_smem(sc, m, inv, p.cells, p.inv_stride, lane);
+        if (lane == 0) {
+            p.episode[e] = ep;
+            p.pose[e] = make_uchar4((unsigned char)r, (unsigned char)c, (unsigned char)f, (unsigned char)sel);
+            if (err) p.err[e] |= err;
+        }
+        if (p.obs != nullptr) {                                       // observation of the new episode replaces the row
+            int32_t* row = p.obs + e * p.obs_dim;
+            for (int k = lane; k < p.obs_dim; k += 32) row[k] = 0;
+            __syncwarp();
+            EnvRow env;                                                   // lidar on the shared-memory copy
+            env.m = sc.row; env.gm = nullptr; env.inv = sc.inv; env.ms = p.ms;
+            env.r = r; env.c = c; env.facing = f; env.sel = sel;
+            if (lane == 0) sc.hist[0] = 0;                                // a shared-memory byte that reads 0
+            __syncwarp();
+            const int8_t* zero = reinterpret_cast<const int8_t*>(sc.hist);
+            if (dc.c.n_beams > 0) {
+                if (dc.lidar.fast) { if (lane < 8) lidar_observe(env, dc, row, zero, lane, 8, lane == 7); }
+                else if (lane == 0) lidar_observe(env, dc, row, zero, 0, 1, true);
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(p.done_ctas, 1) == (int)gridDim.x - 1) { *p.reset_count = 0; *p.done_ctas = 0; }
+    }
 }
 
 __global__ void observe_masked_kernel(const ResetParams p, int32_t* obs, int obs_dim) {
@@ -470,6 +561,8 @@ struct ngw_handle {
     uint32_t* episode = nullptr; int32_t* ep_len = nullptr; uint32_t* err = nullptr; double* stats = nullptr;
     uint8_t* zero_byte = nullptr;
     uint16_t* msg = nullptr;                       // caller-owned message-code buffer (ngw_set_message_buffer)
+    int32_t* reset_list = nullptr; int32_t* reset_ctl = nullptr;   // auto-reset queue; ctl[0] = count, ctl[1] = finished CTAs
+    int sm_count = 148;
     long long launches = 0;
     // host-buffer path
     cudaStream_t hs[HOST_STREAMS] = {nullptr};
@@ -489,7 +582,7 @@ void ngw_destroy(ngw_handle* h) {
     cudaSetDevice(h->device);
     for (auto p : h->d_luts) cudaFree(p);
     cudaFree(h->d_cfgs); cudaFree(h->map); cudaFree(h->pose); cudaFree(h->inv); cudaFree(h->cfg_id);
-    cudaFree(h->episode); cudaFree(h->ep_len); cudaFree(h->err); cudaFree(h->stats); cudaFree(h->zero_byte);
+    cudaFree(h->episode); cudaFree(h->ep_len); cudaFree(h->err); cudaFree(h->stats); cudaFree(h->zero_byte); cudaFree(h->reset_list); cudaFree(h->reset_ctl);
     cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward);   // h_cost / h_done / h_result live in h_reward's block
     for (int i = 0; i < HOST_STREAMS; i++)
         if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
@@ -581,6 +674,10 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
     CK(cudaMalloc(&h->ep_len, (size_t)h->np * 4));
     CK(cudaMalloc(&h->err, (size_t)h->np * 4));
     CK(cudaMalloc(&h->stats, sizeof(double) * NGW_STAT_SLOTS * NGW_STAT_COUNT));
+    CK(cudaMalloc(&h->reset_list, (size_t)h->np * 4));
+    CK(cudaMalloc(&h->reset_ctl, 16));
+    CK(cudaMemset(h->reset_ctl, 0, 16));
+    h->sm_count = prop.multiProcessorCount;
     CK(cudaMalloc(&h->zero_byte, 16));
     CK(cudaMemset(h->zero_byte, 0, 16));
     CK(cudaMemset(h->map, 0, (size_t)h->np * h->cells));
@@ -665,6 +762,8 @@ static ResetParams reset_params(ngw_handle* h, const uint8_t* mask, int phase) {
     p.dcfgs = h->d_cfgs; p.map = h->map; p.pose = h->pose; p.inv = h->inv; p.cfg_id = h->cfg_id; p.episode = h->episode;
     p.ep_len = h->ep_len; p.err = h->err; p.mask = mask; p.n_envs = h->n; p.first_gid = h->first_gid; p.seed = h->seed;
     p.ms = h->ms; p.cells = h->cells; p.inv_stride = h->inv_stride; p.phase = phase; p.zero_byte = h->zero_byte;
+    p.reset_list = h->reset_list; p.reset_count = h->reset_ctl; p.done_ctas = h->reset_ctl + 1; p.obs = nullptr;
+    p.obs_dim = h->obs_dim;
     return p;
 }
 
@@ -705,7 +804,7 @@ static StepParams step_params(ngw_handle* h, const int32_t* actions, int32_t* ob
     p.map_bytes = h->map_bytes; p.inv_bytes = h->inv_bytes; p.obs_bytes = h->obs_bytes;
     p.region_bytes = h->region_bytes; p.auto_reset = auto_reset; p.max_episode_steps = max_episode_steps;
     p.plain_store = h->plain_store ? 1 : 0;
-    p.msg = h->msg;
+    p.msg = h->msg; p.reset_list = h->reset_list; p.reset_count = h->reset_ctl;
     p.n_steps = 1; p.random_policy = 0; p.act_stride = 0; p.policy_seed = 0; p.done_count = nullptr; p.actions_out = nullptr;
     return p;
 }
@@ -750,6 +849,14 @@ static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
     else launch_step_nc<16>(h, p, blocks, smem, s);
     h->launches++;
     CK(cudaGetLastError());
+    const bool multi = p.n_steps > 1 || p.random_policy || p.done_count != nullptr || p.actions_out != nullptr;
+    if (p.actions != nullptr && p.auto_reset && !multi) {           // regenerate the episodes the step kernel queued
+        ResetParams rp = reset_params(h, nullptr, 2);
+        rp.obs = p.obs;
+        reset_list_kernel<<<h->sm_count * 4, 32 * NGW_RESET_WARPS, 0, s>>>(rp);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
     return 0;
 }
 

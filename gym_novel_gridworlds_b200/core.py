@@ -94,6 +94,9 @@ class Wrapper(Env):
     def close(self):
         return self.env.close()
 
+    def seed(self, seed=None):
+        return self.env.seed(seed)
+
 
 # ---------------------------------------------------------------- registry (gym.envs.registration)
 registry = {}

@@ -570,7 +570,6 @@ struct ngw_handle {
     float* h_cost = nullptr; uint8_t* h_result = nullptr;
 };
 
-static int align16(int x) { return (x + 15) & ~15; }
 
 extern "C" {
 

@@ -30,12 +30,18 @@ class NovelGridworldBatchEnv(Env):
     _BREAK_REWARD_ITEMS = ('tree_log',)  # base Break rewards these (pogostick_v1_env.py:288; v0: pogostick_v0_env.py:312)
     _PLACES_TREE_TAP = False           # pogostick_v0_env.py:155-178
 
-    def __init__(self, env=None, num_envs=1, device=None, seed=0, first_env_gid=0):
+    def __init__(self, env=None, num_envs=1, device=None, seed=0, first_env_gid=0, auto_reset=False,
+                 max_episode_steps=0, messages=False):
         self.env = env                                  # env to restore in reset (pogostick_v1_env.py:29,89-109)
         self.num_envs = int(num_envs)
         self.device = device
         self.rng_seed = int(seed)
         self.first_env_gid = int(first_env_gid)
+        # batch extensions (not in the reference): regenerate finished episodes inside step(), optional truncation cap,
+        # info['message'] for batched envs (always on when num_envs == 1)
+        self.auto_reset = bool(auto_reset)
+        self.max_episode_steps = int(max_episode_steps)
+        self.messages = bool(messages)
 
         self.map_size = 10
         self.direction_id = {'NORTH': 0, 'SOUTH': 1, 'WEST': 2, 'EAST': 3}
@@ -231,6 +237,13 @@ class NovelGridworldBatchEnv(Env):
         plt.ylabel('WEST')
         plt.pause(0.01)
         plt.clf()
+
+    def seed(self, seed=None):
+        """The reference has no seed() (it draws from the global np.random); here it re-keys the Philox generator."""
+        if seed is not None:
+            self.rng_seed = int(seed)
+            self.close()                       # the next reset() builds a handle with the new key
+        return [self.rng_seed]
 
     def close(self):
         if self._runtime is not None:

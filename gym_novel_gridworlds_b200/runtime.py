@@ -270,9 +270,9 @@ class ChainRuntime(object):
         self.handle = None
         self.compiled = None
         self._fingerprint = None
-        self.auto_reset = False
-        self.max_episode_steps = 0
-        self.messages = False          # batched envs: set True before the first reset to get info['message']
+        self.auto_reset = base.auto_reset
+        self.max_episode_steps = base.max_episode_steps
+        self.messages = base.messages
 
     # ------------------------------------------------------------------
     def _ensure(self):

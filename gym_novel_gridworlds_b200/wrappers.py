@@ -8,40 +8,41 @@ from .core import Wrapper, _Invalid
 
 
 class SaveTrajectories(Wrapper):
-    """Records the state after every step and pickles the list (wrappers.py:9-54), same dict schema.  With
-    num_envs == 1 the values are the reference's python objects; batched envs store CPU copies of the state tensors."""
+    """Host-side logger with the reference's pickle schema (wrappers.py:9-54): one state dict per step, `save()` writes
+    the list.  With num_envs == 1 the values are the reference's python objects; batched envs store CPU copies of the
+    state tensors (arrays indexed by env)."""
+
+    _STATIC_KEYS = (("map_size", "map_size"), ("items_id", "items_id"), ("items_quantity", "items_quantity"),
+                    ("action_str", "actions_id"), ("last_action", "last_action"))
 
     def __init__(self, env, save_path):
         super().__init__(env)
-        self.save_path = save_path
-        os.makedirs(self.save_path, exist_ok=True)
-        self.state_trajectories = []
+        os.makedirs(save_path, exist_ok=True)
+        self.save_path, self.state_trajectories, self.last_done = save_path, [], False
 
     def step(self, action_id):
-        obs, reward, done, info = self.unwrapped._runtime_for(self).step(action_id)
-        self.last_done = done
+        out = self.unwrapped._runtime_for(self).step(action_id)
+        self.last_done = out[2]
         self.state_trajectories.append(self.get_state())
-        return obs, reward, done, info
+        return out
 
     def get_state(self):
         base = self.unwrapped
-        rt = base._runtime
         if base.num_envs == 1:
-            fields = {"map": base.map, "agent_location": base.agent_location,
-                      "agent_facing_str": base.agent_facing_str, "block_in_front_id": base.block_in_front_id,
-                      "inventory_items_quantity": base.inventory_items_quantity}
+            state = {key: getattr(base, key) for key in ("map", "agent_location", "agent_facing_str",
+                                                         "block_in_front_id", "inventory_items_quantity")}
         else:
-            m, pose, inv = [x.cpu().numpy() for x in rt.handle.export_state()]
-            names = rt.compiled.item_names
-            fields = {"map": m, "agent_location": pose[:, 0:2], "agent_facing_id": pose[:, 2],
-                      "inventory_items_quantity": {n: inv[:, i] for i, n in enumerate(names) if n in base.items}}
-        fields.update({"map_size": base.map_size, "items_id": base.items_id, "items_quantity": base.items_quantity,
-                       "action_str": base.actions_id, "last_action": base.last_action, "last_done": self.last_done})
-        return fields
+            handle, names = base._runtime.handle, base._runtime.compiled.item_names
+            grid, pose, inv = (t.cpu().numpy() for t in handle.export_state())
+            state = {"map": grid, "agent_location": pose[:, :2], "agent_facing_id": pose[:, 2],
+                     "inventory_items_quantity": {n: inv[:, i] for i, n in enumerate(names) if n in base.items}}
+        state.update((key, getattr(base, attr)) for key, attr in self._STATIC_KEYS)
+        state["last_done"] = self.last_done
+        return state
 
     def save(self):
-        path = os.path.join(self.save_path,
-                            datetime.now().strftime("%Y-%m-%d-%H-%M-%S") + "_{env}.bin".format(env=self.env.env_id))
+        stamp = datetime.now().strftime("%Y-%m-%d-%H-%M-%S")
+        path = os.path.join(self.save_path, "%s_%s.bin" % (stamp, self.env.env_id))
         with open(path, 'wb') as f:
             pickle.dump(self.state_trajectories, f)
         print("Trajectories saved at: ", path)
@@ -57,18 +58,20 @@ class LimitActions(Wrapper):
 
     def __init__(self, env, limited_actions):
         super().__init__(env)
+        names = sorted(limited_actions)
         self.limited_actions = limited_actions
-        self.limited_actions_id = {action: i for i, action in enumerate(sorted(self.limited_actions))}
-        self.action_space = spaces.Discrete(len(self.limited_actions_id))
+        self.limited_actions_id = dict(zip(names, range(len(names))))
+        self.action_space = spaces.Discrete(len(names))
 
     def set_limited_actions_id(self, limited_actions_id):
         self.limited_actions_id = limited_actions_id
 
     def _resolve(self, action_id):
-        if action_id not in self.limited_actions_id.values():            # wrappers.py:76
+        by_id = {v: k for k, v in reversed(list(self.limited_actions_id.items()))}      # first name wins, as list.index does
+        if action_id not in by_id:                                                      # wrappers.py:76
             raise _Invalid("AssertionError: Action ID %s is not valid" % (action_id,))
-        name = next(k for k, v in self.limited_actions_id.items() if v == action_id)
-        if name not in self.actions_id:                                   # wrappers.py:80
+        name = by_id[action_id]
+        if name not in self.actions_id:                                                 # wrappers.py:80
             raise _Invalid("AssertionError: %s is not a valid action for %s" % (name, self.env_id))
         return self.env._resolve(self.actions_id[name])
 

@@ -250,3 +250,36 @@ def test_env_restore_chaining_and_save_trajectories(tmp_path):
     assert len(traj) == 3
     assert set(traj[0]) == {"map_size", "map", "agent_location", "agent_facing_str", "block_in_front_id", "items_id",
                             "items_quantity", "inventory_items_quantity", "action_str", "last_action", "last_done"}
+
+
+def test_batched_gym_api_auto_reset_messages_and_mixed_batch():
+    import gym_novel_gridworlds_b200 as gym
+    n = 2000
+    env = gym.make('NovelGridworld-Pogostick-v1', num_envs=n, seed=7, auto_reset=True, max_episode_steps=8, messages=True)
+    env = gym.LidarInFront(gym.LimitActions(env, set(scenarios.C2_SET)))
+    obs = env.reset()
+    assert obs.shape == (n, 63) and obs.dtype == torch.int32
+    dones = 0
+    for t in range(16):
+        a = torch.randint(0, 10, (n,), device='cuda', dtype=torch.int32)
+        obs, reward, done, info = env.step(a)
+        dones += int(done.sum().item())
+        assert len(info['message']) == n and info['step_cost'].shape == (n,) and info['result'].dtype == torch.bool
+    assert dones == 2 * n                                         # truncated (and regenerated) at steps 8 and 16
+    assert env.seed(11) == [11]
+    # host-buffer path through the same API: numpy in, numpy out
+    obs = env.reset()
+    o, r, d, info = env.step(np.zeros(n, np.int32))
+    assert isinstance(o, np.ndarray) and o.shape == (n, 63) and isinstance(r, np.ndarray)
+    # several chains in one batch
+    chains = [gym.LidarInFront(gym.LimitActions(gym.make('NovelGridworld-Pogostick-v1'), set(scenarios.C2_SET))),
+              gym.inject_novelty(gym.LidarInFront(gym.LimitActions(gym.make('NovelGridworld-Pogostick-v1'),
+                                                                   set(scenarios.C2_SET + ['Chop']))), 'addchop')]
+    mb = MixedBatch(chains, 1000, assignment='blocked')
+    assert (mb.cfg_id_host[:500] == 0).all() and (mb.cfg_id_host[500:] == 1).all()
+    obs = mb.reset()
+    out = mb.step(torch.full((1000,), 10, dtype=torch.int32, device='cuda'))      # id 10 = Right (cfg 1) / invalid (cfg 0)
+    flags = mb.handle.error_flags.cpu().numpy()
+    assert (flags[:500] & 1).all() and not (flags[500:] & 1).any()
+    st = mb.handle.stats().cpu().numpy()
+    assert st[0] == 500 and st[6] == 500

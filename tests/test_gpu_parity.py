@@ -283,3 +283,61 @@ def test_batched_gym_api_auto_reset_messages_and_mixed_batch():
     assert (flags[:500] & 1).all() and not (flags[500:] & 1).any()
     st = mb.handle.stats().cpu().numpy()
     assert st[0] == 500 and st[6] == 500
+
+
+@pytest.mark.parametrize('n_cfg', [6, 20])
+def test_many_configs_in_one_batch_inline_and_global_tables(n_cfg):
+    """NC = 16 inline-config kernel (6 configs) and the global-memory fallback (20 configs > 16)."""
+    import gym_novel_gridworlds_b200 as gym
+    variants = [('addchop', 'hard', '', '', ['Chop']), ('addjump', 'hard', '', '', ['Jump']),
+                ('additem', 'easy', 'spring', '', []), ('breakincrease', 'hard', '', '', []),
+                ('axe', 'easy', 'wooden', 'true', ['Select_wooden_axe']), ('fence', 'medium', 'oak', '', [])]
+    compiled = []
+    for i in range(n_cfg):
+        name, diff, a1, a2, extra = variants[i % len(variants)]
+        desc = {'env': scenarios.POGO, 'map_size': 10, 'build_seed': 100 + i,
+                'chain': [['limit', scenarios.C2_SET + extra], ['lidar', 8], ['novelty', name, diff, a1, a2]]}
+        compiled.append(_compiled(desc))
+    n = 64 * n_cfg + 5
+    cfg_id = (np.arange(n) * 7 % n_cfg).astype(np.uint8)
+    _parity_vs_oracle(compiled, n, 40, seed0=777, cfg_id=cfg_id)
+
+
+@pytest.mark.parametrize('ms,beams,n', [(64, 8, 70), (12, 16, 600), (9, 5, 600), (11, 8, 333), (23, 1, 200)])
+def test_map_sizes_and_beam_counts_vs_oracle(ms, beams, n):
+    """Largest grid (one tile per SM, 8 warps per tile), generic lidar LUT path (beam counts != 8), tiny grids."""
+    cc = _compiled({'env': scenarios.BOW, 'map_size': ms, 'chain': [['lidar', beams]]})
+    _parity_vs_oracle([cc], n, 48, seed0=4242)
+
+
+def test_no_lidar_dict_observation_batch_with_auto_reset():
+    cc = _compiled({'env': scenarios.POGO, 'map_size': 10, 'chain': []})
+    assert cc.obs_dim == 0
+    n = 1500
+    ob = OracleBatch([cc], n)
+    ob.reset_legacy(1)
+    h = BatchHandle([cc], n)
+    h.load_state(ob.map, ob.pose, ob.inv)
+    rng = np.random.RandomState(0)
+    for t in range(24):
+        a = rng.randint(0, cc.c.n_actions, size=n).astype(np.int32)
+        o_obs, o_rew, o_done, o_cost, o_res = ob.step(a)
+        obs, rew, done, cost, res = h.step(torch.from_numpy(a).cuda())
+        assert np.array_equal(rew.cpu().numpy(), o_rew) and np.array_equal(res.cpu().numpy(), o_res)
+    assert np.array_equal(h.map.cpu().numpy().reshape(n, -1), ob.map) and np.array_equal(h.inventory.cpu().numpy(), ob.inv)
+    for t in range(6):
+        h.step(torch.zeros(n, dtype=torch.int32, device='cuda'), auto_reset=True, max_episode_steps=3)
+    assert (h.episode.cpu().numpy() == 2).all() and int(h.error_flags.abs().sum().item()) == 0
+
+
+def test_placement_failure_rate_matches_reference_on_a_crowded_grid():
+    """AxeHard(iron) puts 11 items into the 6x6 interior: the reference sometimes asserts 'Cannot place items'
+    (pogostick_v1_env.py:167); the GPU generator must fail at the same rate and flag it."""
+    cc = _compiled(golden_util.get('pogo_A_axe_hard_iron_inc')['meta'])
+    n = 20000
+    h = BatchHandle([cc], n, seed=12)
+    h.reset()
+    gpu_fail = ((h.error_flags.cpu().numpy() & 2) != 0).mean()
+    ref = OracleBatch([cc], n)
+    ref_fail = (ref.reset_legacy(31) != 0).mean()
+    assert abs(gpu_fail - ref_fail) < 4 * np.sqrt(max(ref_fail, 1e-4) / n) + 2e-4, (gpu_fail, ref_fail)

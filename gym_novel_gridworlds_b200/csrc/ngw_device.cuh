@@ -363,8 +363,8 @@ __device__ __forceinline__ void lidar_fast(const EnvRow& e, const DevConfig& dc,
     const int8_t* base = e.m + e.r * e.ms + e.c;
 #pragma unroll
     for (int j = 0; j < NB; j++) { u[j] = dc.lidar.unit[e.facing][b0 + j]; at[j] = base; hit[j] = 0; }
-    int prev0 = 0, prev1 = 0, flying = NB;
-    for (int k = 0; k < K && flying > 0; k++) {
+    int prev0 = 0, prev1 = 0, flying = 1;                             // a unit step is never 0, so OR(u) != 0 <=> a beam still flies
+    for (int k = 0; k < K && flying != 0; k++) {
         const int d0 = dc.lidar.disp[0][k], d1 = dc.lidar.disp[1][k];
         const int s0 = d0 - prev0, s1 = d1 - prev1;                   // warp-uniform step counts (0 or 1 for 8 beams)
         prev0 = d0; prev1 = d1;
@@ -380,8 +380,10 @@ __device__ __forceinline__ void lidar_fast(const EnvRow& e, const DevConfig& dc,
             hit[j] = lands ? (uint32_t)(((k + 1) << 8) | (id[j] & 0xFF)) : hit[j];
             u[j] = lands ? 0 : u[j];
             at[j] = lands ? zero : at[j];
-            flying -= lands ? 1 : 0;
         }
+        flying = 0;
+#pragma unroll
+        for (int j = 0; j < NB; j++) flying |= u[j];
     }
 #pragma unroll
     for (int j = 0; j < NB; j++) {

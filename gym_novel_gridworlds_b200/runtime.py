@@ -236,10 +236,11 @@ def decode_message(code, compiled):
 
 
 class LazyInfo(object):
-    """info of a batched step: tensors, converted to the reference's dict only on demand."""
+    """info of a batched step: tensors; the reference's strings are formatted only when 'message' is asked for."""
 
-    def __init__(self, result, step_cost, msg=None, compiled=None):
-        self.result, self.step_cost, self._msg, self._compiled = result, step_cost, msg, compiled
+    def __init__(self, result, step_cost, msg=None, compiled=None, cfg_ids=None):
+        self.result, self.step_cost = result, step_cost
+        self._msg, self._compiled, self._cfg_ids = msg, compiled, cfg_ids
 
     def __getitem__(self, key):
         if key == 'result':
@@ -248,15 +249,12 @@ class LazyInfo(object):
             return self.step_cost
         if key == 'message':
             if self._msg is None:
-                return None      # message codes are off unless BatchHandle.enable_messages() was called
+                return None      # message codes are off unless the env was made with messages=True
             codes = self._msg.cpu().numpy() if hasattr(self._msg, 'cpu') else self._msg
-            cfg_ids = None
-            return [decode_message(c, self._compiled[0]) for c in codes] if len(self._compiled) == 1 else \
-                [decode_message(c, self._compiled[int(i)]) for c, i in zip(codes, self._cfg_ids())]
+            if self._cfg_ids is None:
+                return [decode_message(c, self._compiled[0]) for c in codes]
+            return [decode_message(c, self._compiled[int(i)]) for c, i in zip(codes, self._cfg_ids)]
         raise KeyError(key)
-
-    def _cfg_ids(self):
-        return getattr(self, 'cfg_ids', [0] * len(self._msg))
 
     def keys(self):
         return ['result', 'step_cost', 'message']

@@ -401,6 +401,7 @@ __device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& 
     if (dc.lidar.fast) {
         if (G == 1) lidar_fast<8>(e, dc, obs, zero, 0);
         else if (G == 2) lidar_fast<4>(e, dc, obs, zero, g * 4);
+        else if (G == 3) { if (g < 2) lidar_fast<3>(e, dc, obs, zero, g * 3); else lidar_fast<2>(e, dc, obs, zero, 6); }
         else if (G == 4) lidar_fast<2>(e, dc, obs, zero, g * 2);
         else lidar_fast<1>(e, dc, obs, zero, g);
     } else {

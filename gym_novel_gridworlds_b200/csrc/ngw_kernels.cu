@@ -697,12 +697,13 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
     h->region_bytes = 16 + 128 + 1024 + h->map_bytes + h->inv_bytes + h->obs_bytes;
     h->region_bytes = (h->region_bytes + 127) & ~127;
     if (h->region_bytes > 227 * 1024) { ngw_destroy(h); return fail("ngw_create: map too large for shared memory"); }
-    // G warps share one tile: 1 for small grids (many tiles fit per SM), more when shared memory limits the tiles
+    // G warps share one tile (warp 0 steps, all G cast 8/G lidar beams): 2 for small grids — the one-step kernel needs
+    // 48 registers, so two-warp tiles of a 65,536-env batch are all resident — more when shared memory limits the tiles
     int tiles_per_sm = (227 * 1024) / (h->region_bytes + 1024);
-    int warps = tiles_per_sm >= 12 ? 1 : (tiles_per_sm >= 6 ? 2 : (tiles_per_sm >= 3 ? 4 : 8));
+    int warps = tiles_per_sm >= 6 ? 2 : (tiles_per_sm >= 3 ? 4 : 8);
     if (const char* w = getenv("NGW_WARPS")) {                      // tuning knob: warps per tile, 1 / 2 / 4 / 8
         int v = atoi(w);
-        if (v == 1 || v == 2 || v == 4 || v == 8) warps = v;
+        if (v == 1 || v == 2 || v == 3 || v == 4 || v == 8) warps = v;
     }
     h->warps = warps;
     CK(cudaFuncSetAttribute(step_kernel<true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

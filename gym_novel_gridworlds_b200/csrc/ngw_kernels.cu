@@ -821,7 +821,10 @@ static void launch_step_nc(ngw_handle* h, const StepParams& p, int blocks, size_
     for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3(blocks); lc.blockDim = dim3(32 * h->warps); lc.dynamicSmemBytes = smem; lc.stream = s;
+    const bool multi = p.n_steps > 1 || p.random_policy || p.done_count != nullptr || p.actions_out != nullptr;
+    // the K-step rollout is all step logic (one lidar pass at the end): one warp per tile keeps more tiles resident
+    const int warps = (multi && h->region_bytes * 12 <= 227 * 1024) ? 1 : h->warps;
+    lc.gridDim = dim3(blocks); lc.blockDim = dim3(32 * warps); lc.dynamicSmemBytes = smem; lc.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -830,7 +833,6 @@ static void launch_step_nc(ngw_handle* h, const StepParams& p, int blocks, size_
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(s, &cap);
     lc.attrs = attr; lc.numAttrs = (h->use_pdl && (cap == cudaStreamCaptureStatusNone || h->pdl_in_graph)) ? 1 : 0;
-    const bool multi = p.n_steps > 1 || p.random_policy || p.done_count != nullptr || p.actions_out != nullptr;
     if (h->use_tma) {
         if (multi) cudaLaunchKernelEx(&lc, step_kernel<true, NC, true>, args);
         else cudaLaunchKernelEx(&lc, step_kernel<true, NC, false>, args);

@@ -925,8 +925,22 @@ int ngw_set_message_buffer(ngw_handle* h, uint16_t* msg_dev) {
     return 0;
 }
 
+int ngw_step_host_end(ngw_handle* h) {
+    if (!h) return fail("null handle");
+    if (!h->hs[0]) return 0;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->hs[0]));
+    return 0;
+}
+
 int ngw_step_host(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done, float* step_cost,
                   uint8_t* result, int32_t auto_reset, int32_t max_episode_steps) {
+    if (ngw_step_host_begin(h, actions, obs, reward, done, step_cost, result, auto_reset, max_episode_steps)) return 1;
+    return ngw_step_host_end(h);
+}
+
+int ngw_step_host_begin(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done,
+                        float* step_cost, uint8_t* result, int32_t auto_reset, int32_t max_episode_steps) {
     if (!h) return fail("null handle");
     if (!actions || !reward || !done || !step_cost || !result) return fail("ngw_step_host: null pointer");
     CK(cudaSetDevice(h->device));
@@ -950,7 +964,6 @@ int ngw_step_host(ngw_handle* h, const int32_t* actions, int32_t* obs, float* re
         CK(cudaMemcpyAsync(step_cost, h->h_cost, cnt * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(result, h->h_result, cnt, cudaMemcpyDeviceToHost, s));
     }
-    CK(cudaStreamSynchronize(s));
     return 0;
 }
 

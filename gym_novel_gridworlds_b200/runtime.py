@@ -196,6 +196,27 @@ class BatchHandle(object):
         return (hb['obs'].numpy(), hb['reward'].numpy(), hb['done'].numpy(), hb['step_cost'].numpy(),
                 hb['result'].numpy())
 
+    def step_host_begin(self, actions, auto_reset=False, max_episode_steps=0):
+        """Enqueue H2D + step + D2H on the handle's own stream and return at once (pipelining over several batches);
+        `step_host_end()` blocks until the pinned output buffers are valid and returns them."""
+        hb = self._host_buffers()
+        hb['actions'].numpy()[:] = np.asarray(actions, dtype=np.int32).reshape(self.n)
+        capi.check(self.lib, self.lib.ngw_step_host_begin(
+            self._h, _ptr(hb['actions']), _ptr(hb['obs']) if self.obs_dim else None, _ptr(hb['reward']),
+            _ptr(hb['done']), _ptr(hb['step_cost']), _ptr(hb['result']), int(bool(auto_reset)),
+            int(max_episode_steps)))
+
+    def step_host_end(self):
+        capi.check(self.lib, self.lib.ngw_step_host_end(self._h))
+        hb = self._host
+        return (hb['obs'].numpy(), hb['reward'].numpy(), hb['done'].numpy(), hb['step_cost'].numpy(),
+                hb['result'].numpy())
+
+    def stats_allreduce(self, reset=False):
+        """Job-wide episode statistics: the handle's counters summed over all ranks (NCCL when torch.distributed is up)."""
+        from .sharding import allreduce_stats
+        return allreduce_stats(self.stats(reset).clone())
+
     def stats(self, reset=False):
         """float64[8] on device, order = opcodes.STAT_NAMES; all-reduce it with NCCL for the job total."""
         capi.check(self.lib, self.lib.ngw_stats(self._h, _ptr(self._stats), int(bool(reset)), self._stream()))

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define NGW_ABI_VERSION 6
+#define NGW_ABI_VERSION 7
 
 #define NGW_MAX_ITEMS 24          /* reference asserts len(items) <= 20 (pogostick_v1_env.py:75,220) */
 #define NGW_MAX_ACTIONS 48
@@ -266,6 +266,13 @@ int ngw_step_host(ngw_handle* h, const int32_t* actions, int32_t* obs, float* re
 int ngw_rollout(ngw_handle* h, const int32_t* actions, int32_t n_steps, uint64_t policy_seed, int32_t* obs,
                 float* reward_sum, float* cost_sum, int32_t* done_count, uint8_t* last_done, uint8_t* last_result,
                 int32_t* actions_out, int32_t auto_reset, int32_t max_episode_steps, void* stream);
+
+/* The host-buffer step split in two, so that a caller with several batches can keep PCIe busy: _begin enqueues the
+ * H2D copy, the launch and the D2H copies on the handle's own stream and returns; _end blocks until this handle's
+ * outputs are valid on the host.  ngw_step_host == _begin + _end. */
+int ngw_step_host_begin(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done,
+                        float* step_cost, uint8_t* result, int32_t auto_reset, int32_t max_episode_steps);
+int ngw_step_host_end(ngw_handle* h);
 
 /* LidarInFront.observation of the current state into DEVICE int32[n_envs][obs_dim]. */
 int ngw_observe(ngw_handle* h, int32_t* obs, void* stream);

@@ -140,7 +140,11 @@ def test_host_buffer_path_matches_device_path():
     for t in range(12):
         a = rng.randint(0, cc.c.n_actions, size=n).astype(np.int32)
         d = [x.cpu().numpy() for x in h1.step(torch.from_numpy(a).cuda())]
-        hb = h2.step_host(a)
+        if t % 2:
+            hb = h2.step_host(a)
+        else:
+            h2.step_host_begin(a)
+            hb = h2.step_host_end()
         for x, y in zip(d, hb):
             assert np.array_equal(x, y)
     assert np.array_equal(h1.map.cpu().numpy(), h2.map.cpu().numpy())

@@ -39,6 +39,23 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 cache-hinted variants (createpolicy + .L2::cache_hint)
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -89,6 +106,7 @@ struct StepParams {
     int ms, cells, inv_stride, obs_dim;
     int map_bytes, inv_bytes, obs_bytes, region_bytes;   // per-warp shared-memory carve-up
     int auto_reset, max_episode_steps;
+    int cache_hints;            // bit 0: state tiles are loaded L2::evict_first, bit 1: the observation tile is stored evict_first
     int plain_store;            // 1 => write tiles back with ordinary coalesced stores instead of TMA bulk stores
     // K-step rollout (n_steps > 1 or random policy): the tile stays in shared memory across the steps
     int n_steps;                // steps per launch (1 for ngw_step)
@@ -196,8 +214,14 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
     if (kTma) {
         if (threadIdx.x == 0) {
             mbar_expect_tx(bar, (uint32_t)(p.map_bytes + p.inv_bytes));
-            bulk_g2s(smap, gmap, (uint32_t)p.map_bytes, bar);
-            bulk_g2s(sinv, ginv, (uint32_t)p.inv_bytes, bar);
+            if (p.cache_hints & 1) {
+                uint64_t pol = policy_evict_first();
+                bulk_g2s_hint(smap, gmap, (uint32_t)p.map_bytes, bar, pol);
+                bulk_g2s_hint(sinv, ginv, (uint32_t)p.inv_bytes, bar, pol);
+            } else {
+                bulk_g2s(smap, gmap, (uint32_t)p.map_bytes, bar);
+                bulk_g2s(sinv, ginv, (uint32_t)p.inv_bytes, bar);
+            }
         }
     } else {
         const uint4* s4 = reinterpret_cast<const uint4*>(gmap);
@@ -342,8 +366,14 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
             fence_async_smem();
             __syncwarp();
             if (threadIdx.x == 0) {
-                if (stepping) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
-                if (p.obs != nullptr) bulk_s2g(p.obs + e0 * p.obs_dim, sobs, (uint32_t)p.obs_bytes);
+                if (p.cache_hints & 2) {
+                    uint64_t pol = policy_evict_first();
+                    if (stepping) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
+                    if (p.obs != nullptr) bulk_s2g_hint(p.obs + e0 * p.obs_dim, sobs, (uint32_t)p.obs_bytes, pol);
+                } else {
+                    if (stepping) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
+                    if (p.obs != nullptr) bulk_s2g(p.obs + e0 * p.obs_dim, sobs, (uint32_t)p.obs_bytes);
+                }
                 bulk_commit();
                 bulk_wait_read0();                                   // shared memory must outlive the reads
             }
@@ -807,6 +837,9 @@ static StepParams step_params(ngw_handle* h, const int32_t* actions, int32_t* ob
     p.map_bytes = h->map_bytes; p.inv_bytes = h->inv_bytes; p.obs_bytes = h->obs_bytes;
     p.region_bytes = h->region_bytes; p.auto_reset = auto_reset; p.max_episode_steps = max_episode_steps;
     p.plain_store = h->plain_store ? 1 : 0;
+    // streaming data (each tile is read once and its 8 KB of observations written once per step) should not linger in L2:
+    // measured on C2 9.15 -> 8.82 us/step, C3 29.3 -> 28.0, C5 278 -> 274 (hinting the inventory store as well: 9.0)
+    p.cache_hints = getenv("NGW_HINTS") ? atoi(getenv("NGW_HINTS")) : 3;
     p.msg = h->msg; p.reset_list = h->reset_list; p.reset_count = h->reset_ctl;
     p.n_steps = 1; p.random_policy = 0; p.act_stride = 0; p.policy_seed = 0; p.done_count = nullptr; p.actions_out = nullptr;
     return p;

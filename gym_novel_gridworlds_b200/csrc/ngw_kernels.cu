@@ -128,7 +128,7 @@ struct StepArgs {
     DevConfig cfg[NC > 0 ? NC : 1];
 };
 
-#define NGW_STAT_SLOTS 32
+#define NGW_STAT_SLOTS 512
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

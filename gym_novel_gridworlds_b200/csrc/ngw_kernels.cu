@@ -849,7 +849,8 @@ static StepParams step_params(ngw_handle* h, const int32_t* actions, int32_t* ob
 
 template <int NC>
 static void launch_step_nc(ngw_handle* h, const StepParams& p, int blocks, size_t smem, cudaStream_t s) {
-    static StepArgs<NC> args;                       // host staging of the argument block (copied by the launch)
+    static thread_local StepArgs<NC> args;          // host staging of the argument block (copied by the launch); per thread,
+                                                    // so distinct handles stay independent across host threads
     args.p = p;
     for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
     cudaLaunchConfig_t lc;

@@ -351,21 +351,21 @@ struct DevConfig {
 // the same address space as the grid row.  A tile can be shared by G warps: warp `g` of `G` casts beams
 // [g*NB, (g+1)*NB) with NB = 8/G (fast path) or beams g, g+G, ... (generic path).
 template <int NB>
-__device__ __forceinline__ void lidar_fast(const EnvRow& e, const DevConfig& dc, int32_t* obs, const int8_t* zero, int b0) {
+__device__ __forceinline__ void lidar_fast(const EnvRow& e, const ngw_config& cfg, const LidarDev& lidar, int32_t* obs,
+                                           const int8_t* zero, int b0) {
     // Each beam keeps a running cell pointer; axis beams advance one unit step per sample, diagonal beams advance
     // when round(0.71 k) grows (disp[1][k] - disp[1][k-1] is 0 or 1).  A beam that lands parks on `zero`, a cell
     // that always reads air, so no per-beam "still flying" test is needed in the loop.
-    const ngw_config& cfg = dc.c;
     const int K = cfg.max_range, L = cfg.n_lidar_items;
     int u[NB];
     const int8_t* at[NB];
     uint32_t hit[NB];                                                 // (sample index << 8) | item id, 0 = still flying
     const int8_t* base = e.m + e.r * e.ms + e.c;
 #pragma unroll
-    for (int j = 0; j < NB; j++) { u[j] = dc.lidar.unit[e.facing][b0 + j]; at[j] = base; hit[j] = 0; }
+    for (int j = 0; j < NB; j++) { u[j] = lidar.unit[e.facing][b0 + j]; at[j] = base; hit[j] = 0; }
     int prev0 = 0, prev1 = 0, flying = 1;                             // a unit step is never 0, so OR(u) != 0 <=> a beam still flies
     for (int k = 0; k < K && flying != 0; k++) {
-        const int d0 = dc.lidar.disp[0][k], d1 = dc.lidar.disp[1][k];
+        const int d0 = lidar.disp[0][k], d1 = lidar.disp[1][k];
         const int s0 = d0 - prev0, s1 = d1 - prev1;                   // warp-uniform step counts (0 or 1 for 8 beams)
         prev0 = d0; prev1 = d1;
         int id[NB];
@@ -394,16 +394,18 @@ __device__ __forceinline__ void lidar_fast(const EnvRow& e, const DevConfig& dc,
     }
 }
 
-__device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& dc, int32_t* obs, const int8_t* zero,
-                                              int g, int G, bool with_tail) {
+// `tables`: the beam tables to walk with — the env's own config, or (mixed batches whose configs all share one lidar
+// geometry) config 0's, so that the table reads stay warp-uniform even when the lanes of a warp differ in config.
+__device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& dc, const LidarDev& tables, int32_t* obs,
+                                              const int8_t* zero, int g, int G, bool with_tail) {
     const ngw_config& cfg = dc.c;
     const int B = cfg.n_beams, K = cfg.max_range, L = cfg.n_lidar_items;
     if (dc.lidar.fast) {
-        if (G == 1) lidar_fast<8>(e, dc, obs, zero, 0);
-        else if (G == 2) lidar_fast<4>(e, dc, obs, zero, g * 4);
-        else if (G == 3) { if (g < 2) lidar_fast<3>(e, dc, obs, zero, g * 3); else lidar_fast<2>(e, dc, obs, zero, 6); }
-        else if (G == 4) lidar_fast<2>(e, dc, obs, zero, g * 2);
-        else lidar_fast<1>(e, dc, obs, zero, g);
+        if (G == 1) lidar_fast<8>(e, cfg, tables, obs, zero, 0);
+        else if (G == 2) lidar_fast<4>(e, cfg, tables, obs, zero, g * 4);
+        else if (G == 3) { if (g < 2) lidar_fast<3>(e, cfg, tables, obs, zero, g * 3); else lidar_fast<2>(e, cfg, tables, obs, zero, 6); }
+        else if (G == 4) lidar_fast<2>(e, cfg, tables, obs, zero, g * 2);
+        else lidar_fast<1>(e, cfg, tables, obs, zero, g);
     } else {
         const int cells = e.ms * e.ms;
         const int pos = e.r * e.ms + e.c;

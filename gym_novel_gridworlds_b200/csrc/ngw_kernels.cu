@@ -106,6 +106,7 @@ struct StepParams {
     int ms, cells, inv_stride, obs_dim;
     int map_bytes, inv_bytes, obs_bytes, region_bytes;   // per-warp shared-memory carve-up
     int auto_reset, max_episode_steps;
+    int lidar_uniform;          // every config has the same beam tables (then config 0's are read, warp-uniformly)
     int cache_hints;            // bit 0: state tiles are loaded L2::evict_first, bit 1: the observation tile is stored evict_first
     int plain_store;            // 1 => write tiles back with ordinary coalesced stores instead of TMA bulk stores
     // K-step rollout (n_steps > 1 or random policy): the tile stays in shared memory across the steps
@@ -353,7 +354,8 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
 
     // ---- LidarInFront observation of the (possibly auto-reset) state into the shared-memory tile
     if (p.obs != nullptr && valid && cfg.n_beams > 0)
-        lidar_observe(env, dc, sobs + lane * p.obs_dim, szero, g, G, g == G - 1);
+        lidar_observe(env, dc, (NC > 1 && p.lidar_uniform) ? args.cfg[0].lidar : dc.lidar, sobs + lane * p.obs_dim, szero, g,
+                      G, g == G - 1);
 
     // Programmatic dependent launch: this tile's compute is done, let the next kernel of the stream start scheduling its
     // CTAs; its prologue (up to griddepcontrol.wait) touches no global memory, so it overlaps this kernel's store phase.
@@ -503,8 +505,8 @@ __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_list_kernel(const 
             __syncwarp();
             const int8_t* zero = reinterpret_cast<const int8_t*>(sc.hist);
             if (dc.c.n_beams > 0) {
-                if (dc.lidar.fast) { if (lane < 8) lidar_observe(env, dc, row, zero, lane, 8, lane == 7); }
-                else if (lane == 0) lidar_observe(env, dc, row, zero, 0, 1, true);
+                if (dc.lidar.fast) { if (lane < 8) lidar_observe(env, dc, dc.lidar, row, zero, lane, 8, lane == 7); }
+                else if (lane == 0) lidar_observe(env, dc, dc.lidar, row, zero, 0, 1, true);
             }
         }
         __syncwarp();
@@ -530,7 +532,7 @@ __global__ void observe_masked_kernel(const ResetParams p, int32_t* obs, int obs
     env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
     int32_t* row = obs + e * obs_dim;
     for (int i = 0; i < obs_dim; i++) row[i] = 0;
-    if (dc.c.n_beams > 0) lidar_observe(env, dc, row, reinterpret_cast<const int8_t*>(p.zero_byte), 0, 1, true);
+    if (dc.c.n_beams > 0) lidar_observe(env, dc, dc.lidar, row, reinterpret_cast<const int8_t*>(p.zero_byte), 0, 1, true);
 }
 
 // AgentMap.get_agentView (observation_wrappers.py:98-118): zero-padded (2v+1)^2 crop centred on the agent
@@ -586,6 +588,7 @@ struct ngw_handle {
     int map_bytes = 0, inv_bytes = 0, obs_bytes = 0, region_bytes = 0, warps = 4;
     bool use_tma = true, collect_stats = true, force_global_cfg = false, plain_store = false, use_pdl = true;
     bool pdl_in_graph = true;
+    bool lidar_uniform = false;
     DevConfig* d_cfgs = nullptr;
     std::vector<int16_t*> d_luts;
     std::vector<DevConfig> h_cfgs;
@@ -694,6 +697,13 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
         }
         dc.lidar.lut = d_lut;
         dc.c.beam_lut = nullptr;
+    }
+    h->lidar_uniform = n_cfgs > 1;
+    for (int i = 1; i < n_cfgs; i++) {
+        const LidarDev &a = h->h_cfgs[0].lidar, &b = h->h_cfgs[i].lidar;
+        if (!a.fast || !b.fast || h->h_cfgs[0].c.max_range != h->h_cfgs[i].c.max_range ||
+            memcmp(a.unit, b.unit, sizeof(a.unit)) != 0 || memcmp(a.disp, b.disp, sizeof(a.disp)) != 0)
+            h->lidar_uniform = false;
     }
     CK(cudaMalloc(&h->d_cfgs, sizeof(DevConfig) * n_cfgs));
     CK(cudaMemcpy(h->d_cfgs, h->h_cfgs.data(), sizeof(DevConfig) * n_cfgs, cudaMemcpyHostToDevice));
@@ -837,6 +847,7 @@ static StepParams step_params(ngw_handle* h, const int32_t* actions, int32_t* ob
     p.map_bytes = h->map_bytes; p.inv_bytes = h->inv_bytes; p.obs_bytes = h->obs_bytes;
     p.region_bytes = h->region_bytes; p.auto_reset = auto_reset; p.max_episode_steps = max_episode_steps;
     p.plain_store = h->plain_store ? 1 : 0;
+    p.lidar_uniform = h->lidar_uniform ? 1 : 0;
     // streaming data (each tile is read once and its 8 KB of observations written once per step) should not linger in L2:
     // measured on C2 9.15 -> 8.82 us/step, C3 29.3 -> 28.0, C5 278 -> 274 (hinting the inventory store as well: 9.0)
     p.cache_hints = getenv("NGW_HINTS") ? atoi(getenv("NGW_HINTS")) : 3;

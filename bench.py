@@ -322,6 +322,25 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     roll_ms = r0.elapsed_time(r1)
 
+    # ---- closed-loop rollout: integer linear policy evaluated on the device from each step's observation
+    roll_policy_ms = None
+    if batches[0].obs_dim > 0 and int(n_act.max().item()) <= 16:
+        A = int(n_act.max().item())
+        gw = torch.Generator(device=dev)
+        gw.manual_seed(7)
+        W = torch.randint(-9, 10, (batches[0].obs_dim, A), generator=gw, device=dev, dtype=torch.int32)
+        bvec = torch.randint(-30, 31, (A,), generator=gw, device=dev, dtype=torch.int32)
+        for h in batches:
+            h.rollout(roll_T, policy=(W, bvec), **step_kw)
+        torch.cuda.synchronize(dev)
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for i in range(n_roll):
+            batches[i % n_batches].rollout(roll_T, policy=(W, bvec), **step_kw)
+        q1.record()
+        torch.cuda.synchronize(dev)
+        roll_policy_ms = q0.elapsed_time(q1)
+
     # ---- eager (one python call per launch) figure, for the launch-bound picture
     n_eager = min(K, 2000)
     torch.cuda.synchronize(dev)
@@ -419,6 +438,10 @@ def run_ours(args, rank, world, local_rank):
             "rollout": {"note": "ngw_rollout: %d steps per launch, on-device uniform random policy, tile resident in "
                                 "shared memory; outputs are per-env sums + final observation" % roll_T,
                         "value": world * envs * roll_T * n_roll / (roll_ms * 1e-3), "unit": "env-steps/s"},
+            "rollout_policy": None if roll_policy_ms is None else {
+                "note": "ngw_rollout_policy: %d steps per launch, action = argmax(b + obs @ W) on the device from each "
+                        "step's lidar observation" % roll_T,
+                "value": world * envs * roll_T * n_roll / (roll_policy_ms * 1e-3), "unit": "env-steps/s"},
             "eager": {"value": envs / (eager_ms * 1e-3), "unit": "env-steps/s", "us_per_step": eager_ms * 1e3},
             "episode_stats": dict(zip(('steps', 'episodes', 'successes', 'reward_sum', 'cost_sum', 'resets',
                                        'invalid'), [float(x) for x in stats.cpu().numpy()[:7]])),

@@ -8,7 +8,7 @@ from . import opcodes as oc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libngw_b200.so')
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class ActionEntryC(C.Structure):
@@ -83,6 +83,9 @@ EXPORTS = {
                                 C.c_int32, C.c_int32]),
     'ngw_rollout': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    'ngw_rollout_policy': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_void_p]),
     'ngw_step_host_begin': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int32, C.c_int32]),
     'ngw_step_host_end': (C.c_int, [C.c_void_p]),

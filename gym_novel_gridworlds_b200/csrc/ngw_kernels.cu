@@ -116,6 +116,9 @@ struct StepParams {
     unsigned long long policy_seed;
     int32_t* done_count;        // optional: episodes finished per env during the launch
     int32_t* actions_out;       // optional: actions taken
+    const int32_t* policy_w;    // closed-loop linear policy: int32 [obs_dim][policy_actions] (nullptr = off)
+    const int32_t* policy_b;    // int32 [policy_actions]
+    int policy_actions;
     uint16_t* msg;              // optional: info['message'] codes (enum ngw_msg | arg << 5)
     int32_t* reset_list;        // single-step auto-reset: finished envs are queued here ...
     int32_t* reset_count;       // ... and regenerated by reset_list_kernel right after this launch
@@ -241,7 +244,8 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
     int action = 0;
     if (g == 0) {
         ps = p.pose[e];
-        if (stepping && valid) action = p.actions[e];
+        const bool given_actions = !(kMulti && (p.random_policy || p.policy_w != nullptr));   // else `actions` is a marker
+        if (stepping && valid && given_actions) action = p.actions[e];
     }
 
     if (kTma) mbar_wait(bar, 0);
@@ -264,8 +268,32 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
             const bool random_policy = kMulti && p.random_policy;
             for (int t = 0; t < n_steps; t++) {
                 int next_action = 0;                                  // prefetch the next step's action behind this step
-                if (!random_policy && t + 1 < n_steps && valid) next_action = p.actions[(t + 1) * p.act_stride + e];
-                if (random_policy && valid) {                         // uniform over the config's action ids
+                if (!random_policy && !(kMulti && p.policy_w != nullptr) && t + 1 < n_steps && valid)
+                    next_action = p.actions[(t + 1) * p.act_stride + e];
+                if (kMulti && p.policy_w != nullptr) {                // closed loop: observe, then greedy linear policy
+                    int32_t* row = sobs + lane * p.obs_dim;
+                    for (int j = 0; j < p.obs_dim; j++) row[j] = 0;
+                    if (valid && cfg.n_beams > 0) lidar_observe(env, dc, dc.lidar, row, szero, 0, 1, true);
+                    if (valid) {
+                        int acc[16];
+                        const int A = p.policy_actions;
+#pragma unroll
+                        for (int a = 0; a < 16; a++) acc[a] = a < A ? p.policy_b[a] : 0;
+                        const int D = cfg.n_lidar_items * cfg.n_beams + cfg.n_inv_obs;
+                        for (int j = 0; j < D; j++) {
+                            const int v = row[j];
+                            if (v == 0) continue;                      // the observation is sparse (<= 8 hits + inventory)
+                            const int32_t* w = p.policy_w + (size_t)j * A;
+#pragma unroll
+                            for (int a = 0; a < 16; a++) if (a < A) acc[a] += v * w[a];
+                        }
+                        int best = 0, best_v = acc[0];
+                        const int n_valid_actions = cfg.n_actions < A ? cfg.n_actions : A;
+#pragma unroll
+                        for (int a = 1; a < 16; a++) if (a < n_valid_actions && acc[a] > best_v) { best_v = acc[a]; best = a; }
+                        action = best;
+                    }
+                } else if (random_policy && valid) {                  // uniform over the config's action ids
                     Philox pr;
                     pr.init(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, 0xFFF);
                     action = (int)pr.below((uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
@@ -852,6 +880,7 @@ static StepParams step_params(ngw_handle* h, const int32_t* actions, int32_t* ob
     // measured on C2 9.15 -> 8.82 us/step, C3 29.3 -> 28.0, C5 278 -> 274 (hinting the inventory store as well: 9.0)
     p.cache_hints = getenv("NGW_HINTS") ? atoi(getenv("NGW_HINTS")) : 3;
     p.msg = h->msg; p.reset_list = h->reset_list; p.reset_count = h->reset_ctl;
+    p.policy_w = nullptr; p.policy_b = nullptr; p.policy_actions = 0;
     p.n_steps = 1; p.random_policy = 0; p.act_stride = 0; p.policy_seed = 0; p.done_count = nullptr; p.actions_out = nullptr;
     return p;
 }
@@ -866,7 +895,8 @@ static void launch_step_nc(ngw_handle* h, const StepParams& p, int blocks, size_
     for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
-    const bool multi = p.n_steps > 1 || p.random_policy || p.done_count != nullptr || p.actions_out != nullptr;
+    const bool multi = p.n_steps > 1 || p.random_policy || p.done_count != nullptr || p.actions_out != nullptr ||
+                       p.policy_w != nullptr;
     // the K-step rollout is all step logic (one lidar pass at the end): one warp per tile keeps more tiles resident
     const int warps = (multi && h->region_bytes * 12 <= 227 * 1024) ? 1 : h->warps;
     lc.gridDim = dim3(blocks); lc.blockDim = dim3(32 * warps); lc.dynamicSmemBytes = smem; lc.stream = s;
@@ -899,7 +929,8 @@ static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
     else launch_step_nc<16>(h, p, blocks, smem, s);
     h->launches++;
     CK(cudaGetLastError());
-    const bool multi = p.n_steps > 1 || p.random_policy || p.done_count != nullptr || p.actions_out != nullptr;
+    const bool multi = p.n_steps > 1 || p.random_policy || p.done_count != nullptr || p.actions_out != nullptr ||
+                       p.policy_w != nullptr;
     if (p.actions != nullptr && p.auto_reset && !multi) {           // regenerate the episodes the step kernel queued
         ResetParams rp = reset_params(h, nullptr, 2);
         rp.obs = p.obs;
@@ -936,6 +967,25 @@ int ngw_rollout(ngw_handle* h, const int32_t* actions, int32_t n_steps, uint64_t
                                0, h->n);
     p.n_steps = n_steps; p.random_policy = actions ? 0 : 1; p.act_stride = h->n; p.policy_seed = policy_seed;
     p.done_count = done_count; p.actions_out = actions_out;
+    return launch_step(h, p, (cudaStream_t)stream);
+}
+
+int ngw_rollout_policy(ngw_handle* h, const int32_t* weights, const int32_t* bias, int32_t n_policy_actions,
+                       int32_t n_steps, int32_t* obs, float* reward_sum, float* cost_sum, int32_t* done_count,
+                       uint8_t* last_done, uint8_t* last_result, int32_t* actions_out, int32_t auto_reset,
+                       int32_t max_episode_steps, void* stream) {
+    if (!h) return fail("null handle");
+    if (!weights || !bias || n_policy_actions < 1 || n_policy_actions > 16)
+        return fail("ngw_rollout_policy: need weights, bias and 1..16 policy actions");
+    if (h->obs_dim == 0 || !obs) return fail("ngw_rollout_policy: needs a LidarInFront observation (and an obs buffer)");
+    if (n_steps < 1) return fail("ngw_rollout_policy: n_steps must be >= 1");
+    if (!reward_sum || !cost_sum || !last_done || !last_result) return fail("ngw_rollout_policy: null output pointer");
+    if ((uintptr_t)obs & 15) return fail("ngw_rollout_policy: obs must be 16-byte aligned");
+    CK(cudaSetDevice(h->device));
+    StepParams p = step_params(h, reinterpret_cast<const int32_t*>(h->zero_byte), obs, reward_sum, last_done, cost_sum,
+                               last_result, auto_reset, max_episode_steps, 0, h->n);
+    p.n_steps = n_steps; p.random_policy = 0; p.act_stride = h->n; p.done_count = done_count; p.actions_out = actions_out;
+    p.policy_w = weights; p.policy_b = bias; p.policy_actions = n_policy_actions;
     return launch_step(h, p, (cudaStream_t)stream);
 }
 

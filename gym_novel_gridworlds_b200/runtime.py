@@ -137,10 +137,24 @@ class BatchHandle(object):
         return self.obs, self.reward, self.done, self.step_cost, self.result
 
     def rollout(self, n_steps, actions=None, policy_seed=0, auto_reset=False, max_episode_steps=0,
-                record_actions=False):
+                record_actions=False, policy=None):
         """n_steps consecutive steps in ONE launch (tile resident in shared memory).  actions: int32 CUDA tensor
-        [n_steps, n] or None for the on-device uniform random policy.  Returns (obs after the last step, reward sum,
-        step_cost sum, episodes finished, last done, last result[, actions taken])."""
+        [n_steps, n]; None = on-device uniform random policy; policy=(W int32 [obs_dim, A], b int32 [A]) = closed loop,
+        action = argmax(b + obs @ W) computed on the device from the current observation.  Returns (obs after the last
+        step, reward sum, step_cost sum, episodes finished, last done, last result[, actions taken])."""
+        if policy is not None:
+            w = torch.as_tensor(policy[0], device=self.device).to(torch.int32).contiguous()
+            b = torch.as_tensor(policy[1], device=self.device).to(torch.int32).contiguous()
+            assert w.shape == (self.obs_dim, b.numel()) and b.numel() <= 16
+            if not hasattr(self, '_done_count'):
+                self._done_count = torch.zeros(self.n, dtype=torch.int32, device=self.device)
+            taken = torch.empty((n_steps, self.n), dtype=torch.int32, device=self.device) if record_actions else None
+            capi.check(self.lib, self.lib.ngw_rollout_policy(
+                self._h, _ptr(w), _ptr(b), int(b.numel()), int(n_steps), _ptr(self.obs), _ptr(self.reward),
+                _ptr(self.step_cost), _ptr(self._done_count), _ptr(self.done), _ptr(self.result), _ptr(taken),
+                int(bool(auto_reset)), int(max_episode_steps), self._stream()))
+            out = (self.obs, self.reward, self.step_cost, self._done_count, self.done, self.result)
+            return out + (taken,) if record_actions else out
         if actions is not None:
             actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
             assert actions.shape == (n_steps, self.n)

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define NGW_ABI_VERSION 7
+#define NGW_ABI_VERSION 8
 
 #define NGW_MAX_ITEMS 24          /* reference asserts len(items) <= 20 (pogostick_v1_env.py:75,220) */
 #define NGW_MAX_ACTIONS 48
@@ -266,6 +266,15 @@ int ngw_step_host(ngw_handle* h, const int32_t* actions, int32_t* obs, float* re
 int ngw_rollout(ngw_handle* h, const int32_t* actions, int32_t n_steps, uint64_t policy_seed, int32_t* obs,
                 float* reward_sum, float* cost_sum, int32_t* done_count, uint8_t* last_done, uint8_t* last_result,
                 int32_t* actions_out, int32_t auto_reset, int32_t max_episode_steps, void* stream);
+
+/* Closed-loop K-step rollout: at every step the action is argmax_a (bias[a] + sum_j obs[j] * weights[j][a]) over the
+ * env's valid action ids, computed on the device from the current LidarInFront observation (lowest id wins ties).
+ * weights: DEVICE int32[obs_dim][n_policy_actions], bias: DEVICE int32[n_policy_actions], n_policy_actions <= 16.
+ * Integer arithmetic => bit-reproducible on the host.  Outputs as ngw_rollout. */
+int ngw_rollout_policy(ngw_handle* h, const int32_t* weights, const int32_t* bias, int32_t n_policy_actions,
+                       int32_t n_steps, int32_t* obs, float* reward_sum, float* cost_sum, int32_t* done_count,
+                       uint8_t* last_done, uint8_t* last_result, int32_t* actions_out, int32_t auto_reset,
+                       int32_t max_episode_steps, void* stream);
 
 /* The host-buffer step split in two, so that a caller with several batches can keep PCIe busy: _begin enqueues the
  * H2D copy, the launch and the D2H copies on the handle's own stream and returns; _end blocks until this handle's

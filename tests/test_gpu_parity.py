@@ -345,3 +345,29 @@ def test_placement_failure_rate_matches_reference_on_a_crowded_grid():
     ref = OracleBatch([cc], n)
     ref_fail = (ref.reset_legacy(31) != 0).mean()
     assert abs(gpu_fail - ref_fail) < 4 * np.sqrt(max(ref_fail, 1e-4) / n) + 2e-4, (gpu_fail, ref_fail)
+
+
+def test_closed_loop_policy_rollout_matches_host_replay():
+    """N1 policy hook: observations consumed and actions produced on the device (integer linear policy, greedy)."""
+    cc = _compiled({'env': scenarios.POGO, 'map_size': 10, 'chain': [['limit', scenarios.C2_SET], ['lidar', 8]]})
+    n, T, A = 1500 + 3, 48, cc.c.n_actions
+    ob = OracleBatch([cc], n)
+    ob.reset_legacy(2718)
+    h = BatchHandle([cc], n)
+    h.load_state(ob.map, ob.pose, ob.inv)
+    rng = np.random.RandomState(3)
+    W = rng.randint(-9, 10, size=(cc.obs_dim, A)).astype(np.int32)
+    b = rng.randint(-30, 31, size=A).astype(np.int32)
+    out = h.rollout(T, policy=(W, b), record_actions=True)
+    taken = out[-1].cpu().numpy()
+    rew = np.zeros(n)
+    for t in range(T):
+        obs = ob.observe().astype(np.int64)
+        a = np.argmax(obs @ W.astype(np.int64) + b, axis=1).astype(np.int32)       # first maximum, like the kernel
+        assert np.array_equal(a, taken[t]), "step %d" % t
+        o_obs, o_rew, o_done, o_cost, o_res = ob.step(a)
+        rew += o_rew
+    assert len(np.unique(taken)) >= 4                                             # the policy is not degenerate
+    assert np.array_equal(h.map.cpu().numpy().reshape(n, -1), ob.map) and np.array_equal(h.pose.cpu().numpy(), ob.pose)
+    assert np.array_equal(h.inventory.cpu().numpy(), ob.inv)
+    assert np.array_equal(out[0].cpu().numpy()[:, :cc.obs_dim], o_obs) and np.array_equal(out[1].cpu().numpy(), rew)

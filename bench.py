@@ -328,15 +328,15 @@ def run_ours(args, rank, world, local_rank):
         A = int(n_act.max().item())
         gw = torch.Generator(device=dev)
         gw.manual_seed(7)
-        W = torch.randint(-9, 10, (batches[0].obs_dim, A), generator=gw, device=dev, dtype=torch.int32)
-        bvec = torch.randint(-30, 31, (A,), generator=gw, device=dev, dtype=torch.int32)
+        w_pol = torch.randint(-9, 10, (batches[0].obs_dim, A), generator=gw, device=dev, dtype=torch.int32)
+        b_pol = torch.randint(-30, 31, (A,), generator=gw, device=dev, dtype=torch.int32)
         for h in batches:
-            h.rollout(roll_T, policy=(W, bvec), **step_kw)
+            h.rollout(roll_T, policy=(w_pol, b_pol), **step_kw)
         torch.cuda.synchronize(dev)
         q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         q0.record()
         for i in range(n_roll):
-            batches[i % n_batches].rollout(roll_T, policy=(W, bvec), **step_kw)
+            batches[i % n_batches].rollout(roll_T, policy=(w_pol, b_pol), **step_kw)
         q1.record()
         torch.cuda.synchronize(dev)
         roll_policy_ms = q0.elapsed_time(q1)

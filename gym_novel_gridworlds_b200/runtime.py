@@ -79,7 +79,10 @@ class BatchHandle(object):
 
     # ------------------------------------------------------------------
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        try:                                    # raw handle of torch's current stream, without building a Stream object
+            return C.c_void_p(torch._C._cuda_getCurrentRawStream(self.device.index))
+        except AttributeError:
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def close(self):
         if getattr(self, '_h', None) is not None and self._h.value:

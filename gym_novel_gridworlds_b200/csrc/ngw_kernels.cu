@@ -651,6 +651,9 @@ void ngw_destroy(ngw_handle* h) {
     delete h;
 }
 
+static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, int64_t n_envs, int32_t map_size,
+                       int32_t device, int64_t first_env_gid, uint64_t seed, const cudaDeviceProp& prop);
+
 int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t n_envs, int32_t map_size,
                int32_t device, int64_t first_env_gid, uint64_t seed) {
     if (!out || !cfgs || n_cfgs < 1 || n_cfgs > 255) return fail("ngw_create: need 1..255 configs");
@@ -661,6 +664,19 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail("ngw_create: this library is built for sm_100a (B200) only");
     ngw_handle* h = new ngw_handle();
+    h->device = device;
+    if (create_init(h, cfgs, n_cfgs, n_envs, map_size, device, first_env_gid, seed, prop)) {
+        std::string why = g_err;                    // ngw_destroy must not clobber the reason
+        ngw_destroy(h);
+        g_err = why;
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, int64_t n_envs, int32_t map_size,
+                       int32_t device, int64_t first_env_gid, uint64_t seed, const cudaDeviceProp& prop) {
     h->device = device; h->n = n_envs; h->np = (n_envs + 31) / 32 * 32; h->first_gid = first_env_gid; h->seed = seed;
     h->ms = map_size; h->cells = map_size * map_size; h->n_cfgs = n_cfgs;
     h->use_tma = getenv("NGW_NO_TMA") == nullptr;
@@ -674,13 +690,12 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
         if (c.n_items < 1 || c.n_items > NGW_MAX_ITEMS || c.n_actions < 0 || c.n_actions > NGW_MAX_ACTIONS ||
             c.n_recipes > NGW_MAX_RECIPES || c.n_place > NGW_MAX_PLACE || c.n_reset_ops > NGW_MAX_RESET_OPS ||
             c.n_beams < 0 || c.max_range < 0 || c.n_beams * c.max_range > 4096) {
-            delete h;
             return fail("ngw_create: config " + std::to_string(i) + " out of range");
         }
         if (c.n_items > h->inv_stride) h->inv_stride = c.n_items;
         int d = c.n_beams > 0 ? c.n_lidar_items * c.n_beams + c.n_inv_obs : 0;
         if (d > h->obs_dim) h->obs_dim = d;
-        if (c.n_beams > 0 && c.beam_lut == nullptr) { delete h; return fail("ngw_create: lidar config without beam_lut"); }
+        if (c.n_beams > 0 && c.beam_lut == nullptr) return fail("ngw_create: lidar config without beam_lut");
     }
     // device configs: the host beam LUT (d_row, d_col) becomes either the factorised 8-beam tables or an int16
     // linear-offset LUT for this map size
@@ -764,7 +779,7 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
     h->obs_bytes = 128 * (h->obs_dim > 0 ? h->obs_dim : 0);
     h->region_bytes = 16 + 128 + 1024 + h->map_bytes + h->inv_bytes + h->obs_bytes;
     h->region_bytes = (h->region_bytes + 127) & ~127;
-    if (h->region_bytes > 227 * 1024) { ngw_destroy(h); return fail("ngw_create: map too large for shared memory"); }
+    if (h->region_bytes > 227 * 1024) return fail("ngw_create: map too large for shared memory");
     // G warps share one tile (warp 0 steps, all G cast 8/G lidar beams): 2 for small grids — the one-step kernel needs
     // 48 registers, so two-warp tiles of a 65,536-env batch are all resident — more when shared memory limits the tiles
     int tiles_per_sm = (227 * 1024) / (h->region_bytes + 1024);
@@ -790,7 +805,6 @@ int ngw_create(ngw_handle** out, const ngw_config* cfgs, int32_t n_cfgs, int64_t
     CK(cudaFuncSetAttribute(step_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(step_kernel<false, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(step_kernel<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    *out = h;
     return 0;
 }
 

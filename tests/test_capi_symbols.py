@@ -58,3 +58,23 @@ def test_python_constants_match_header():
 def test_ctypes_config_layout_matches_the_c_compiler():
     from oracle import oracle_lib
     assert oracle_lib.lib().ngo_sizeof_config() == C.sizeof(capi.ConfigC)
+
+
+@pytest.mark.skipif(not os.path.exists(capi.LIB_PATH), reason="libngw_b200.so not built")
+def test_no_gpu_means_a_loud_failure_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import bench
+    from gym_novel_gridworlds_b200.compiler import compile_chain
+    from gym_novel_gridworlds_b200.runtime import BatchHandle
+    cc = compile_chain(bench.build_c2_chain())
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        BatchHandle([cc], 64)
+    lib = capi.load_library()
+    h = C.c_void_p()
+    assert lib.ngw_create(C.byref(h), C.byref(cc.c), 1, 64, 10, 0, 0, 0) != 0
+    assert lib.ngw_last_error() and not h.value
+    env = bench.build_c2_chain()
+    with pytest.raises(RuntimeError):
+        env.reset()

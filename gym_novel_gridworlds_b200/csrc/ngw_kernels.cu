@@ -194,10 +194,11 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     int8_t* szero = reinterpret_cast<int8_t*>(smem + 8);             // 8 bytes that always read 0 (landed lidar beams park here)
     uchar4* spose = reinterpret_cast<uchar4*>(smem + 16);            // pose after the step, for the other warps
-    uint32_t* sscratch = reinterpret_cast<uint32_t*>(smem + 16 + 128);   // 1 KB: radix-select histogram of the auto-reset
-    int8_t* smap = reinterpret_cast<int8_t*>(smem + 16 + 128 + 1024);
-    int32_t* sinv = reinterpret_cast<int32_t*>(smem + 16 + 128 + 1024 + p.map_bytes);
-    int32_t* sobs = reinterpret_cast<int32_t*>(smem + 16 + 128 + 1024 + p.map_bytes + p.inv_bytes);
+    constexpr int kScratch = kMulti ? 1024 : 0;                      // radix-select histogram of the in-place auto-reset (rollout only)
+    uint32_t* sscratch = reinterpret_cast<uint32_t*>(smem + 16 + 128);
+    int8_t* smap = reinterpret_cast<int8_t*>(smem + 16 + 128 + kScratch);
+    int32_t* sinv = reinterpret_cast<int32_t*>(smem + 16 + 128 + kScratch + p.map_bytes);
+    int32_t* sobs = reinterpret_cast<int32_t*>(smem + 16 + 128 + kScratch + p.map_bytes + p.inv_bytes);
 
     // ---- prologue without global memory: barrier, zero pad, zeroed observation tile
     const int8_t* gmap = p.map + e0 * p.cells;
@@ -913,7 +914,8 @@ static void launch_step_nc(ngw_handle* h, const StepParams& p, int blocks, size_
                        p.policy_w != nullptr;
     // the K-step rollout is all step logic (one lidar pass at the end): one warp per tile keeps more tiles resident
     const int warps = (multi && h->region_bytes * 12 <= 227 * 1024) ? 1 : h->warps;
-    lc.gridDim = dim3(blocks); lc.blockDim = dim3(32 * warps); lc.dynamicSmemBytes = smem; lc.stream = s;
+    lc.gridDim = dim3(blocks); lc.blockDim = dim3(32 * warps); lc.dynamicSmemBytes = multi ? smem : smem - 1024;
+    lc.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;

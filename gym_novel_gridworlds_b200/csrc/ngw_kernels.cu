@@ -176,6 +176,29 @@ __device__ __noinline__ void auto_reset_warp(const StepParams& p, const DevConfi
     }
 }
 
+// Episode statistics of one tile: warp reductions + one atomic per counter into one of NGW_STAT_SLOTS slots.
+__device__ __forceinline__ void tile_stats(double* stats, int lane, int valid, int done, int success, int did_reset,
+                                           int invalid, int reward, float cost) {
+    // five small counts (each <= 32) share one reduction: 6 bits apiece
+    unsigned packed = (unsigned)(valid ? done : 0) | ((unsigned)success << 6) | ((unsigned)did_reset << 12) |
+                      ((unsigned)invalid << 18) | ((unsigned)(valid ? 1 : 0) << 24);
+    packed = __reduce_add_sync(0xFFFFFFFFu, packed);
+    const int r_sum = __reduce_add_sync(0xFFFFFFFFu, reward);
+    const float c_sum = warp_sum(cost);
+    if (lane == 0) {
+        const int n_done = packed & 63, n_succ = (packed >> 6) & 63, n_reset = (packed >> 12) & 63;
+        const int n_inv = (packed >> 18) & 63, n_valid = (packed >> 24) & 63;
+        double* s = stats + (size_t)(blockIdx.x % NGW_STAT_SLOTS) * NGW_STAT_COUNT;
+        atomicAdd(&s[NGW_STAT_STEPS], (double)(n_valid - n_inv));
+        atomicAdd(&s[NGW_STAT_REWARD_SUM], (double)r_sum);
+        atomicAdd(&s[NGW_STAT_COST_SUM], (double)c_sum);
+        if (n_done) atomicAdd(&s[NGW_STAT_EPISODES], (double)n_done);
+        if (n_succ) atomicAdd(&s[NGW_STAT_SUCCESSES], (double)n_succ);
+        if (n_reset) atomicAdd(&s[NGW_STAT_RESETS], (double)n_reset);
+        if (n_inv) atomicAdd(&s[NGW_STAT_INVALID], (double)n_inv);
+    }
+}
+
 // ------------------------------------------------------------------ the fused step + LidarInFront kernel
 // One CTA = one tile of 32 consecutive envs, G = blockDim.x / 32 warps.  Lane l of every warp owns env l of the tile.
 // Warp 0 runs the flattened step; then all G warps cast 8/G lidar beams each for their lane's env.  G = 1 is the plain
@@ -252,6 +275,9 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
     if (kTma) mbar_wait(bar, 0);
     else __syncthreads();
 
+    StepOut st_out;                                                  // one-step kernel: statistics are folded after the lidar,
+    st_out.reward = 0; st_out.done = 0; st_out.result = 0; st_out.cost = 0.0f; st_out.msg = 0;   // off the path to the barrier
+    int st_success = 0, st_reset = 0, st_invalid = 0;
     EnvRow env;
     env.m = smap + lane * p.cells;
     env.gm = p.map + e * p.cells;
@@ -342,27 +368,12 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
                         env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
                     }
                 }
-                if (p.stats != nullptr) {
-                    int n_done = __reduce_add_sync(0xFFFFFFFFu, valid ? o.done : 0);
-                    int n_succ = __reduce_add_sync(0xFFFFFFFFu, success);
-                    int n_reset = __reduce_add_sync(0xFFFFFFFFu, did_reset);
-                    int n_inv = __reduce_add_sync(0xFFFFFFFFu, invalid);
-                    int n_valid = __reduce_add_sync(0xFFFFFFFFu, valid ? 1 : 0);
-                    int r_sum = __reduce_add_sync(0xFFFFFFFFu, o.reward);
-                    float c_sum = warp_sum(o.cost);
-                    if (lane == 0) {
-                        double* s = p.stats + (size_t)(blockIdx.x % NGW_STAT_SLOTS) * NGW_STAT_COUNT;
-                        atomicAdd(&s[NGW_STAT_STEPS], (double)(n_valid - n_inv));
-                        atomicAdd(&s[NGW_STAT_REWARD_SUM], (double)r_sum);
-                        atomicAdd(&s[NGW_STAT_COST_SUM], (double)c_sum);
-                        if (n_done) atomicAdd(&s[NGW_STAT_EPISODES], (double)n_done);
-                        if (n_succ) atomicAdd(&s[NGW_STAT_SUCCESSES], (double)n_succ);
-                        if (n_reset) atomicAdd(&s[NGW_STAT_RESETS], (double)n_reset);
-                        if (n_inv) atomicAdd(&s[NGW_STAT_INVALID], (double)n_inv);
-                    }
-                }
+                if (kMulti && p.stats != nullptr)
+                    tile_stats(p.stats, lane, valid, o.done, success, did_reset, invalid, o.reward, o.cost);
+                if (!kMulti) { st_success = success; st_reset = did_reset; st_invalid = invalid; }
                 action = next_action;
             }
+            if (!kMulti) st_out = o;
             if (valid) {
                 p.pose[e] = ps;
                 p.reward[e] = reward_sum;                             // == the step's reward when n_steps == 1
@@ -385,6 +396,9 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
     if (p.obs != nullptr && valid && cfg.n_beams > 0)
         lidar_observe(env, dc, (NC > 1 && p.lidar_uniform) ? args.cfg[0].lidar : dc.lidar, sobs + lane * p.obs_dim, szero, g,
                       G, g == G - 1);
+
+    if (!kMulti && g == 0 && stepping && p.stats != nullptr)
+        tile_stats(p.stats, lane, valid, st_out.done, st_success, st_reset, st_invalid, st_out.reward, st_out.cost);
 
     // Programmatic dependent launch: this tile's compute is done, let the next kernel of the stream start scheduling its
     // CTAs; its prologue (up to griddepcontrol.wait) touches no global memory, so it overlaps this kernel's store phase.

@@ -373,14 +373,14 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
                 if (!kMulti) { st_success = success; st_reset = did_reset; st_invalid = invalid; }
                 action = next_action;
             }
-            if (!kMulti) st_out = o;
-            if (valid) {
+            if (!kMulti) st_out = o;                                  // one-step kernel: outputs are stored after the lidar
+            if (kMulti && valid) {
                 p.pose[e] = ps;
-                p.reward[e] = reward_sum;                             // == the step's reward when n_steps == 1
+                p.reward[e] = reward_sum;
                 p.done[e] = (uint8_t)o.done;
                 p.cost[e] = cost_sum;
                 p.result[e] = (uint8_t)o.result;
-                if (kMulti && p.done_count != nullptr) p.done_count[e] = done_count;
+                if (p.done_count != nullptr) p.done_count[e] = done_count;
                 if (p.msg != nullptr) p.msg[e] = (uint16_t)o.msg;
             }
         }
@@ -397,8 +397,18 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
         lidar_observe(env, dc, (NC > 1 && p.lidar_uniform) ? args.cfg[0].lidar : dc.lidar, sobs + lane * p.obs_dim, szero, g,
                       G, g == G - 1);
 
-    if (!kMulti && g == 0 && stepping && p.stats != nullptr)
-        tile_stats(p.stats, lane, valid, st_out.done, st_success, st_reset, st_invalid, st_out.reward, st_out.cost);
+    if (!kMulti && g == 0 && stepping) {                             // outputs and statistics, off the path to the barrier
+        if (valid) {
+            p.pose[e] = ps;
+            p.reward[e] = (float)st_out.reward;
+            p.done[e] = (uint8_t)st_out.done;
+            p.cost[e] = st_out.cost;
+            p.result[e] = (uint8_t)st_out.result;
+            if (p.msg != nullptr) p.msg[e] = (uint16_t)st_out.msg;
+        }
+        if (p.stats != nullptr)
+            tile_stats(p.stats, lane, valid, st_out.done, st_success, st_reset, st_invalid, st_out.reward, st_out.cost);
+    }
 
     // Programmatic dependent launch: this tile's compute is done, let the next kernel of the stream start scheduling its
     // CTAs; its prologue (up to griddepcontrol.wait) touches no global memory, so it overlaps this kernel's store phase.

@@ -205,6 +205,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group('nccl', device_id=dev)
 
     desc, compiled, envs, cfg_rule, step_kw = build_workload(args.workload)

@@ -26,6 +26,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+    os.environ['NCCL_DEBUG'] = 'WARN'                  # keep NCCL's version banner off stdout: ONE JSON line only
 
 ENVS_PER_BATCH = 65536
 C2_SET = ['Forward', 'Left', 'Right', 'Break', 'Place_tree_tap', 'Extract_rubber',
@@ -205,9 +207,20 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: one JSON line only
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner to stdout when the communicator is created (NCCL_DEBUG=VERSION is set in this
+        # image); stdout must carry ONE JSON line, so fd 1 points at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     desc, compiled, envs, cfg_rule, step_kw = build_workload(args.workload)
     n_cfg = len(compiled)

@@ -1,7 +1,7 @@
 // ngw_device.cuh — per-env device code of the batched NovelGridworld simulator (sm_100a).
 //
 // One lane owns one environment.  The lane's grid row, inventory row and observation row live in
-// shared memory (staged by the kernels in ngw_kernels.cu); everything here works on those rows through
+// shared memory (staged by the kernels in ngw_step.cuh); everything here works on those rows through
 // plain pointers, so the same code also runs straight on global memory in the (cold) reset kernel.
 //
 // Semantics follow the reference file:line cited at each function (paths under

@@ -1,0 +1,447 @@
+// ngw_step.cuh — the hot kernel of libngw_b200.so: fused step + novelties + LidarInFront (+ rollout), sm_100a only.
+//
+// Data layout in HBM (struct of arrays, rows padded to a multiple of 32 envs so a tile of 32 envs is one contiguous,
+// 128-byte aligned span in every array):
+//     map   int8  [Np][ms*ms]      pose uchar4 [Np] (row, col, facing, selected)      inventory int32 [Np][Is]
+//     cfg_id uint8 [Np]            episode u32 [Np]     ep_len i32 [Np]     error_flags u32 [Np]
+//
+// step_kernel: one CTA = one tile of 32 envs, one lane = one env.  The tile's grid rows and inventory rows are brought
+// into shared memory with two TMA 1-D bulk copies (cp.async.bulk + mbarrier), warp 0 runs the flattened reference step
+// on the rows, all warps cast the LidarInFront beams into an observation tile in shared memory, and the inventory tile
+// and observation tile leave with two TMA bulk stores; pose / reward / done / step_cost / result are plain coalesced
+// accesses.  Algorithmic bytes per env-step are in DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "ngw_device.cuh"
+
+namespace ngw {
+
+// ------------------------------------------------------------------ PTX helpers (TMA 1-D bulk copies, mbarrier)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// L2 cache-hinted variants (createpolicy + .L2::cache_hint)
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait sleeps in hardware; the time bound turns a lost transaction into a trap instead of a hung GPU
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > 4000000000ll) __trap();
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------ parameters
+struct StepParams {
+    const DevConfig* dcfgs;     // global-memory copy of the configs (cold paths, and the hot path when NC == 0)
+    int8_t* map;
+    uchar4* pose;
+    int32_t* inv;
+    const uint8_t* cfg_id;
+    uint32_t* episode;
+    int32_t* ep_len;
+    uint32_t* err;
+    const int32_t* actions;     // nullptr => observe only (no step, no outputs but obs)
+    int32_t* obs;               // nullptr => no observation
+    float* reward;
+    uint8_t* done;
+    float* cost;
+    uint8_t* result;
+    double* stats;              // [NGW_STAT_SLOTS][NGW_STAT_COUNT] or nullptr
+    long long env_begin, env_end;   // env range of this launch (env_begin multiple of 32)
+    long long first_gid;
+    unsigned long long seed;
+    int ms, cells, inv_stride, obs_dim;
+    int map_bytes, inv_bytes, obs_bytes, region_bytes;   // per-warp shared-memory carve-up
+    int auto_reset, max_episode_steps;
+    int lidar_uniform;          // every config has the same beam tables (then config 0's are read, warp-uniformly)
+    int cache_hints;            // bit 0: state tiles are loaded L2::evict_first, bit 1: the observation tile is stored evict_first
+    int plain_store;            // 1 => write tiles back with ordinary coalesced stores instead of TMA bulk stores
+    // K-step rollout (n_steps > 1 or random policy): the tile stays in shared memory across the steps
+    int n_steps;                // steps per launch (1 for ngw_step)
+    int random_policy;          // 1 => actions drawn on the device (Philox), `actions` is only a non-null marker
+    long long act_stride;       // elements between consecutive steps in `actions` / `actions_out`
+    unsigned long long policy_seed;
+    int32_t* done_count;        // optional: episodes finished per env during the launch
+    int32_t* actions_out;       // optional: actions taken
+    const int32_t* policy_w;    // closed-loop linear policy: int32 [obs_dim][policy_actions] (nullptr = off)
+    const int32_t* policy_b;    // int32 [policy_actions]
+    int policy_actions;
+    uint16_t* msg;              // optional: info['message'] codes (enum ngw_msg | arg << 5)
+    int32_t* reset_list;        // single-step auto-reset: finished envs are queued here ...
+    int32_t* reset_count;       // ... and regenerated by reset_list_kernel right after this launch
+};
+
+// Kernel argument block: the parameters plus up to NC configs INLINE, so that every config read in the hot path
+// is a constant-bank operand (c[0x0][..]) instead of a global load.  NC == 0 falls back to global memory.
+template <int NC>
+struct StepArgs {
+    StepParams p;
+    DevConfig cfg[NC > 0 ? NC : 1];
+};
+
+#define NGW_STAT_SLOTS 512
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void warp_copy16(void* dst, const void* src, int bytes, int lane) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    for (int i = lane; i < (bytes >> 4); i += 32) d[i] = s[i];
+}
+
+// Cold: fused auto-reset.  Called by the whole step warp; every lane that finished an episode is regenerated in turn by
+// all 32 lanes (reset_env_warp), then its grid row goes back to HBM with coalesced stores.
+__device__ __noinline__ void auto_reset_warp(const StepParams& p, const DevConfig* dcfgs, int cfg_i, bool need,
+                                             int8_t* smap, int32_t* sinv, uint32_t* hist, long long e0, uchar4& ps) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();                                                    // every lane's step writes to the tile are visible
+    uint32_t pending = __ballot_sync(0xFFFFFFFFu, need);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const long long e = e0 + src;
+        const int ci = __shfl_sync(0xFFFFFFFFu, cfg_i, src);
+        uint32_t ep = p.episode[e] + 1;
+        __syncwarp();
+        if (lane == 0) p.episode[e] = ep;
+        int8_t* m = smap + src * p.cells;
+        int32_t* inv = sinv + src * p.inv_stride;
+        int r = 0, c = 0, f = 0, sel = 0;
+        uint32_t err = reset_env_warp(&dcfgs[ci].c, m, inv, p.ms, p.inv_stride, p.seed, (uint64_t)(p.first_gid + e), ep,
+                                      true, 0, NGW_MAX_RESET_OPS, hist, r, c, f, sel);
+        int8_t* grow = p.map + e * p.cells;
+        for (int i = lane; i < p.cells; i += 32) grow[i] = m[i];
+        if (lane == src) {
+            ps = make_uchar4((unsigned char)r, (unsigned char)c, (unsigned char)f, (unsigned char)sel);
+            if (err) p.err[e] |= err;
+        }
+        __syncwarp();
+    }
+}
+
+// Episode statistics of one tile: warp reductions + one atomic per counter into one of NGW_STAT_SLOTS slots.
+__device__ __forceinline__ void tile_stats(double* stats, int lane, int valid, int done, int success, int did_reset,
+                                           int invalid, int reward, float cost) {
+    // five small counts (each <= 32) share one reduction: 6 bits apiece
+    unsigned packed = (unsigned)(valid ? done : 0) | ((unsigned)success << 6) | ((unsigned)did_reset << 12) |
+                      ((unsigned)invalid << 18) | ((unsigned)(valid ? 1 : 0) << 24);
+    packed = __reduce_add_sync(0xFFFFFFFFu, packed);
+    const int r_sum = __reduce_add_sync(0xFFFFFFFFu, reward);
+    const float c_sum = warp_sum(cost);
+    if (lane == 0) {
+        const int n_done = packed & 63, n_succ = (packed >> 6) & 63, n_reset = (packed >> 12) & 63;
+        const int n_inv = (packed >> 18) & 63, n_valid = (packed >> 24) & 63;
+        double* s = stats + (size_t)(blockIdx.x % NGW_STAT_SLOTS) * NGW_STAT_COUNT;
+        atomicAdd(&s[NGW_STAT_STEPS], (double)(n_valid - n_inv));
+        atomicAdd(&s[NGW_STAT_REWARD_SUM], (double)r_sum);
+        atomicAdd(&s[NGW_STAT_COST_SUM], (double)c_sum);
+        if (n_done) atomicAdd(&s[NGW_STAT_EPISODES], (double)n_done);
+        if (n_succ) atomicAdd(&s[NGW_STAT_SUCCESSES], (double)n_succ);
+        if (n_reset) atomicAdd(&s[NGW_STAT_RESETS], (double)n_reset);
+        if (n_inv) atomicAdd(&s[NGW_STAT_INVALID], (double)n_inv);
+    }
+}
+
+// ------------------------------------------------------------------ the fused step + LidarInFront kernel
+// One CTA = one tile of 32 consecutive envs, G = blockDim.x / 32 warps.  Lane l of every warp owns env l of the tile.
+// Warp 0 runs the flattened step; then all G warps cast 8/G lidar beams each for their lane's env.  G = 1 is the plain
+// one-warp-per-tile kernel; G > 1 shortens the per-tile latency where shared memory limits the tiles per SM.
+template <bool kTma, int NC, bool kMulti>
+__global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepArgs<NC> args) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const StepParams& p = args.p;
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, G = blockDim.x >> 5;
+    const long long e0 = p.env_begin + (long long)blockIdx.x * 32;
+    const long long e = e0 + lane;
+    const bool valid = e < p.env_end;
+    const bool full_tile = e0 + 32 <= p.env_end;
+    const bool stepping = p.actions != nullptr;
+
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    int8_t* szero = reinterpret_cast<int8_t*>(smem + 8);             // 8 bytes that always read 0 (landed lidar beams park here)
+    uchar4* spose = reinterpret_cast<uchar4*>(smem + 16);            // pose after the step, for the other warps
+    constexpr int kScratch = kMulti ? 1024 : 0;                      // radix-select histogram of the in-place auto-reset (rollout only)
+    uint32_t* sscratch = reinterpret_cast<uint32_t*>(smem + 16 + 128);
+    int8_t* smap = reinterpret_cast<int8_t*>(smem + 16 + 128 + kScratch);
+    int32_t* sinv = reinterpret_cast<int32_t*>(smem + 16 + 128 + kScratch + p.map_bytes);
+    int32_t* sobs = reinterpret_cast<int32_t*>(smem + 16 + 128 + kScratch + p.map_bytes + p.inv_bytes);
+
+    // ---- prologue without global memory: barrier, zero pad, zeroed observation tile
+    const int8_t* gmap = p.map + e0 * p.cells;
+    int32_t* ginv = p.inv + e0 * p.inv_stride;
+    if (threadIdx.x == 0) {
+        if (kTma) mbar_init(bar, 1);
+        *reinterpret_cast<uint64_t*>(szero) = 0ull;
+    }
+    if (p.obs != nullptr) {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* o4 = reinterpret_cast<uint4*>(sobs);
+        for (int i = threadIdx.x; i < (p.obs_bytes >> 4); i += blockDim.x) o4[i] = z;
+    }
+    __syncthreads();                                                 // barrier init visible before anyone waits on it
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // previous kernel of the stream done + visible
+
+    // ---- stage the tile: grid rows + inventory rows (state arrays are padded, a full tile is always readable)
+    if (kTma) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, (uint32_t)(p.map_bytes + p.inv_bytes));
+            if (p.cache_hints & 1) {
+                uint64_t pol = policy_evict_first();
+                bulk_g2s_hint(smap, gmap, (uint32_t)p.map_bytes, bar, pol);
+                bulk_g2s_hint(sinv, ginv, (uint32_t)p.inv_bytes, bar, pol);
+            } else {
+                bulk_g2s(smap, gmap, (uint32_t)p.map_bytes, bar);
+                bulk_g2s(sinv, ginv, (uint32_t)p.inv_bytes, bar);
+            }
+        }
+    } else {
+        const uint4* s4 = reinterpret_cast<const uint4*>(gmap);
+        uint4* d4 = reinterpret_cast<uint4*>(smap);
+        for (int i = threadIdx.x; i < (p.map_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
+        s4 = reinterpret_cast<const uint4*>(ginv);
+        d4 = reinterpret_cast<uint4*>(sinv);
+        for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
+    }
+
+    // ---- while the copies fly: per-lane scalars
+    const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[e];
+    const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
+    const ngw_config& cfg = dc.c;
+    uchar4 ps = make_uchar4(0, 0, 0, 0);
+    int action = 0;
+    if (g == 0) {
+        ps = p.pose[e];
+        const bool given_actions = !(kMulti && (p.random_policy || p.policy_w != nullptr));   // else `actions` is a marker
+        if (stepping && valid && given_actions) action = p.actions[e];
+    }
+
+    if (kTma) mbar_wait(bar, 0);
+    else __syncthreads();
+
+    StepOut st_out;                                                  // one-step kernel: statistics are folded after the lidar,
+    st_out.reward = 0; st_out.done = 0; st_out.result = 0; st_out.cost = 0.0f; st_out.msg = 0;   // off the path to the barrier
+    int st_success = 0, st_reset = 0, st_invalid = 0;
+    EnvRow env;
+    env.m = smap + lane * p.cells;
+    env.gm = p.map + e * p.cells;
+    env.inv = sinv + lane * p.inv_stride;
+    env.ms = p.ms;
+
+    if (g == 0) {
+        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+        if (stepping) {
+            StepOut o;
+            o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0;
+            float reward_sum = 0.0f, cost_sum = 0.0f;
+            int done_count = 0;
+            const int n_steps = kMulti ? p.n_steps : 1;               // kMulti == false: the plain one-step kernel
+            const bool random_policy = kMulti && p.random_policy;
+            for (int t = 0; t < n_steps; t++) {
+                int next_action = 0;                                  // prefetch the next step's action behind this step
+                if (!random_policy && !(kMulti && p.policy_w != nullptr) && t + 1 < n_steps && valid)
+                    next_action = p.actions[(t + 1) * p.act_stride + e];
+                if (kMulti && p.policy_w != nullptr) {                // closed loop: observe, then greedy linear policy
+                    int32_t* row = sobs + lane * p.obs_dim;
+                    for (int j = 0; j < p.obs_dim; j++) row[j] = 0;
+                    if (valid && cfg.n_beams > 0) lidar_observe(env, dc, dc.lidar, row, szero, 0, 1, true);
+                    if (valid) {
+                        int acc[16];
+                        const int A = p.policy_actions;
+#pragma unroll
+                        for (int a = 0; a < 16; a++) acc[a] = a < A ? p.policy_b[a] : 0;
+                        const int D = cfg.n_lidar_items * cfg.n_beams + cfg.n_inv_obs;
+                        for (int j = 0; j < D; j++) {
+                            const int v = row[j];
+                            if (v == 0) continue;                      // the observation is sparse (<= 8 hits + inventory)
+                            const int32_t* w = p.policy_w + (size_t)j * A;
+#pragma unroll
+                            for (int a = 0; a < 16; a++) if (a < A) acc[a] += v * w[a];
+                        }
+                        int best = 0, best_v = acc[0];
+                        const int n_valid_actions = cfg.n_actions < A ? cfg.n_actions : A;
+#pragma unroll
+                        for (int a = 1; a < 16; a++) if (a < n_valid_actions && acc[a] > best_v) { best_v = acc[a]; best = a; }
+                        action = best;
+                    }
+                } else if (random_policy && valid) {                  // uniform over the config's action ids
+                    Philox pr;
+                    pr.init(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, 0xFFF);
+                    action = (int)pr.below((uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
+                }
+                if (kMulti && p.actions_out != nullptr && valid) p.actions_out[t * p.act_stride + e] = action;
+                o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0;
+                int invalid = 0, did_reset = 0, success = 0;
+                if (valid) {
+                    ngw_action_entry a;
+                    a.op = NGW_OP_INVALID;
+                    if (action >= 0 && action < cfg.n_actions) {
+                        uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
+                        memcpy(&a, &raw, sizeof(a));
+                    }
+                    if (a.op == NGW_OP_INVALID) {                     // wrappers.py:76 / pogostick_v1_env.py:236 would raise
+                        invalid = 1;
+                        p.err[e] |= NGW_ERR_INVALID_ACTION;
+                    } else {
+                        step_env(env, cfg, a, o);
+                        success = o.done && env.inv[cfg.id_goal] >= 1;
+                        int finished = o.done;
+                        if (p.max_episode_steps > 0) {
+                            int len = p.ep_len[e] + 1;
+                            if (len >= p.max_episode_steps) { finished = 1; o.done = 1; } // harness truncation knob
+                            p.ep_len[e] = finished && p.auto_reset ? 0 : len;
+                        }
+                        if (finished && p.auto_reset) { did_reset = 1; }
+                    }
+                    ps = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
+                                     (unsigned char)env.sel);
+                    reward_sum += (float)o.reward; cost_sum += o.cost; done_count += o.done;
+                }
+                if (p.auto_reset) {
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, did_reset);
+                    if (bal != 0 && !kMulti) {
+                        // single step: queue the finished envs; reset_list_kernel (next in the stream, one warp per env at
+                        // full occupancy) regenerates them and overwrites their observation rows
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(p.reset_count, __popc(bal));
+                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                        if (did_reset) p.reset_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)e;
+                    } else if (bal != 0) {
+                        // rollout: the next step needs the new episode now -> regenerate in place, warp-cooperatively
+                        auto_reset_warp(p, p.dcfgs, cfg_i, did_reset != 0, smap, sinv, sscratch, e0, ps);
+                        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+                    }
+                }
+                if (kMulti && p.stats != nullptr)
+                    tile_stats(p.stats, lane, valid, o.done, success, did_reset, invalid, o.reward, o.cost);
+                if (!kMulti) { st_success = success; st_reset = did_reset; st_invalid = invalid; }
+                action = next_action;
+            }
+            if (!kMulti) st_out = o;                                  // one-step kernel: outputs are stored after the lidar
+            if (kMulti && valid) {
+                p.pose[e] = ps;
+                p.reward[e] = reward_sum;
+                p.done[e] = (uint8_t)o.done;
+                p.cost[e] = cost_sum;
+                p.result[e] = (uint8_t)o.result;
+                if (p.done_count != nullptr) p.done_count[e] = done_count;
+                if (p.msg != nullptr) p.msg[e] = (uint16_t)o.msg;
+            }
+        }
+        if (G > 1) spose[lane] = ps;
+    }
+    if (G > 1) {
+        __syncthreads();                                             // step results (grid, inventory, pose) visible to all warps
+        ps = spose[lane];
+        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+    }
+
+    // ---- LidarInFront observation of the (possibly auto-reset) state into the shared-memory tile
+    if (p.obs != nullptr && valid && cfg.n_beams > 0)
+        lidar_observe(env, dc, (NC > 1 && p.lidar_uniform) ? args.cfg[0].lidar : dc.lidar, sobs + lane * p.obs_dim, szero, g,
+                      G, g == G - 1);
+
+    if (!kMulti && g == 0 && stepping) {                             // outputs and statistics, off the path to the barrier
+        if (valid) {
+            p.pose[e] = ps;
+            p.reward[e] = (float)st_out.reward;
+            p.done[e] = (uint8_t)st_out.done;
+            p.cost[e] = st_out.cost;
+            p.result[e] = (uint8_t)st_out.result;
+            if (p.msg != nullptr) p.msg[e] = (uint16_t)st_out.msg;
+        }
+        if (p.stats != nullptr)
+            tile_stats(p.stats, lane, valid, st_out.done, st_success, st_reset, st_invalid, st_out.reward, st_out.cost);
+    }
+
+    // Programmatic dependent launch: this tile's compute is done, let the next kernel of the stream start scheduling its
+    // CTAs; its prologue (up to griddepcontrol.wait) touches no global memory, so it overlaps this kernel's store phase.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    // ---- write back: inventory tile (only when stepping) and observation tile
+    __syncthreads();
+    if (kTma && full_tile && !p.plain_store) {
+        if (threadIdx.x < 32) {
+            fence_async_smem();
+            __syncwarp();
+            if (threadIdx.x == 0) {
+                if (p.cache_hints & 2) {
+                    uint64_t pol = policy_evict_first();
+                    if (stepping) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
+                    if (p.obs != nullptr) bulk_s2g_hint(p.obs + e0 * p.obs_dim, sobs, (uint32_t)p.obs_bytes, pol);
+                } else {
+                    if (stepping) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
+                    if (p.obs != nullptr) bulk_s2g(p.obs + e0 * p.obs_dim, sobs, (uint32_t)p.obs_bytes);
+                }
+                bulk_commit();
+                bulk_wait_read0();                                   // shared memory must outlive the reads
+            }
+        }
+    } else {
+        if (stepping) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
+            uint4* d4 = reinterpret_cast<uint4*>(ginv);
+            for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
+        }
+        if (p.obs != nullptr) {
+            int n = (int)((p.env_end - e0 < 32 ? p.env_end - e0 : 32)) * p.obs_dim;
+            int32_t* gobs = p.obs + e0 * p.obs_dim;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) gobs[i] = sobs[i];
+        }
+    }
+}
+
+
+}  // namespace ngw

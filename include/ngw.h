@@ -2,7 +2,7 @@
  * ngw.h — C-ABI of the B200-native batched NovelGridworld simulator (libngw_b200.so)
  *
  * One header, three users:
- *   - gym_novel_gridworlds_b200/csrc/ *.cu   the sm_100a kernels and the C-ABI library (the product),
+ *   - gym_novel_gridworlds_b200/csrc/ *.cu*  the sm_100a kernels and the C-ABI library (the product),
  *   - oracle/ngw_oracle.c                    the CPU restatement used ONLY as the parity checker,
  *   - gym_novel_gridworlds_b200/capi.py      ctypes mirror of these structs (the Python host layer).
  *

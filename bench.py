@@ -137,8 +137,20 @@ class ClockSampler(threading.Thread):
         names = {0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x10: 'sync_boost',
                  0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown', 0x80: 'hw_power_brake_slowdown',
                  0x100: 'display_clock_setting'}
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if not self.samples:                            # NVML unavailable: one nvidia-smi reading as a last resort
+            try:
+                import subprocess
+                q = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=clocks.sm,clocks.max.sm,'
+                                    'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+                                    'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap',
+                                    '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=20)
+                f = [x.strip() for x in q.stdout.strip().split(',')]
+                labels = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+                return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]),
+                        "reasons": [n for n, v in zip(labels, f[2:]) if v.lower().startswith('active')],
+                        "samples": 1, "source": "nvidia-smi after the timed region"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         inside = [s for s in self.samples if t0 <= s[0] <= t1] or [s for s in self.samples if s[3] > 0] or self.samples
         reasons = 0
         for s in inside:

@@ -425,7 +425,15 @@ void ngo_observe(const ngw_config* cfg, int ms, const int8_t* map, const uint8_t
     for (int b = 0; b < B; b++) {
         double x, y;
         if (B <= 64) { x = ratio[pose[2]][b][0]; y = ratio[pose[2]][b][1]; }
-        else { int dr, dc; ngo_beam_offset(pose[2], B, b, 1, &dr, &dc); x = dr; y = dc; }
+        else {                                                        /* more beams than the cache holds: evaluate directly */
+            static const double PI2 = 3.141592653589793;
+            int f = pose[2];
+            double theta = (f == NGW_NORTH) ? PI2 : (f == NGW_SOUTH) ? 0.0 : (f == NGW_WEST) ? 3 * PI2 / 2 : PI2 / 2;
+            double start = theta - PI2, step = ((theta + PI2) - start) / (double)B;
+            double angle = start + (double)b * step;
+            x = rint(cos(angle) * 100.0) / 100.0;
+            y = rint(sin(angle) * 100.0) / 100.0;
+        }
         for (int k = 1; k <= cfg->max_range; k++) {
             int rr = r + (int)rint((double)k * x), cc = c + (int)rint((double)k * y);   /* np.round(k * ratio) */
             if (rr < 0 || rr >= ms || cc < 0 || cc >= ms) break;      /* unreachable on a walled map */

@@ -20,7 +20,7 @@
  *                                     bow_v1_env.py:228-340, wrappers.py:74-85,
  *                                     observation_wrappers.py:32-80, novelty_wrappers.py step methods)
  *   ngw_observe                   <- LidarInFront.observation                  (observation_wrappers.py:70-80)
- *   ngw_load_state / ngw_state_ptrs <- the `env=` restore branch of reset / get_observation's live
+ *   ngw_load_state / ngw_state   <- the `env=` restore branch of reset / get_observation's live
  *                                     references                              (pogostick_v1_env.py:89-109,214-228)
  *   ngw_stats                     <- (absent in the reference; episode statistics for the NCCL reduce)
  *
@@ -243,8 +243,9 @@ int ngw_load_state(ngw_handle* h, const int8_t* map, const uint8_t* pose, const 
 int ngw_reset(ngw_handle* h, const uint8_t* mask, int32_t* obs, void* stream);
 
 /* One fused step of every env: action semantics + novelties + reward/done/step_cost + LidarInFront
- * observation (+ Philox auto-reset of done envs when auto_reset != 0, + truncation when
- * max_episode_steps > 0).  All pointers are DEVICE pointers; obs may be NULL when obs_dim == 0. */
+ * observation (+ Philox auto-reset of done envs when auto_reset != 0 — queued by the step kernel and regenerated by
+ * a second small kernel of the same call —, + truncation when max_episode_steps > 0).  All pointers are DEVICE
+ * pointers, obs 16-byte aligned; obs may be NULL when obs_dim == 0. */
 int ngw_step(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done,
              float* step_cost, uint8_t* result, int32_t auto_reset, int32_t max_episode_steps, void* stream);
 
@@ -252,9 +253,10 @@ int ngw_step(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward,
  * (NULL switches it off again; off by default — the hot path then writes nothing). */
 int ngw_set_message_buffer(ngw_handle* h, uint16_t* msg_dev);
 
-/* Same call with HOST buffers (the reference-facing path): copies actions in, steps, copies
- * obs/reward/done/step_cost/result out, chunk-pipelined over internal pinned staging; returns after
- * the outputs are valid on the host. */
+/* Same call with HOST buffers (the reference-facing path): copies actions in (H2D), steps, copies
+ * obs/reward/done/step_cost/result out (D2H) on the handle's own stream; returns after the outputs are valid
+ * on the host.  Pinned buffers make the copies true DMA; if step_cost == reward + n, done == step_cost + n and
+ * result == done + n (bytes: reward | step_cost | done | result contiguous) the four small outputs travel in one copy. */
 int ngw_step_host(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done,
                   float* step_cost, uint8_t* result, int32_t auto_reset, int32_t max_episode_steps);
 

@@ -2,18 +2,27 @@
 """bench.py — env-steps/sec of the fused step + LidarInFront hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-    torchrun --nproc-per-node N bench.py --gpus N ...          (one rank per GPU, weak scaling)
+    torchrun --nproc-per-node N bench.py --gpus N ...          (one rank per GPU)
 
 A "step" is ONE pass of the hot path over ONE batch of 65,536 envs of BASELINE config C2
 (NovelGridworld-Pogostick-v1 + LimitActions(10 actions) + LidarInFront(8 beams)), random actions.
 To keep L2 cold between timed iterations the run rotates over several independent batches whose combined
 working set (state + outputs) exceeds the 126 MB L2 ("inputs larger than L2").
 
-Prints ONE JSON line (rank 0).  `value` = device-timed throughput with inputs resident in HBM (CUDA-graph
-replay of the K launches, no host in the loop); `e2e` = the same metric through the host-buffer C-ABI call
-(ngw_step_host: pinned H2D of actions, kernel, D2H of obs/reward/done/step_cost/result every step);
-`roofline` = algorithmic bytes per launch / average launch duration vs the measured HBM copy peak;
-`cpu_baseline` = the C oracle port on the box's host cores.  `--impl reference` times that CPU port alone.
+Prints ONE JSON line (rank 0):
+  value       device-timed throughput, inputs resident in HBM: CUDA-graph replay of exactly K launches on one stream,
+              CUDA events on that stream; the K-step region is repeated until >= 50 ms were timed, median reported,
+              MAX over ranks.
+  e2e         the same metric through the host-buffer C-ABI call (ngw_step_host_begin/_end): pinned H2D of the actions,
+              one launch, D2H of obs/reward/done/step_cost/result every step, >= 200 steps; observation rows in the
+              compact NGW_OBS_U8 layout (uint8 lidar ranges + int32 inventory tail; `int32_rows` = the default layout);
+              `pcie` = a plain cudaMemcpyAsync probe of the same bytes on every rank at the same time.
+  roofline    algorithmic bytes per launch / average launch duration vs the measured HBM copy peak.
+  workloads   BASELINE configs C3, C4 (1,048,576 envs sharded over the ranks, env i -> novelty i mod 4) and C5
+              (524,288 envs per GPU, fused auto-reset), same timing method, per-GPU roofline fraction.
+  cpu_baseline  the C port of the reference path (oracle/ngw_oracle.c) on all host threads, and — when the unmodified
+              Python reference is installed under baseline/_ref — its single-process and process-pool throughput.
+`--impl reference` times the C port alone (rank 0 only), same config keys.
 """
 import argparse
 import json
@@ -35,6 +44,11 @@ C2_SET = ['Forward', 'Left', 'Right', 'Break', 'Place_tree_tap', 'Extract_rubber
 METRIC = "env-steps/sec, Pogostick-v1+LidarInFront, 1/2/4/8 B200 vs host-CPU reference"
 N_ACTION_SETS = 16
 GRAPH_STEPS = 1024
+L2_BYTES = 126e6
+VALUE_FLOOR_MS = 50.0            # the K-step region is repeated until this much was timed
+E2E_MIN_STEPS = 200
+REFERENCE_FLOOR_S = 2.0
+C4_TOTAL_ENVS = 1048576
 
 
 def build_c2_chain(num_envs=1, device=None):
@@ -46,8 +60,7 @@ def build_c2_chain(num_envs=1, device=None):
 
 def build_workload(name):
     """BASELINE.json configs -> (description, [compiled configs], envs per batch per GPU, cfg-id rule, step kwargs).
-    C2 is the headline (default); C3-C5 are extra measurements (`--workload`)."""
-    import numpy as np
+    C2 is the headline; C3-C5 are measured into `workloads` (or alone with `--workload`)."""
     import gym_novel_gridworlds_b200 as gym
     from gym_novel_gridworlds_b200.compiler import compile_chain
 
@@ -75,7 +88,7 @@ def build_workload(name):
         rule = 'interleaved' if name == 'C4' else 'blocked'
         return ("C4: Pogostick-v1 + LimitActions + LidarInFront(8), per-env novelty addchop / addjump / additem(medium) / "
                 "remapaction(hard), config ids %s, 1048576 envs/batch, one launch per step" % rule,
-                [compile_chain(c) for c in chains], 1048576, rule, {})
+                [compile_chain(c) for c in chains], C4_TOTAL_ENVS, rule, {})
     if name == 'C5':
         env = gym.inject_novelty(pogo(map_size=40), 'additem', 'hard', 'spring')
         return ("C5: Pogostick-v1 map_size 40 + additem(hard) + LidarInFront(8), 524288 envs/batch per GPU, fused "
@@ -84,11 +97,35 @@ def build_workload(name):
     raise ValueError(name)
 
 
-def algorithmic_bytes_per_env_step(cc):
-    """read ms^2 + 4 (pose) + 4 I (inventory) + 4 (action); write 4 (pose) + 4 I + 4 (L B + I_obs)
-    + 4 (reward) + 4 (step_cost) + 1 (done) + 1 (result); grid write-back counted as 0."""
+def algorithmic_bytes_per_env_step(cc, obs_format='i32'):
+    """SURVEY §8d with the dtypes actually written: read ms^2 + 4 (pose) + 4 I (inventory) + 4 (action); write 4 (pose)
+    + 4 I + observation row + 4 (reward) + 4 (step_cost) + 1 (done) + 1 (result); grid write-back counted as 0.
+    Observation row: int32 [L B + I_obs], or (NGW_OBS_U8) uint8 [L B] padded to 4 + int32 [I_obs]."""
     ms, n_items, d = cc.map_size, cc.n_items, cc.obs_dim
-    return (ms * ms + 4 + 4 * n_items + 4) + (4 + 4 * n_items + 4 * d + 4 + 4 + 1 + 1)
+    n_lidar = cc.c.n_lidar_items * cc.c.n_beams
+    row = 4 * d if obs_format == 'i32' else ((n_lidar + 3) // 4 * 4 + 4 * cc.c.n_inv_obs if d else 0)
+    return (ms * ms + 4 + 4 * n_items + 4) + (4 + 4 * n_items + row + 4 + 4 + 1 + 1)
+
+
+def workload_bytes_per_env_step(compiled, obs_format='i32'):
+    """mean over the configs of a batch (+1 byte config id per env when the batch is mixed)"""
+    return float(np.mean([algorithmic_bytes_per_env_step(cc, obs_format) for cc in compiled])) + (1 if len(compiled) > 1 else 0)
+
+
+def batches_to_exceed_l2(envs, bytes_step):
+    return max(2, int(np.ceil(1.6 * L2_BYTES / (envs * bytes_step))))
+
+
+def c2_config(n_gpus):
+    """The `config` object of the JSON line — static, so that both arms (--impl ours / reference) print the same one."""
+    n_b = batches_to_exceed_l2(ENVS_PER_BATCH, 446.0)
+    return {"workload": "C2: NovelGridworld-Pogostick-v1 + LimitActions(10) + LidarInFront(8), 65536 envs/batch, "
+                        "uniform random actions",
+            "envs_per_batch": ENVS_PER_BATCH, "batches_rotated": n_b,
+            "l2": "inputs larger than L2: %d rotating batches, %.0f MB combined working set vs 126 MB L2"
+                  % (n_b, n_b * ENVS_PER_BATCH * 446.0 / 1e6),
+            "obs_dtype": "int32 rows for value/roofline (446 B/env-step); e2e moves NGW_OBS_U8 rows",
+            "parallelism": "independent shards, one process per GPU x%d, no collective on the step path" % n_gpus}
 
 
 def measured_hbm_peak():
@@ -98,6 +135,16 @@ def measured_hbm_peak():
             return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     except Exception:
         return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def measured_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed multi-launch ncu capture."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')) as f:
+            rec = json.load(f).get(workload)
+        return (rec or {}).get('dram_bytes_per_launch'), (rec or {}).get('source')
+    except Exception:
+        return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -152,17 +199,50 @@ class ClockSampler(threading.Thread):
             except Exception:
                 return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         inside = [s for s in self.samples if t0 <= s[0] <= t1] or [s for s in self.samples if s[3] > 0] or self.samples
+        busy = [s for s in inside if s[3] > 0] or inside
         reasons = 0
         for s in inside:
             reasons |= s[2]
-        return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": self.max_mhz,
+        return {"sm_mhz": float(np.median([s[1] for s in busy])), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(n for b, n in names.items() if reasons & b), "samples": len(inside)}
 
 
-def cpu_port_run(cc, envs, steps, warmup, threads, time_budget_s=None):
-    """Times the C oracle port (oracle/ngw_oracle.c) on `envs` environments with all host threads.  Threads own
-    contiguous env slices and run them without a per-step barrier (envs are independent) — the fastest honest CPU
-    arrangement of the reference algorithm; every step still writes obs/reward/done/step_cost/result."""
+# ---------------------------------------------------------------------------------------------- host-side helpers
+def pin_to_gpu_numa(local_rank):
+    """One process per GPU: run this rank's host threads — and therefore first-touch its pinned buffers — on the CPUs
+    NVML reports as local to the GPU (its NUMA node), when the container's cpuset allows any of them."""
+    info = {"applied": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        allowed = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(allowed | {os.cpu_count() or 1}) // 64) + 1)
+        ideal = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        pci = pynvml.nvmlDeviceGetPciInfo(h).busId
+        pci = pci.decode() if isinstance(pci, bytes) else pci
+        node = None
+        try:
+            with open('/sys/bus/pci/devices/%s/numa_node' % pci.lower()[-12:]) as f:
+                node = int(f.read().strip())
+        except Exception:
+            pass
+        info.update({"gpu_numa_node": node, "gpu_local_cpus": len(ideal), "allowed_cpus": len(allowed)})
+        both = ideal & allowed
+        if both and both != allowed:
+            os.sched_setaffinity(0, both)
+            info["applied"] = True
+        info["cpus_used"] = len(os.sched_getaffinity(0))
+    except Exception as e:                                    # no NVML / no permission: stay where the launcher put us
+        info["error"] = str(e)[:80]
+    return info
+
+
+def cpu_port_regions(cc, envs, K, warmup, threads, floor_s, max_regions=400):
+    """Times the C oracle port (oracle/ngw_oracle.c): a region = K steps over `envs` environments with all host threads
+    (threads own contiguous env slices, no per-step barrier — the fastest honest CPU arrangement of the reference
+    algorithm; every step still writes obs/reward/done/step_cost/result).  Regions repeat until floor_s seconds were
+    timed; returns the list of region durations."""
     from oracle.oracle_lib import OracleBatch
     ob = OracleBatch([cc], envs)
     ob.reset_legacy(1)
@@ -170,21 +250,75 @@ def cpu_port_run(cc, envs, steps, warmup, threads, time_budget_s=None):
     acts = np.stack([rng.randint(0, cc.c.n_actions, size=envs).astype(np.int32) for _ in range(N_ACTION_SETS)])
     if warmup:
         ob.rollout(acts, warmup, n_threads=threads)
-    done, chunk = 0, 16
-    t0 = time.perf_counter()
-    while done < steps:
-        n = min(chunk, steps - done)
-        ob.rollout(acts, n, n_threads=threads)
-        done += n
-        if time_budget_s is not None and time.perf_counter() - t0 > time_budget_s:
-            break
-    return done, time.perf_counter() - t0
+    regions, total = [], 0.0
+    while (total < floor_s or len(regions) < 3) and len(regions) < max_regions:
+        t0 = time.perf_counter()
+        ob.rollout(acts, K, n_threads=threads)
+        dt = time.perf_counter() - t0
+        regions.append(dt)
+        total += dt
+    return regions
+
+
+def _python_reference_worker(args):
+    seconds, seed, ref_root, repo_root = args
+    import contextlib
+    import io
+    for p in (os.path.join(repo_root, 'tests'), repo_root):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import scenarios
+    desc = {'env': scenarios.POGO, 'map_size': 10, 'chain': [['limit', scenarios.C2_SET], ['lidar', 8]]}
+    with contextlib.redirect_stdout(io.StringIO()):
+        env = scenarios.build_chain(scenarios.reference_namespace(ref_root), desc)
+        n_act = len(env.limited_actions_id)
+        np.random.seed(seed)
+        env.reset()
+        rng = np.random.RandomState(seed)
+        steps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(100):                                  # tests/random_action.py:51-55 without render/prints
+                obs, r, done, info = env.step(int(rng.randint(n_act)))
+                if done:
+                    env.reset()
+            steps += 100
+        return steps / (time.perf_counter() - t0)
+
+
+def python_reference_baseline(seconds=4.0):
+    """The UNMODIFIED Python reference (installed under git-ignored baseline/_ref by __graft_entry__.build(), imported
+    through oracle/gymstub) on C2: one process, and a pool of os.cpu_count() worker processes with one env each
+    (SubprocVecEnv style: stable-baselines is not installed)."""
+    ref_root = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_root, 'gym_novel_gridworlds')):
+        return {"unavailable": "baseline/_ref/gym_novel_gridworlds is not installed (run __graft_entry__.build() where "
+                               "/root/reference exists)"}
+    import multiprocessing as mp
+    try:
+        ctx = mp.get_context('spawn')                             # never fork a process that holds a CUDA context
+        workers = os.cpu_count() or 1
+        with ctx.Pool(1) as pool:
+            single = pool.map(_python_reference_worker, [(seconds, 0, ref_root, ROOT)])[0]
+        with ctx.Pool(workers) as pool:
+            pooled = sum(pool.map(_python_reference_worker, [(seconds, i, ref_root, ROOT) for i in range(workers)]))
+        model = ''
+        try:
+            with open('/proc/cpuinfo') as f:
+                model = [ln.split(':', 1)[1].strip() for ln in f if ln.startswith('model name')][0]
+        except Exception:
+            pass
+        return {"single_process": single, "pool": pooled, "pool_workers": workers, "unit": "env-steps/s",
+                "seconds_each": seconds, "cpu": model, "python": sys.version.split()[0], "numpy": np.__version__,
+                "what": "gtatiya/gym-novel-gridworlds, unmodified, C2 chain, random actions, reset on done"}
+    except Exception as e:
+        return {"unavailable": "python reference failed: %s" % str(e)[:120]}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path.  The reference itself is Python and
-    cannot travel to the GPU box, so this is its C port (the oracle) with every host thread.  A step is one pass
-    over S envs of the same C2 workload, S bounded so that K steps end within a few minutes."""
+    """--impl reference: the reference's CPU implementation of the path = its C port (the oracle) with every host
+    thread; the unmodified Python reference is reported beside it by the main arm (cpu_baseline.python_reference).
+    A step is one pass over S envs of the same C2 workload, S bounded so that K steps end within a few minutes; the
+    K-step region is repeated for >= 2 s and the median region is reported."""
     if rank != 0:
         return
     from gym_novel_gridworlds_b200.compiler import compile_chain
@@ -194,28 +328,223 @@ def run_reference(args, rank, world):
     envs = ENVS_PER_BATCH
     while envs > 1024 and envs * K > 4e8:
         envs //= 2
-    steps, dt = cpu_port_run(cc, envs, K, args.warmup, threads)
-    value = steps * envs / dt
-    sample = ("%d steps x %d envs of C2 (bounded sample of the 65536-env batch), C port of the reference path "
-              "(oracle/ngw_oracle.c), %d threads, no per-step barrier" % (steps, envs, threads))
+    regions = cpu_port_regions(cc, envs, K, args.warmup, threads, REFERENCE_FLOOR_S)
+    dt = float(np.median(regions))
+    value = K * envs / dt
+    sample = ("%d regions of %d steps x %d envs of C2 (%.1f s timed, median region), C port of the reference path "
+              "(oracle/ngw_oracle.c), %d threads, no per-step barrier" % (len(regions), K, envs, sum(regions), threads))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "steps": K, "warmup": args.warmup, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "C2: NovelGridworld-Pogostick-v1 + LimitActions(10) + LidarInFront(8), "
-                               "uniform random actions", "envs_per_step": envs},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": c2_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample,
+                         "envs_per_step": envs},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------- GPU side
+class Workload(object):
+    """Rotating batches of one BASELINE workload on this rank, sharded by global env id."""
+
+    def __init__(self, name, rank, world, dev, obs_format='i32', n_batches=None):
+        import torch
+        from gym_novel_gridworlds_b200.runtime import BatchHandle
+        from gym_novel_gridworlds_b200.sharding import shard_range
+        self.name = name
+        self.desc, self.compiled, total, self.rule, self.kw = build_workload(name)
+        n_cfg = len(self.compiled)
+        self.bytes_step = workload_bytes_per_env_step(self.compiled, obs_format)
+        if name.startswith('C4'):                      # strong scaling: the 1M-env job is cut into contiguous id ranges
+            lo, hi = shard_range(total, rank, world)
+            self.scaling, self.total_envs = 'strong', total
+        else:                                          # weak scaling: every GPU runs the configured batch
+            lo, hi = rank * total, (rank + 1) * total
+            self.scaling, self.total_envs = 'weak', total * world
+        self.envs = hi - lo
+        self.n_batches = n_batches or batches_to_exceed_l2(self.envs, self.bytes_step)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + rank)
+        self.batches = []
+        for b in range(self.n_batches):
+            gid0 = b * self.total_envs + lo            # global env id of this shard's first env in rotation slot b
+            cfg_id = None
+            if n_cfg > 1:
+                gid = lo + np.arange(self.envs, dtype=np.int64)
+                cfg_id = (gid % n_cfg) if self.rule == 'interleaved' else np.minimum(gid * n_cfg // total, n_cfg - 1)
+            h = BatchHandle(self.compiled, self.envs, device=dev, seed=0, first_env_gid=gid0, cfg_id=cfg_id,
+                            obs_format=obs_format)
+            h.reset()
+            if self.kw.get('max_episode_steps', 0) > 0:        # stagger episode ages so truncation-resets spread evenly
+                h.ep_len.copy_(torch.randint(0, self.kw['max_episode_steps'], (self.envs,), generator=gen, device=dev,
+                                             dtype=torch.int32))
+            self.batches.append(h)
+        n_act = torch.tensor([cc.c.n_actions for cc in self.compiled], device=dev, dtype=torch.int64)
+        self.max_actions = int(n_act.max().item())
+        per_env_n = n_act[self.batches[0].cfg_id.long()]
+        self.n_sets = N_ACTION_SETS if self.envs <= 262144 else 4
+        self.act_sets = []
+        for _ in range(self.n_sets):
+            r = torch.randint(0, 1 << 30, (self.envs,), generator=gen, device=dev, dtype=torch.int64)
+            self.act_sets.append((r % per_env_n).to(torch.int32))
+        self.reset_error_flags = sum(int((h.error_flags != 0).sum().item()) for h in self.batches)
+
+    def step(self, i):
+        self.batches[i % self.n_batches].step(self.act_sets[i % self.n_sets], **self.kw)
+
+    def launches(self):
+        return sum(h.launch_count() for h in self.batches)
+
+    def close(self):
+        for h in self.batches:
+            h.close()
+        self.batches = []
+
+
+def time_regions(wl, K, dev, world, floor_ms=VALUE_FLOOR_MS, n_streams=1, max_regions=4000):
+    """Exactly K steps per region as CUDA-graph replays on one launching stream, CUDA events on that stream around every
+    region; barrier + synchronize on both sides of the whole measurement.  Returns (region durations in ms, wall
+    bracket, launches per step, steps per graph)."""
+    import torch
+    import torch.distributed as dist
+    n_b = wl.n_batches
+    g_steps = min(K, GRAPH_STEPS)
+    g_steps -= g_steps % n_b if g_steps >= n_b else 0                   # whole rotations per replay
+    g_steps = max(g_steps, 1)
+    stream = torch.cuda.Stream(dev)
+
+    def capture(n, first=0):
+        g = torch.cuda.CUDAGraph()
+        side = [torch.cuda.Stream(dev) for _ in range(n_streams)] if n_streams > 1 else []
+        with torch.cuda.stream(stream):
+            with torch.cuda.graph(g, stream=stream):
+                if not side:
+                    for i in range(n):
+                        wl.step(first + i)
+                else:                                   # independent batches on parallel branches of the graph
+                    for s_ in side:
+                        s_.wait_stream(stream)
+                    for i in range(n):
+                        with torch.cuda.stream(side[((first + i) % n_b) % n_streams]):
+                            wl.step(first + i)
+                    for s_ in side:
+                        stream.wait_stream(s_)
+        return g
+
+    before = wl.launches()
+    graph = capture(g_steps)
+    launches_per_step = (wl.launches() - before) / g_steps
+    replays, rem = K // g_steps, K % g_steps
+    graph_rem = capture(rem, replays * g_steps) if rem else None
+
+    def region():
+        for _ in range(replays):
+            graph.replay()
+        if graph_rem:
+            graph_rem.replay()
+
+    with torch.cuda.stream(stream):
+        region()                                                         # graph warm-up (uploads the exec graphs)
+    torch.cuda.synchronize(dev)
+    # how many regions make the floor: probe one
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        p0.record(stream)
+        region()
+        p1.record(stream)
+    torch.cuda.synchronize(dev)
+    n_regions = int(min(max_regions, max(3, np.ceil(floor_ms / max(p0.elapsed_time(p1), 1e-3)))))
+    if world > 1:
+        t = torch.tensor([n_regions], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_regions = int(t.item())
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_regions + 1)]
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        evs[0].record(stream)
+        for r in range(n_regions):
+            region()
+            evs[r + 1].record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t1 = time.perf_counter()
+    return [evs[r].elapsed_time(evs[r + 1]) for r in range(n_regions)], (t0, t1), launches_per_step, g_steps
+
+
+def pcie_probe(dev, d2h_bytes, h2d_bytes, world, reps=60):
+    """Plain cudaMemcpyAsync of one step's worth of bytes between pinned host memory and HBM, both directions at once
+    (two streams), on every rank at the same time: the PCIe roofline of the host-buffer path at this N."""
+    import torch
+    import torch.distributed as dist
+    dsrc = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    hdst = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    hsrc = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8).pin_memory()
+    ddst = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8, device=dev)
+    s_out, s_in = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    for _ in range(3):
+        with torch.cuda.stream(s_out):
+            hdst.copy_(dsrc, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(s_out):
+        e0.record(s_out)
+    for _ in range(reps):
+        with torch.cuda.stream(s_in):
+            ddst.copy_(hsrc, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hdst.copy_(dsrc, non_blocking=True)
+    with torch.cuda.stream(s_out):
+        e1.record(s_out)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1) / reps
+    return {"d2h_gbs": d2h_bytes / (ms * 1e-3) / 1e9, "ms_per_step_bytes": ms}
+
+
+def e2e_run(wl, n_steps, dev, world, host_acts):
+    """ngw_step_host_begin/_end over the rotating batches, depth-2 software pipeline: batch i+1 is enqueued (H2D,
+    launch, D2H on its handle's stream) before the host waits for batch i, so the PCIe link never idles; every step
+    copies its inputs in and its complete results out, and the results are read on the host."""
+    import torch
+    import torch.distributed as dist
+    n_b, n_sets, kw = wl.n_batches, wl.n_sets, wl.kw
+    for i in range(max(3, n_b)):                                        # every handle allocates its pinned buffers here
+        wl.batches[i % n_b].step_host(host_acts[i % n_sets], **kw)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    checksum = 0.0
+    t0 = time.perf_counter()
+    wl.batches[0].step_host_begin(host_acts[0], **kw)
+    for i in range(n_steps):
+        if i + 1 < n_steps:
+            wl.batches[(i + 1) % n_b].step_host_begin(host_acts[(i + 1) % n_sets], **kw)
+        obs, rew, dn, cost, res = wl.batches[i % n_b].step_host_end()
+        checksum += float(rew[0]) + float(obs[0, 0])                    # touch the results on the host
+    t_pipe = time.perf_counter() - t0
+    t0 = time.perf_counter()                                            # the plain blocking call, one batch at a time
+    n_block = max(20, n_steps // 4)
+    for i in range(n_block):
+        obs, rew, dn, cost, res = wl.batches[i % n_b].step_host(host_acts[i % n_sets], **kw)
+        checksum += float(rew[0]) + float(obs[0, 0])
+    t_block = (time.perf_counter() - t0) * n_steps / n_block           # scaled to n_steps
+    return t_pipe, t_block, checksum
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from gym_novel_gridworlds_b200.runtime import BatchHandle
 
+    numa = pin_to_gpu_numa(local_rank)                                  # before any pinned allocation
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
@@ -234,259 +563,196 @@ def run_ours(args, rank, world, local_rank):
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
 
-    desc, compiled, envs, cfg_rule, step_kw = build_workload(args.workload)
-    n_cfg = len(compiled)
-    # algorithmic bytes: mean over the configs of the batch (+1 byte config id per env when mixed)
-    bytes_step = float(np.mean([algorithmic_bytes_per_env_step(cc) for cc in compiled])) + (1 if n_cfg > 1 else 0)
-    per_batch_ws = envs * bytes_step
-    n_batches = max(2, int(np.ceil(1.6 * 126e6 / per_batch_ws)))       # combined working set >= 1.6x L2
-    batches, act_sets = [], []
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    for b in range(n_batches):
-        gid0 = (rank * n_batches + b) * envs
-        cfg_id = None
-        if n_cfg > 1:
-            idx = np.arange(envs, dtype=np.int64)
-            cfg_id = (idx % n_cfg) if cfg_rule == 'interleaved' else np.minimum(idx * n_cfg // envs, n_cfg - 1)
-        h = BatchHandle(compiled, envs, device=dev, seed=0, first_env_gid=gid0, cfg_id=cfg_id)
-        h.reset()
-        if step_kw.get('max_episode_steps', 0) > 0:                     # stagger episode ages so truncation-resets spread evenly
-            h.ep_len.copy_(torch.randint(0, step_kw['max_episode_steps'], (envs,), generator=gen, device=dev,
-                                         dtype=torch.int32))
-        batches.append(h)
-    n_act = torch.tensor([cc.c.n_actions for cc in compiled], device=dev, dtype=torch.int64)
-    per_env_n = n_act[batches[0].cfg_id.long()]
-    n_sets = N_ACTION_SETS if envs <= 262144 else 4
-    for _ in range(n_sets):
-        r = torch.randint(0, 1 << 30, (envs,), generator=gen, device=dev, dtype=torch.int64)
-        act_sets.append((r % per_env_n).to(torch.int32))
-    flags = sum(int((h.error_flags != 0).sum().item()) for h in batches)
+    def reduce_max(values):
+        t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)                     # device-timed durations: max over ranks
+        return [float(x) for x in t.cpu().numpy()]
 
-    def one_step(i):
-        batches[i % n_batches].step(act_sets[i % n_sets], **step_kw)
-
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    peak, peak_src = measured_hbm_peak()
     sampler = ClockSampler(local_rank)
     sampler.start()
 
-    # ---- warm-up (eager launches), then capture the launch sequence into CUDA graphs
-    W, K = max(args.warmup, 3), args.steps
-    for i in range(W):
-        one_step(i)
+    # ================= headline workload (C2 unless --workload says otherwise), int32 observation rows
+    wl = Workload(args.workload, rank, world, dev)
+    envs, n_batches, bytes_step = wl.envs, wl.n_batches, wl.bytes_step
+    for i in range(W):                                                  # warm-up: eager launches
+        wl.step(i)
     torch.cuda.synchronize(dev)
-    launches_before = sum(h.launch_count() for h in batches)
-    g_steps = min(K, GRAPH_STEPS)
-    g_steps -= g_steps % n_batches if g_steps >= n_batches else 0       # whole rotations per replay
-    g_steps = max(g_steps, 1)
-    stream = torch.cuda.Stream(dev)
-
-    def capture(n, n_streams=1):
-        g = torch.cuda.CUDAGraph()
-        side = [torch.cuda.Stream(dev) for _ in range(n_streams)] if n_streams > 1 else []
-        with torch.cuda.stream(stream):
-            with torch.cuda.graph(g, stream=stream):
-                if not side:
-                    for i in range(n):
-                        one_step(i)
-                else:                                   # independent batches on parallel branches of the graph
-                    for s_ in side:
-                        s_.wait_stream(stream)
-                    for i in range(n):
-                        with torch.cuda.stream(side[(i % n_batches) % n_streams]):
-                            one_step(i)
-                    for s_ in side:
-                        stream.wait_stream(s_)
-        return g
-
-    def timed(graph, replays, graph_rem):
-        with torch.cuda.stream(stream):
-            graph.replay()                                               # graph warm-up (uploads the exec graph)
-            if graph_rem:
-                graph_rem.replay()
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        with torch.cuda.stream(stream):
-            ev0.record(stream)
-            for _ in range(replays):
-                graph.replay()
-            if graph_rem:
-                graph_rem.replay()
-            ev1.record(stream)
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        return ev0.elapsed_time(ev1), t0, time.perf_counter()
-
-    graph = capture(g_steps)
-    launches_per_step = (sum(h.launch_count() for h in batches) - launches_before) / g_steps
-    replays, rem = K // g_steps, K % g_steps
-    graph_rem = capture(rem) if rem else None
-
-    # ---- timed region: exactly K steps, one stream, CUDA events on the launching stream, barrier + sync both sides;
-    #      repeated `--repeats` times, the median repeat is reported
-    runs = sorted((timed(graph, replays, graph_rem) for _ in range(max(1, args.repeats))), key=lambda r: r[0])
-    ms_total, t_wall0, t_wall1 = runs[len(runs) // 2]
-    ms_all = [r[0] for r in runs]
-
-    # ---- same K steps with independent batches overlapped on 3 parallel graph branches (extra figure)
-    n_ov = min(3, n_batches)
-    graph_ov = capture(g_steps, n_ov)
-    graph_ov_rem = capture(rem, n_ov) if rem else None
-    ms_overlap = sorted(timed(graph_ov, replays, graph_ov_rem)[0] for _ in range(max(1, args.repeats)))[max(1, args.repeats) // 2]
+    regions, (t_wall0, t_wall1), launches_per_step, g_steps = time_regions(wl, K, dev, world)
+    ms_region = float(np.median(regions))
+    ov_regions = time_regions(wl, K, dev, world, n_streams=min(3, n_batches))[0]
+    ms_overlap = float(np.median(ov_regions))
 
     # ---- K-step rollout kernel: 64 steps per launch, uniform random policy drawn on the device
     roll_T = 64
-    for h in batches:
-        h.rollout(roll_T, None, policy_seed=1, **step_kw)
+    for h in wl.batches:
+        h.rollout(roll_T, None, policy_seed=1, **wl.kw)
     torch.cuda.synchronize(dev)
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_roll = max(2 * n_batches, 8)
     r0.record()
     for i in range(n_roll):
-        batches[i % n_batches].rollout(roll_T, None, policy_seed=2 + i, **step_kw)
+        wl.batches[i % n_batches].rollout(roll_T, None, policy_seed=2 + i, **wl.kw)
     r1.record()
     torch.cuda.synchronize(dev)
     roll_ms = r0.elapsed_time(r1)
-
     # ---- closed-loop rollout: integer linear policy evaluated on the device from each step's observation
-    roll_policy_ms = None
-    if batches[0].obs_dim > 0 and int(n_act.max().item()) <= 16:
-        A = int(n_act.max().item())
+    roll_policy_ms = 0.0
+    if wl.batches[0].obs_dim > 0 and wl.max_actions <= 16:
         gw = torch.Generator(device=dev)
         gw.manual_seed(7)
-        w_pol = torch.randint(-9, 10, (batches[0].obs_dim, A), generator=gw, device=dev, dtype=torch.int32)
-        b_pol = torch.randint(-30, 31, (A,), generator=gw, device=dev, dtype=torch.int32)
-        for h in batches:
-            h.rollout(roll_T, policy=(w_pol, b_pol), **step_kw)
+        w_pol = torch.randint(-9, 10, (wl.batches[0].obs_dim, wl.max_actions), generator=gw, device=dev, dtype=torch.int32)
+        b_pol = torch.randint(-30, 31, (wl.max_actions,), generator=gw, device=dev, dtype=torch.int32)
+        for h in wl.batches:
+            h.rollout(roll_T, policy=(w_pol, b_pol), **wl.kw)
         torch.cuda.synchronize(dev)
         q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         q0.record()
         for i in range(n_roll):
-            batches[i % n_batches].rollout(roll_T, policy=(w_pol, b_pol), **step_kw)
+            wl.batches[i % n_batches].rollout(roll_T, policy=(w_pol, b_pol), **wl.kw)
         q1.record()
         torch.cuda.synchronize(dev)
         roll_policy_ms = q0.elapsed_time(q1)
-
     # ---- eager (one python call per launch) figure, for the launch-bound picture
-    n_eager = min(K, 2000)
+    n_eager = min(max(K, 200), 2000)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(n_eager):
-        one_step(i)
+        wl.step(i)
     e1.record()
     torch.cuda.synchronize(dev)
     eager_ms = e0.elapsed_time(e1) / n_eager
+    stats = torch.zeros(8, dtype=torch.float64, device=dev)
+    for h in wl.batches:
+        stats += h.stats()
+    host_acts = [a.cpu().numpy() for a in wl.act_sets]
+    d_obs = wl.batches[0].obs_dim
+    headline_flags = wl.reset_error_flags
+    headline_compiled = wl.compiled
 
-    # ---- end-to-end through the host-buffer C-ABI call (ngw_step_host), pinned buffers, every step H2D + D2H
-    n_e2e = min(K, 200 if envs <= 65536 else 40)
-    host_acts = [a.cpu().numpy() for a in act_sets]
-    for i in range(max(3, n_batches)):                                  # every handle allocates its pinned buffers here
-        batches[i % n_batches].step_host(host_acts[i % n_sets], **step_kw)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    checksum = 0.0
-    # depth-2 software pipeline over the rotating batches: batch i+1 is enqueued (H2D, launch, D2H on its own stream)
-    # before the host waits for batch i, so the PCIe link never idles; every step still copies its inputs in and its
-    # complete results out, and the results are read on the host
-    batches[0].step_host_begin(host_acts[0], **step_kw)
-    for i in range(n_e2e):
-        if i + 1 < n_e2e:
-            batches[(i + 1) % n_batches].step_host_begin(host_acts[(i + 1) % n_sets], **step_kw)
-        obs, rew, dn, cost, res = batches[i % n_batches].step_host_end()
-        checksum += float(rew[0]) + float(obs[0, 0])                    # touch the results on the host
-    t_e2e = time.perf_counter() - t0
-    # the plain blocking call, one batch at a time
-    t0 = time.perf_counter()
-    for i in range(n_e2e):
-        obs, rew, dn, cost, res = batches[i % n_batches].step_host(host_acts[i % n_sets], **step_kw)
-        checksum += float(rew[0]) + float(obs[0, 0])
-    t_e2e_blocking = time.perf_counter() - t0
+    # ================= end to end through the host-buffer C-ABI call, compact rows (and the int32 rows for comparison)
+    n_e2e = max(K, E2E_MIN_STEPS) if envs <= 65536 else max(min(K, 40), 20)
+    n_e2e_i32 = max(n_e2e // 2, 20)
+    t_e2e_i32, t_block_i32, _ = e2e_run(wl, n_e2e_i32, dev, world, host_acts)
+    wl.close()
+    wl8 = Workload(args.workload, rank, world, dev, obs_format='u8', n_batches=n_batches)
+    row8 = wl8.batches[0].obs_row_bytes if d_obs else 0
+    t_e2e, t_block, _ = e2e_run(wl8, n_e2e, dev, world, host_acts)
+    d2h_u8, d2h_i32, h2d = (row8 + 10) * envs, (4 * d_obs + 10) * envs, 4 * envs
+    probe = pcie_probe(dev, d2h_u8, h2d, world)
+    wl8.close()
+
+    # ================= the other BASELINE workloads at this N (skipped when a single workload was asked for)
+    extra, extra_times = {}, []
+    names = [] if (args.workload != 'C2' or args.no_workloads) else ['C3', 'C4', 'C5']
+    K_x = min(K, 256)
+    for name in names:
+        w = Workload(name, rank, world, dev)
+        for i in range(max(3, w.n_batches)):
+            w.step(i)
+        torch.cuda.synchronize(dev)
+        reg, _, lps, _ = time_regions(w, K_x, dev, world)
+        extra[name] = {"workload": w.desc, "scaling": w.scaling, "envs_per_gpu": w.envs, "total_envs": w.total_envs,
+                       "batches_rotated": w.n_batches, "steps": K_x, "regions": len(reg),
+                       "launches_per_step": lps, "algorithmic_bytes_per_env_step": w.bytes_step,
+                       "reset_error_flags": w.reset_error_flags}
+        extra_times.append(float(np.median(reg)))
+        st = torch.zeros(8, dtype=torch.float64, device=dev)
+        for h in w.batches:
+            st += h.stats()
+        if world > 1:
+            dist.all_reduce(st, op=dist.ReduceOp.SUM)
+        extra[name]["episode_stats"] = {"steps": float(st[0].item()), "episodes": float(st[1].item()),
+                                        "resets": float(st[5].item())}
+        w.close()
     t_timed_end = time.perf_counter()
 
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     clocks = sampler.summary(t_wall0, t_timed_end)
 
-    stats = torch.zeros(8, dtype=torch.float64, device=dev)
-    for h in batches:
-        stats += h.stats()
-    times = torch.tensor([ms_total, t_e2e * 1e3, ms_overlap], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)                     # max over ranks
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)                     # episode statistics over NCCL
-    ms_total, e2e_ms_total, ms_overlap = [float(x) for x in times.cpu().numpy()]
+    red = reduce_max([ms_region, ms_overlap, t_e2e, t_block, t_e2e_i32, t_block_i32, roll_ms, roll_policy_ms, eager_ms,
+                      probe["ms_per_step_bytes"]] + extra_times)
+    (ms_region, ms_overlap, t_e2e, t_block, t_e2e_i32, t_block_i32, roll_ms, roll_policy_ms, eager_ms, probe_ms) = red[:10]
+    extra_times = red[10:]
 
     if rank == 0:
-        ms_per_step = ms_total / K
-        value = world * envs * K / (ms_total * 1e-3)
-        peak, peak_src = measured_hbm_peak()
+        ms_per_step = ms_region / K
+        total_envs = wl.total_envs if wl.scaling == 'strong' else world * envs
+        value = total_envs * K / (ms_region * 1e-3)
         achieved = envs * bytes_step / (ms_per_step * 1e-3) / 1e9
         ov_achieved = envs * bytes_step / (ms_overlap / K * 1e-3) / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')) as f:
-                traffic = json.load(f).get(args.workload, {}).get('dram_bytes_per_launch')
-        except Exception:
-            pass
-        d_obs = batches[0].obs_dim
+        traffic, traffic_src = measured_traffic(args.workload)
+        e2e_value = total_envs * n_e2e / t_e2e
+        pcie_gbs = d2h_u8 / (probe_ms * 1e-3) / 1e9
+        pcie_limit = world * envs / (probe_ms * 1e-3)
+        for name, ms in zip(names, extra_times):
+            x = extra[name]
+            x["us_per_step"] = ms / K_x * 1e3
+            x["value"] = x["total_envs"] * K_x / (ms * 1e-3)
+            x["unit"] = "env-steps/s"
+            x["achieved_gbs_per_gpu"] = x["envs_per_gpu"] * x["algorithmic_bytes_per_env_step"] / (ms / K_x * 1e-3) / 1e9
+            x["frac_of_hbm_peak"] = x["achieved_gbs_per_gpu"] / peak
+        cfg = c2_config(world) if args.workload == 'C2' else {"workload": wl.desc, "envs_per_batch": envs,
+                                                                "batches_rotated": n_batches}
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32", "data": "synthetic",
-            "config": {"workload": desc, "envs_per_batch": envs, "batches_rotated": n_batches,
-                       "l2": "inputs larger than L2: %d rotating batches, %.0f MB combined working set vs 126 MB L2"
-                             % (n_batches, n_batches * per_batch_ws / 1e6),
-                       "launch": "one stream, CUDA-graph replay of %d-step graphs (one kernel launch per step); eager "
-                                 "python loop = %.2f us/step" % (g_steps, eager_ms * 1e3),
-                       "per_gpu_envs": n_batches * envs, "parallelism": "independent shards x%d" % world,
-                       "reset_error_flags": flags},
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic", "config": cfg,
             "clocks": clocks,
-            "e2e": {"value": world * envs * n_e2e / (e2e_ms_total * 1e-3), "unit": "env-steps/s",
-                    "h2d_bytes_per_step": 4 * envs,
-                    "d2h_bytes_per_step": (4 * d_obs + 4 + 4 + 1 + 1) * envs,
-                    "steps": n_e2e,
-                    "api": "ngw_step_host_begin/_end, pinned host buffers: H2D actions, one launch, D2H obs/reward/done/"
-                           "step_cost/result per step; batch i+1 enqueued before waiting for batch i",
-                    "blocking_value": world * envs * n_e2e / t_e2e_blocking},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_u8,
+                    "steps": n_e2e, "obs_format": "NGW_OBS_U8 (uint8 lidar ranges + int32 inventory tail, %d B/env)" % row8,
+                    "api": "ngw_step_host_begin/_end, pinned host buffers: H2D actions, one launch, D2H obs/reward/"
+                           "step_cost/done/result per step; batch i+1 enqueued before waiting for batch i",
+                    "blocking_value": total_envs * n_e2e / t_block,
+                    "pcie": {"d2h_gbs_per_gpu": pcie_gbs, "limit_env_steps_per_s": pcie_limit,
+                             "frac": e2e_value / pcie_limit,
+                             "note": "plain cudaMemcpyAsync of the same bytes per step, both directions, all ranks at once"},
+                    "int32_rows": {"value": total_envs * n_e2e_i32 / t_e2e_i32, "d2h_bytes_per_step": d2h_i32,
+                                   "blocking_value": total_envs * n_e2e_i32 / t_block_i32, "steps": n_e2e_i32},
+                    "numa": numa},
             "gpu_launches": int(round(launches_per_step * K)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "ngw::step_kernel", "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": bytes_step,
-                         "algorithmic_bytes_per_launch": envs * bytes_step,
-                         "avg_launch_us": ms_per_step * 1e3},
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "ngw::step_kernel",
+                         "peak_source": peak_src, "algorithmic_bytes_per_env_step": bytes_step,
+                         "algorithmic_bytes_per_launch": envs * bytes_step, "avg_launch_us": ms_per_step * 1e3},
+            "timing": {"regions": len(regions),
+                       "region_ms_min_med_max": [min(regions), float(np.median(regions)), max(regions)],
+                       "timed_ms_total": float(sum(regions)), "graph_steps": g_steps,
+                       "launch": "one stream, CUDA-graph replay (one kernel launch per step)",
+                       "reset_error_flags": headline_flags, "per_gpu_envs_resident": n_batches * envs},
             "overlapped": {"note": "same K steps, independent batches on %d parallel graph branches (launches overlap)"
-                                   % n_ov, "value": world * envs * K / (ms_overlap * 1e-3), "unit": "env-steps/s",
+                                   % min(3, n_batches), "value": total_envs * K / (ms_overlap * 1e-3), "unit": "env-steps/s",
                            "us_per_step": ms_overlap / K * 1e3, "achieved_gbs": ov_achieved,
                            "frac_of_hbm_peak": ov_achieved / peak},
             "rollout": {"note": "ngw_rollout: %d steps per launch, on-device uniform random policy, tile resident in "
                                 "shared memory; outputs are per-env sums + final observation" % roll_T,
-                        "value": world * envs * roll_T * n_roll / (roll_ms * 1e-3), "unit": "env-steps/s"},
-            "rollout_policy": None if roll_policy_ms is None else {
+                        "value": total_envs * roll_T * n_roll / (roll_ms * 1e-3), "unit": "env-steps/s"},
+            "rollout_policy": None if not roll_policy_ms else {
                 "note": "ngw_rollout_policy: %d steps per launch, action = argmax(b + obs @ W) on the device from each "
                         "step's lidar observation" % roll_T,
-                "value": world * envs * roll_T * n_roll / (roll_policy_ms * 1e-3), "unit": "env-steps/s"},
-            "eager": {"value": envs / (eager_ms * 1e-3), "unit": "env-steps/s", "us_per_step": eager_ms * 1e3},
+                "value": total_envs * roll_T * n_roll / (roll_policy_ms * 1e-3), "unit": "env-steps/s"},
+            "eager": {"value": total_envs / (eager_ms * 1e-3), "unit": "env-steps/s", "us_per_step": eager_ms * 1e3},
+            "workloads": extra,
             "episode_stats": dict(zip(('steps', 'episodes', 'successes', 'reward_sum', 'cost_sum', 'resets',
                                        'invalid'), [float(x) for x in stats.cpu().numpy()[:7]])),
             "wall_ms_timed_region": (t_wall1 - t_wall0) * 1e3,
-            "repeats": {"n": len(ms_all), "ms_per_step_min_med_max": [ms_all[0] / K, ms_all[len(ms_all) // 2] / K,
-                                                                       ms_all[-1] / K]},
         }
         if world == 1 and not args.no_cpu_baseline and args.workload == 'C2':
             threads = os.cpu_count() or 1
-            steps_cpu, dt = cpu_port_run(compiled[0], ENVS_PER_BATCH, 10 ** 9, 16, threads, time_budget_s=3.0)
+            reg = cpu_port_regions(headline_compiled[0], ENVS_PER_BATCH, 64, 16, threads, 3.0)
+            dt = float(np.median(reg))
             line["cpu_baseline"] = {
-                "value": steps_cpu * ENVS_PER_BATCH / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                "sample": "%d steps x %d envs (%.1f s wall, ~%.0f s of CPU work), C port of the reference path "
-                          "(oracle/ngw_oracle.c), %d threads, no per-step barrier"
-                          % (steps_cpu, ENVS_PER_BATCH, dt, dt * threads, threads)}
+                "value": 64 * ENVS_PER_BATCH / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                "sample": "%d regions of 64 steps x %d envs (%.1f s wall, ~%.0f s of CPU work, median region), C port of "
+                          "the reference path (oracle/ngw_oracle.c), %d threads, no per-step barrier"
+                          % (len(reg), ENVS_PER_BATCH, sum(reg), sum(reg) * threads, threads),
+                "python_reference": python_reference_baseline()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -495,11 +761,11 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=32768)
+    ap.add_argument('--steps', type=int, default=4096)
     ap.add_argument('--warmup', type=int, default=64)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--repeats', type=int, default=3, help='timed region is run this many times; the median is reported')
+    ap.add_argument('--no-workloads', action='store_true', help='skip the C3/C4/C5 measurements of the default line')
     ap.add_argument('--workload', default='C2', choices=['C2', 'C3', 'C4', 'C4-blocked', 'C5'])
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

@@ -8,7 +8,8 @@ from . import opcodes as oc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libngw_b200.so')
-ABI_VERSION = 8
+ABI_VERSION = 9
+OBS_I32, OBS_U8 = 0, 1
 
 
 class ActionEntryC(C.Structure):
@@ -62,7 +63,8 @@ class StateViewC(C.Structure):
                 ('episode', C.c_void_p), ('ep_len', C.c_void_p), ('error_flags', C.c_void_p),
                 ('inv_stride', C.c_int32), ('obs_dim', C.c_int32),
                 ('n_envs', C.c_int64), ('n_envs_padded', C.c_int64),
-                ('map_size', C.c_int32), ('n_configs', C.c_int32)]
+                ('map_size', C.c_int32), ('n_configs', C.c_int32),
+                ('obs_format', C.c_int32), ('obs_row_bytes', C.c_int32)]
 
 
 # name -> (restype, argtypes); the same list is checked against include/ngw.h by the CPU test-suite
@@ -73,8 +75,11 @@ EXPORTS = {
     'ngw_last_error': (C.c_char_p, []),
     'ngw_abi_version': (C.c_int, []),
     'ngw_state': (C.c_int, [C.c_void_p, C.POINTER(StateViewC)]),
+    'ngw_set_obs_format': (C.c_int, [C.c_void_p, C.c_int32]),
+    'ngw_lidar_path': (C.c_int, [C.POINTER(ConfigC), C.c_int32]),
     'ngw_set_env_configs': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'ngw_load_state': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    'ngw_export_state': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     'ngw_reset': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'ngw_step': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_int32, C.c_int32, C.c_void_p]),

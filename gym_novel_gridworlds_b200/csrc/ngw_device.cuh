@@ -329,16 +329,22 @@ __device__ __forceinline__ void step_env(EnvRow& e, const ngw_config& cfg, const
 }
 
 // ------------------------------------------------------------------ LidarInFront (observation_wrappers.py:32-80)
-// Device-side companion of an ngw_config, built by ngw_create from the host beam LUT.
-//   fast path (8 beams, the reference default): the LUT factorises into a unit step per (facing, beam) times a
-//   displacement per (beam parity, sample) — axis beams advance k cells, diagonal beams round(0.71 k) cells — so
-//   the 8 beams are cast together, sample by sample, with 8 independent shared-memory reads in flight.
-//   generic path (any other beam count): int16 linear-offset LUT [4][B][K] in global memory.
+// Device-side companion of an ngw_config, built by ngw_create from the host beam LUT.  Three paths, chosen per config:
+//   lines   (8 beams whose LUT is the canonical compass geometry — the reference default): the beams lie on the four
+//           lines through the agent (row, column, two diagonals).  Every cell of a line is read once into an occupancy
+//           bit mask (fixed trip count = map size, no data-dependent loop), the nearest set bit on either side of the
+//           agent is the cell a beam lands on (ffs / clz), and the reported range is the number of cells for axis beams
+//           or firstk[cells] for diagonal beams (the first sample k with round(0.71 k) == cells, from the host LUT).
+//   fast    (8 beams, factorised unit step x displacement tables, any rotation pattern): pointer-walking beams.
+//   generic (any other beam count): int16 linear-offset LUT [4][B][K] in global memory.
 #define NGW_MAX_RANGE 96
 struct LidarDev {
     int32_t fast;                       // 1 => unit/disp tables are valid
+    int32_t lines;                      // 1 => canonical geometry: firstk/rot are valid (line-gather path)
     int16_t unit[4][8];                 // linear offset d_row * ms + d_col of one step of beam b when facing f
     uint8_t disp[2][NGW_MAX_RANGE];     // cells travelled at sample k (0-based) by even / odd beams
+    uint8_t firstk[NGW_MAX_MAP_SIZE];   // firstk[d-1]: 1-based sample at which a diagonal beam first reaches its d-th cell, 0 = never
+    alignas(4) uint8_t rot[4];          // beam b of an agent facing f looks along compass direction (b + rot[f]) & 7
     const int16_t* lut;                 // generic path: device int16 [4][B][K]
 };
 
@@ -347,11 +353,130 @@ struct DevConfig {
     LidarDev lidar;
 };
 
+// One env's observation row: lidar part as int32 (the reference's vector) or as uint8 (NGW_OBS_U8: ranges are
+// <= max_range <= 90, so the narrowing is exact), followed by the int32 inventory tail at byte offset tail_off.
+struct ObsRow {
+    unsigned char* p;
+    int u8;
+    __device__ __forceinline__ void put(int idx, int v) const {
+        if (u8) p[idx] = (unsigned char)v;
+        else reinterpret_cast<int32_t*>(p)[idx] = v;
+    }
+    __device__ __forceinline__ int32_t* tail(int n_lidar) const {
+        return reinterpret_cast<int32_t*>(p + (u8 ? ((n_lidar + 3) & ~3) : 4 * n_lidar));
+    }
+};
+
+// Small per-config lookup tables the lidar reads with per-lane indices (shared memory in the step kernel, global
+// memory in the cold kernels): item id -> lidar slot, diagonal cells -> first sample.
+struct LidarLuts {
+    const int8_t* slot;                 // [NGW_MAX_ITEMS]
+    const uint8_t* firstk;              // [NGW_MAX_MAP_SIZE]
+};
+
+template <typename MaskT> __device__ __forceinline__ int mask_ffs(MaskT x);
+template <> __device__ __forceinline__ int mask_ffs<uint32_t>(uint32_t x) { return __ffs((int)x); }
+template <> __device__ __forceinline__ int mask_ffs<uint64_t>(uint64_t x) { return __ffsll((long long)x); }
+template <typename MaskT> __device__ __forceinline__ int mask_msb(MaskT x);      // index of the highest set bit, x != 0
+template <> __device__ __forceinline__ int mask_msb<uint32_t>(uint32_t x) { return 31 - __clz((int)x); }
+template <> __device__ __forceinline__ int mask_msb<uint64_t>(uint64_t x) { return 63 - __clzll((long long)x); }
+
+// occupancy of the four lines through (r, c); bit i = cell of the line in grid row i (row line: grid column i).
+// kSafe clamps the diagonal addresses into the row (cold kernels on global memory); the step kernel's shared-memory
+// rows have >= ms bytes of readable padding on both sides, and out-of-grid bits are masked off either way.
+template <typename MaskT, int MS, bool kSafe>
+__device__ __forceinline__ void gather_lines(const int8_t* m, int ms_rt, int r, int c, int sel, MaskT& row, MaskT& col,
+                                             MaskT& dg, MaskT& an) {
+    const int ms = MS > 0 ? MS : ms_rt;
+    const int8_t* prow = m + r * ms;
+    const int8_t* pcol = m + c;
+    const int8_t* pdg = m + (c - r);                                  // row i: column c - r + i
+    const int8_t* pan = m + (c + r);                                  // row i: column c + r - i
+    row = 0; col = 0; dg = 0; an = 0;
+    const bool s0 = sel & 1, s1 = sel & 2, s2 = sel & 4, s3 = sel & 8;
+#pragma unroll
+    for (int i = 0; i < ms; i++) {
+        const MaskT bit = (MaskT)1 << i;
+        if (s0 && prow[i] != 0) row |= bit;
+        if (s1 && pcol[i * ms] != 0) col |= bit;
+        if (kSafe) {
+            int cd = c - r + i, ca = c + r - i;
+            cd = cd < 0 ? 0 : (cd > ms - 1 ? ms - 1 : cd);
+            ca = ca < 0 ? 0 : (ca > ms - 1 ? ms - 1 : ca);
+            if (s2 && m[i * ms + cd] != 0) dg |= bit;
+            if (s3 && m[i * ms + ca] != 0) an |= bit;
+        } else {
+            if (s2 && pdg[i * (ms + 1)] != 0) dg |= bit;
+            if (s3 && pan[i * (ms - 1)] != 0) an |= bit;
+        }
+    }
+    // rows whose diagonal cell lies outside the grid: r - c <= i <= r - c + ms - 1, resp. c + r - ms + 1 <= i <= c + r
+    const MaskT full = (MaskT)(~(MaskT)0) >> (8 * (int)sizeof(MaskT) - ms);
+    const int dlo = r - c, alo = c + r - (ms - 1);
+    dg &= dlo >= 0 ? (full << dlo) : (full >> (-dlo));
+    an &= alo >= 0 ? (full << alo) : (full >> (-alo));
+}
+
+// the two beams of one line: `p` = the agent's bit index on the line, `stride` = linear offset of one cell towards
+// higher bit indices, a_pos / a_neg = compass directions of the two beams
+template <typename MaskT>
+__device__ __forceinline__ void line_beams(MaskT occ, int p, int stride, const int8_t* here, bool diagonal, int a_pos,
+                                           int a_neg, int K, int L, int rot, const LidarLuts& luts, const ObsRow& obs) {
+    const MaskT hi = (occ >> p) >> 1;                                 // bit 0 = the cell next to the agent
+    const MaskT lo = occ & (((MaskT)1 << p) - 1);
+    const int n_pos = mask_ffs<MaskT>(hi);                            // cells to the first non-air cell, 0 = none
+    const int n_neg = lo != 0 ? p - mask_msb<MaskT>(lo) : 0;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int n = side ? n_neg : n_pos;
+        const int a = side ? a_neg : a_pos;
+        if (n == 0) continue;
+        const int k = diagonal ? (int)luts.firstk[n - 1] : (n <= K ? n : 0);   // obsw:52-58: sample index of that cell
+        if (k == 0) continue;                                         // beyond max_beam_range
+        const int id = here[side ? -n * stride : n * stride];
+        const int slot = luts.slot[id];                               // -1: occludes but is not a lidar item (Q2)
+        if (slot >= 0) obs.put(((a - rot) & 7) * L + slot, k);
+    }
+}
+
+template <typename MaskT, int MS, bool kSafe>
+__device__ __forceinline__ void lidar_lines_t(const EnvRow& e, const ngw_config& cfg, const LidarDev& t,
+                                              const LidarLuts& luts, const ObsRow& obs, int sel) {
+    MaskT row, col, dg, an;
+    gather_lines<MaskT, MS, kSafe>(e.m, e.ms, e.r, e.c, sel, row, col, dg, an);
+    const int ms = MS > 0 ? MS : e.ms;
+    const int K = cfg.max_range, L = cfg.n_lidar_items;
+    const int rot = (int)((*reinterpret_cast<const uint32_t*>(t.rot) >> (8 * e.facing)) & 7u);   // one uniform table read
+    const int8_t* here = e.m + e.r * ms + e.c;
+    // compass directions (d_row, d_col): 0 (+1,0)  1 (+1,+1)  2 (0,+1)  3 (-1,+1)  4 (-1,0)  5 (-1,-1)  6 (0,-1)  7 (+1,-1)
+    if (sel & 1) line_beams<MaskT>(row, e.c, 1, here, false, 2, 6, K, L, rot, luts, obs);
+    if (sel & 2) line_beams<MaskT>(col, e.r, ms, here, false, 0, 4, K, L, rot, luts, obs);
+    if (sel & 4) line_beams<MaskT>(dg, e.r, ms + 1, here, true, 1, 5, K, L, rot, luts, obs);
+    if (sel & 8) line_beams<MaskT>(an, e.r, ms - 1, here, true, 7, 3, K, L, rot, luts, obs);
+}
+
+template <bool kSafe>
+__device__ __forceinline__ void lidar_lines(const EnvRow& e, const ngw_config& cfg, const LidarDev& t,
+                                            const LidarLuts& luts, const ObsRow& obs, int sel) {
+    if (e.ms == 10) lidar_lines_t<uint32_t, 10, kSafe>(e, cfg, t, luts, obs, sel);      // the reference's default grid
+    else if (e.ms <= 32) lidar_lines_t<uint32_t, 0, kSafe>(e, cfg, t, luts, obs, sel);
+    else if (e.ms == 40) lidar_lines_t<uint64_t, 40, kSafe>(e, cfg, t, luts, obs, sel);
+    else lidar_lines_t<uint64_t, 0, kSafe>(e, cfg, t, luts, obs, sel);
+}
+
+// which of the four lines warp g of G handles (bit 0 row, 1 column, 2 diagonal, 3 anti-diagonal)
+__device__ __forceinline__ int lidar_line_share(int g, int G) {
+    if (G == 1) return 0xF;
+    if (G == 2) return g == 0 ? 0x3 : 0xC;
+    if (G == 3) return g == 0 ? 0x3 : (g == 1 ? 0x4 : 0x8);
+    return g < 4 ? (1 << g) : 0;
+}
+
 // obs row must be zero-filled for the lidar part by the caller; `zero` points at a byte that always reads 0 and lives in
 // the same address space as the grid row.  A tile can be shared by G warps: warp `g` of `G` casts beams
 // [g*NB, (g+1)*NB) with NB = 8/G (fast path) or beams g, g+G, ... (generic path).
 template <int NB>
-__device__ __forceinline__ void lidar_fast(const EnvRow& e, const ngw_config& cfg, const LidarDev& lidar, int32_t* obs,
+__device__ __forceinline__ void lidar_fast(const EnvRow& e, const ngw_config& cfg, const LidarDev& lidar, const ObsRow& obs,
                                            const int8_t* zero, int b0) {
     // Each beam keeps a running cell pointer; axis beams advance one unit step per sample, diagonal beams advance
     // when round(0.71 k) grows (disp[1][k] - disp[1][k-1] is 0 or 1).  A beam that lands parks on `zero`, a cell
@@ -389,18 +514,25 @@ __device__ __forceinline__ void lidar_fast(const EnvRow& e, const ngw_config& cf
     for (int j = 0; j < NB; j++) {
         if (hit[j]) {
             int slot = cfg.lidar_slot[hit[j] & 0xFF];                 // -1: occludes but is not a lidar item (Q2)
-            if (slot >= 0) obs[(b0 + j) * L + slot] = (int)(hit[j] >> 8);
+            if (slot >= 0) obs.put((b0 + j) * L + slot, (int)(hit[j] >> 8));
         }
     }
 }
 
 // `tables`: the beam tables to walk with — the env's own config, or (mixed batches whose configs all share one lidar
 // geometry) config 0's, so that the table reads stay warp-uniform even when the lanes of a warp differ in config.
-__device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& dc, const LidarDev& tables, int32_t* obs,
-                                              const int8_t* zero, int g, int G, bool with_tail) {
+// `luts` (line path only): where the per-lane indexed slot / firstk tables live; luts.slot == nullptr selects the
+// pointer-walking path even when the geometry is canonical.
+template <bool kSafe>
+__device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& dc, const LidarDev& tables,
+                                              const LidarLuts& luts, const ObsRow& obs, const int8_t* zero, int g, int G,
+                                              bool with_tail) {
     const ngw_config& cfg = dc.c;
     const int B = cfg.n_beams, K = cfg.max_range, L = cfg.n_lidar_items;
-    if (dc.lidar.fast) {
+    if (dc.lidar.lines && luts.slot != nullptr) {
+        const int sel = lidar_line_share(g, G);
+        if (sel) lidar_lines<kSafe>(e, cfg, tables, luts, obs, sel);
+    } else if (dc.lidar.fast) {
         if (G == 1) lidar_fast<8>(e, cfg, tables, obs, zero, 0);
         else if (G == 2) lidar_fast<4>(e, cfg, tables, obs, zero, g * 4);
         else if (G == 3) { if (g < 2) lidar_fast<3>(e, cfg, tables, obs, zero, g * 3); else lidar_fast<2>(e, cfg, tables, obs, zero, 6); }
@@ -417,7 +549,7 @@ __device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& 
                 int id = e.m[idx];
                 if (id != 0) {
                     int slot = cfg.lidar_slot[id];
-                    if (slot >= 0) obs[b * L + slot] = k + 1;
+                    if (slot >= 0) obs.put(b * L + slot, k + 1);
                     break;
                 }
             }
@@ -425,7 +557,7 @@ __device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& 
     }
     if (with_tail) {
         const int n_tail = cfg.n_inv_obs;
-        int32_t* tail = obs + L * B;
+        int32_t* tail = obs.tail(L * B);
         for (int i = 0; i < n_tail; i++) tail[i] = e.inv[cfg.inv_obs_item[i]];   // sorted-name order (Q7)
     }
 }

@@ -24,8 +24,8 @@ struct ResetParams {
     const int32_t* reset_list;  // reset_list_kernel: queue written by the step kernel
     int32_t* reset_count;
     int32_t* done_ctas;
-    int32_t* obs;
-    int obs_dim;
+    unsigned char* obs;         // observation rows of obs_row_bytes bytes (layout as in the step kernel)
+    int obs_dim, obs_row_bytes, obs_u8;
 };
 
 #define NGW_RESET_WARPS 4
@@ -81,8 +81,10 @@ __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_kernel(const Reset
 }
 
 // Second half of the single-step auto-reset: a grid-stride loop of warps over the queue the step kernel filled.  Each
-// warp regenerates one env in HBM (reset_env_warp), then 8 lanes cast its LidarInFront beams into its observation row.
-// The last CTA to finish empties the queue for the next step.
+// warp regenerates one env on a shared-memory copy of its rows (reset_env_warp), casts its LidarInFront beams into its
+// observation row and writes the rows back.  Like ngw_reset, the observation of the new episode is taken after
+// reset_obs_after_ops ops (quirk Q3: a novelty wrapped outside LidarInFront patches the state after the observation
+// was computed).  The last CTA to finish empties the queue for the next step.
 __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_list_kernel(const ResetParams p) {
     __shared__ ResetScratch scratch[NGW_RESET_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -95,30 +97,42 @@ __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_list_kernel(const 
         int r = ps.x, c = ps.y, f = ps.z, sel = ps.w;
         int8_t* m = p.map + e * p.cells;
         int32_t* inv = p.inv + e * p.inv_stride;
+        const uint64_t gid = (uint64_t)(p.first_gid + e);
         uint32_t ep = p.episode[e] + 1;
         __syncwarp();
-        uint32_t err = reset_env_warp(&dc.c, sc.row, sc.inv, p.ms, p.inv_stride, p.seed, (uint64_t)(p.first_gid + e), ep,
-                                      true, 0, NGW_MAX_RESET_OPS, sc.hist, r, c, f, sel);
+        int k_obs = dc.c.reset_obs_after_ops;
+        if (p.obs == nullptr || k_obs >= dc.c.n_reset_ops) k_obs = NGW_MAX_RESET_OPS;
+        uint32_t err = reset_env_warp(&dc.c, sc.row, sc.inv, p.ms, p.inv_stride, p.seed, gid, ep, true, 0, k_obs, sc.hist,
+                                      r, c, f, sel);
+        if (p.obs != nullptr) {                                       // observation of the new episode replaces the row
+            ObsRow orow;
+            orow.p = p.obs + e * p.obs_row_bytes;
+            orow.u8 = p.obs_u8;
+            uint32_t* row = reinterpret_cast<uint32_t*>(orow.p);
+            for (int k = lane; k < (p.obs_row_bytes >> 2); k += 32) row[k] = 0;
+            if (lane == 0) sc.hist[0] = 0;                                // a shared-memory byte that reads 0
+            __syncwarp();
+            EnvRow env;                                                   // lidar on the shared-memory copy
+            env.m = sc.row; env.gm = nullptr; env.inv = sc.inv; env.ms = p.ms;
+            env.r = r; env.c = c; env.facing = f; env.sel = sel;
+            const int8_t* zero = reinterpret_cast<const int8_t*>(sc.hist);
+            LidarLuts luts;
+            luts.slot = dc.c.lidar_slot; luts.firstk = dc.lidar.firstk;
+            if (dc.c.n_beams > 0) {
+                if (dc.lidar.lines) { if (lane < 4) lidar_observe<true>(env, dc, dc.lidar, luts, orow, zero, lane, 4, lane == 3); }
+                else if (dc.lidar.fast) { if (lane < 8) lidar_observe<true>(env, dc, dc.lidar, luts, orow, zero, lane, 8, lane == 7); }
+                else if (lane == 0) lidar_observe<true>(env, dc, dc.lidar, luts, orow, zero, 0, 1, true);
+            }
+            __syncwarp();
+        }
+        if (k_obs < dc.c.n_reset_ops)
+            err |= reset_env_warp(&dc.c, sc.row, sc.inv, p.ms, p.inv_stride, p.seed, gid, ep, false, k_obs,
+                                  NGW_MAX_RESET_OPS, sc.hist, r, c, f, sel);
         rows_from_smem(sc, m, inv, p.cells, p.inv_stride, lane);
         if (lane == 0) {
             p.episode[e] = ep;
             p.pose[e] = make_uchar4((unsigned char)r, (unsigned char)c, (unsigned char)f, (unsigned char)sel);
             if (err) p.err[e] |= err;
-        }
-        if (p.obs != nullptr) {                                       // observation of the new episode replaces the row
-            int32_t* row = p.obs + e * p.obs_dim;
-            for (int k = lane; k < p.obs_dim; k += 32) row[k] = 0;
-            __syncwarp();
-            EnvRow env;                                                   // lidar on the shared-memory copy
-            env.m = sc.row; env.gm = nullptr; env.inv = sc.inv; env.ms = p.ms;
-            env.r = r; env.c = c; env.facing = f; env.sel = sel;
-            if (lane == 0) sc.hist[0] = 0;                                // a shared-memory byte that reads 0
-            __syncwarp();
-            const int8_t* zero = reinterpret_cast<const int8_t*>(sc.hist);
-            if (dc.c.n_beams > 0) {
-                if (dc.lidar.fast) { if (lane < 8) lidar_observe(env, dc, dc.lidar, row, zero, lane, 8, lane == 7); }
-                else if (lane == 0) lidar_observe(env, dc, dc.lidar, row, zero, 0, 1, true);
-            }
         }
         __syncwarp();
     }
@@ -129,7 +143,7 @@ __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_list_kernel(const 
     }
 }
 
-__global__ void observe_masked_kernel(const ResetParams p, int32_t* obs, int obs_dim) {
+__global__ void observe_masked_kernel(const ResetParams p) {
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.n_envs) return;
     if (p.mask != nullptr && p.mask[e] == 0) return;
@@ -141,9 +155,15 @@ __global__ void observe_masked_kernel(const ResetParams p, int32_t* obs, int obs
     env.ms = p.ms;
     uchar4 ps = p.pose[e];
     env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
-    int32_t* row = obs + e * obs_dim;
-    for (int i = 0; i < obs_dim; i++) row[i] = 0;
-    if (dc.c.n_beams > 0) lidar_observe(env, dc, dc.lidar, row, reinterpret_cast<const int8_t*>(p.zero_byte), 0, 1, true);
+    ObsRow orow;
+    orow.p = p.obs + e * p.obs_row_bytes;
+    orow.u8 = p.obs_u8;
+    uint32_t* row = reinterpret_cast<uint32_t*>(orow.p);
+    for (int i = 0; i < (p.obs_row_bytes >> 2); i++) row[i] = 0;
+    LidarLuts luts;
+    luts.slot = dc.c.lidar_slot; luts.firstk = dc.lidar.firstk;
+    if (dc.c.n_beams > 0)
+        lidar_observe<true>(env, dc, dc.lidar, luts, orow, reinterpret_cast<const int8_t*>(p.zero_byte), 0, 1, true);
 }
 
 // AgentMap.get_agentView (observation_wrappers.py:98-118): zero-padded (2v+1)^2 crop centred on the agent

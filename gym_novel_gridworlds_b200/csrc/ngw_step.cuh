@@ -76,7 +76,7 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------ parameters
@@ -90,7 +90,7 @@ struct StepParams {
     int32_t* ep_len;
     uint32_t* err;
     const int32_t* actions;     // nullptr => observe only (no step, no outputs but obs)
-    int32_t* obs;               // nullptr => no observation
+    unsigned char* obs;         // nullptr => no observation; rows of obs_row_bytes bytes (int32 or uint8 lidar part)
     float* reward;
     uint8_t* done;
     float* cost;
@@ -100,11 +100,19 @@ struct StepParams {
     long long first_gid;
     unsigned long long seed;
     int ms, cells, inv_stride, obs_dim;
-    int map_bytes, inv_bytes, obs_bytes, region_bytes;   // per-warp shared-memory carve-up
+    int map_bytes, inv_bytes, obs_bytes;                 // bytes of one 32-env tile of each array
+    int obs_row_bytes, obs_u8;                           // observation row layout (NGW_OBS_I32 / NGW_OBS_U8)
+    // shared-memory carve-up (bytes from the start of dynamic shared memory), all multiples of 128
+    int off_luts, off_scratch, off_in, off_obs;
+    int in_stages, obs_stages;  // input (grid + inventory) buffers / observation buffers per CTA
+    int tiles_per_cta;          // a CTA handles tiles blockIdx.x, blockIdx.x + gridDim.x, ... (tiles_per_cta of them at most)
+    int n_tiles;
     int auto_reset, max_episode_steps;
     int lidar_uniform;          // every config has the same beam tables (then config 0's are read, warp-uniformly)
     int cache_hints;            // bit 0: state tiles are loaded L2::evict_first, bit 1: the observation tile is stored evict_first
     int plain_store;            // 1 => write tiles back with ordinary coalesced stores instead of TMA bulk stores
+    int dbg_skip;               // attribution knob (NGW_SKIP, results are then WRONG): 1 step, 2 lidar, 4 outputs + statistics,
+                                // 8 observation store, 16 inventory store
     // K-step rollout (n_steps > 1 or random policy): the tile stays in shared memory across the steps
     int n_steps;                // steps per launch (1 for ngw_step)
     int random_policy;          // 1 => actions drawn on the device (Philox), `actions` is only a non-null marker
@@ -129,17 +137,14 @@ struct StepArgs {
 };
 
 #define NGW_STAT_SLOTS 512
+#define NGW_SMEM_HDR 256            // mbarriers, zero pad, pose hand-over
+#define NGW_MAX_IN_STAGES 3
+#define NGW_MAX_OBS_STAGES 2
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     return v;
-}
-
-__device__ __forceinline__ void warp_copy16(void* dst, const void* src, int bytes, int lane) {
-    const uint4* s = reinterpret_cast<const uint4*>(src);
-    uint4* d = reinterpret_cast<uint4*>(dst);
-    for (int i = lane; i < (bytes >> 4); i += 32) d[i] = s[i];
 }
 
 // Cold: fused auto-reset.  Called by the whole step warp; every lane that finished an episode is regenerated in turn by
@@ -173,7 +178,7 @@ __device__ __noinline__ void auto_reset_warp(const StepParams& p, const DevConfi
 }
 
 // Episode statistics of one tile: warp reductions + one atomic per counter into one of NGW_STAT_SLOTS slots.
-__device__ __forceinline__ void tile_stats(double* stats, int lane, int valid, int done, int success, int did_reset,
+__device__ __forceinline__ void tile_stats(double* stats, int slot, int lane, int valid, int done, int success, int did_reset,
                                            int invalid, int reward, float cost) {
     // five small counts (each <= 32) share one reduction: 6 bits apiece
     unsigned packed = (unsigned)(valid ? done : 0) | ((unsigned)success << 6) | ((unsigned)did_reset << 12) |
@@ -184,7 +189,7 @@ __device__ __forceinline__ void tile_stats(double* stats, int lane, int valid, i
     if (lane == 0) {
         const int n_done = packed & 63, n_succ = (packed >> 6) & 63, n_reset = (packed >> 12) & 63;
         const int n_inv = (packed >> 18) & 63, n_valid = (packed >> 24) & 63;
-        double* s = stats + (size_t)(blockIdx.x % NGW_STAT_SLOTS) * NGW_STAT_COUNT;
+        double* s = stats + (size_t)(slot % NGW_STAT_SLOTS) * NGW_STAT_COUNT;
         atomicAdd(&s[NGW_STAT_STEPS], (double)(n_valid - n_inv));
         atomicAdd(&s[NGW_STAT_REWARD_SUM], (double)r_sum);
         atomicAdd(&s[NGW_STAT_COST_SUM], (double)c_sum);
@@ -195,252 +200,328 @@ __device__ __forceinline__ void tile_stats(double* stats, int lane, int valid, i
     }
 }
 
+// closed-loop policy of ngw_rollout_policy: argmax_a (b[a] + sum_j obs[j] W[j][a]) over the env's valid ids, first maximum
+__device__ __forceinline__ int linear_policy_action(const StepParams& p, const ngw_config& cfg, const int32_t* row) {
+    int acc[16];
+    const int A = p.policy_actions;
+#pragma unroll
+    for (int a = 0; a < 16; a++) acc[a] = a < A ? p.policy_b[a] : 0;
+    const int D = cfg.n_lidar_items * cfg.n_beams + cfg.n_inv_obs;
+    for (int j = 0; j < D; j++) {
+        const int v = row[j];
+        if (v == 0) continue;                                         // the observation is sparse (<= 8 hits + inventory)
+        const int32_t* w = p.policy_w + (size_t)j * A;
+#pragma unroll
+        for (int a = 0; a < 16; a++) if (a < A) acc[a] += v * w[a];
+    }
+    int best = 0, best_v = acc[0];
+    const int n_valid_actions = cfg.n_actions < A ? cfg.n_actions : A;
+#pragma unroll
+    for (int a = 1; a < 16; a++) if (a < n_valid_actions && acc[a] > best_v) { best_v = acc[a]; best = a; }
+    return best;
+}
+
 // ------------------------------------------------------------------ the fused step + LidarInFront kernel
-// One CTA = one tile of 32 consecutive envs, G = blockDim.x / 32 warps.  Lane l of every warp owns env l of the tile.
-// Warp 0 runs the flattened step; then all G warps cast 8/G lidar beams each for their lane's env.  G = 1 is the plain
-// one-warp-per-tile kernel; G > 1 shortens the per-tile latency where shared memory limits the tiles per SM.
+// A tile = 32 consecutive envs; lane l of every warp owns env l of the tile; G = blockDim.x / 32 warps share a tile:
+// warp 0 runs the flattened step, then all G warps cast the LidarInFront beams of their lane's env (G = 1: one warp
+// does everything).  A CTA handles up to tiles_per_cta tiles (blockIdx.x, blockIdx.x + gridDim.x, ...) through a ring of
+// in_stages input buffers (grid + inventory rows, TMA loads one tile ahead) and obs_stages observation buffers, so the
+// loads of the next tile and the stores of the previous one overlap this tile's compute INSIDE one launch.
 template <bool kTma, int NC, bool kMulti>
 __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepArgs<NC> args) {
     extern __shared__ __align__(128) unsigned char smem[];
     const StepParams& p = args.p;
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, G = blockDim.x >> 5;
-    const long long e0 = p.env_begin + (long long)blockIdx.x * 32;
-    const long long e = e0 + lane;
-    const bool valid = e < p.env_end;
-    const bool full_tile = e0 + 32 <= p.env_end;
     const bool stepping = p.actions != nullptr;
 
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    int8_t* szero = reinterpret_cast<int8_t*>(smem + 8);             // 8 bytes that always read 0 (landed lidar beams park here)
-    uchar4* spose = reinterpret_cast<uchar4*>(smem + 16);            // pose after the step, for the other warps
-    constexpr int kScratch = kMulti ? 1024 : 0;                      // radix-select histogram of the in-place auto-reset (rollout only)
-    uint32_t* sscratch = reinterpret_cast<uint32_t*>(smem + 16 + 128);
-    int8_t* smap = reinterpret_cast<int8_t*>(smem + 16 + 128 + kScratch);
-    int32_t* sinv = reinterpret_cast<int32_t*>(smem + 16 + 128 + kScratch + p.map_bytes);
-    int32_t* sobs = reinterpret_cast<int32_t*>(smem + 16 + 128 + kScratch + p.map_bytes + p.inv_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);              // [NGW_MAX_IN_STAGES] "tile landed" barriers
+    int8_t* szero = reinterpret_cast<int8_t*>(smem + 32);            // 8 bytes that always read 0 (landed lidar beams park here)
+    uchar4* spose = reinterpret_cast<uchar4*>(smem + 64);            // pose after the step, for the other warps
+    uint8_t* sfirstk = smem + p.off_luts;                            // lidar tables read with per-lane indices
+    int8_t* sslot = reinterpret_cast<int8_t*>(smem + p.off_luts + NGW_MAX_MAP_SIZE);
+    uint32_t* sscratch = reinterpret_cast<uint32_t*>(smem + p.off_scratch);   // radix-select histogram (rollout only)
+    const int in_bytes = p.map_bytes + p.inv_bytes;
 
-    // ---- prologue without global memory: barrier, zero pad, zeroed observation tile
-    const int8_t* gmap = p.map + e0 * p.cells;
-    int32_t* ginv = p.inv + e0 * p.inv_stride;
+    // ---- prologue without global state: barriers, zero pad, lidar tables, zeroed observation tiles
     if (threadIdx.x == 0) {
-        if (kTma) mbar_init(bar, 1);
+        if (kTma)
+            for (int s = 0; s < p.in_stages; s++) mbar_init(&bars[s], 1);
         *reinterpret_cast<uint64_t*>(szero) = 0ull;
     }
+    if (NC > 0) {                                                    // config tables are kernel arguments (constant bank)
+        if (threadIdx.x < NGW_MAX_MAP_SIZE / 4)
+            reinterpret_cast<uint32_t*>(sfirstk)[threadIdx.x] =
+                reinterpret_cast<const uint32_t*>(args.cfg[0].lidar.firstk)[threadIdx.x];
+        for (int k = 0; k < NC; k++)
+            if (threadIdx.x < NGW_MAX_ITEMS / 4)
+                reinterpret_cast<uint32_t*>(sslot + k * NGW_MAX_ITEMS)[threadIdx.x] =
+                    reinterpret_cast<const uint32_t*>(args.cfg[k].c.lidar_slot)[threadIdx.x];
+    }
     if (p.obs != nullptr) {
-        uint4 z = make_uint4(0, 0, 0, 0);
-        uint4* o4 = reinterpret_cast<uint4*>(sobs);
-        for (int i = threadIdx.x; i < (p.obs_bytes >> 4); i += blockDim.x) o4[i] = z;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* o4 = reinterpret_cast<uint4*>(smem + p.off_obs);
+        for (int i = threadIdx.x; i < ((p.obs_bytes * p.obs_stages) >> 4); i += blockDim.x) o4[i] = z;
     }
     __syncthreads();                                                 // barrier init visible before anyone waits on it
     asm volatile("griddepcontrol.wait;" ::: "memory");               // previous kernel of the stream done + visible
 
-    // ---- stage the tile: grid rows + inventory rows (state arrays are padded, a full tile is always readable)
-    if (kTma) {
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, (uint32_t)(p.map_bytes + p.inv_bytes));
+    const int n_mine = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_iter = n_mine < p.tiles_per_cta ? n_mine : p.tiles_per_cta;
+    uint64_t pol_first = 0;
+    if (kTma && threadIdx.x == 0) {
+        if (p.cache_hints) pol_first = policy_evict_first();
+        // stage the first tiles: grid rows + inventory rows (state arrays are padded, a full tile is always readable)
+        const int n_pre = n_iter < p.in_stages ? n_iter : p.in_stages;
+        for (int it = 0; it < n_pre; it++) {
+            const long long t0 = p.env_begin + ((long long)blockIdx.x + (long long)it * gridDim.x) * 32;
+            unsigned char* dst = smem + p.off_in + it * in_bytes;
+            mbar_expect_tx(&bars[it], (uint32_t)in_bytes);
             if (p.cache_hints & 1) {
-                uint64_t pol = policy_evict_first();
-                bulk_g2s_hint(smap, gmap, (uint32_t)p.map_bytes, bar, pol);
-                bulk_g2s_hint(sinv, ginv, (uint32_t)p.inv_bytes, bar, pol);
+                bulk_g2s_hint(dst, p.map + t0 * p.cells, (uint32_t)p.map_bytes, &bars[it], pol_first);
+                bulk_g2s_hint(dst + p.map_bytes, p.inv + t0 * p.inv_stride, (uint32_t)p.inv_bytes, &bars[it], pol_first);
             } else {
-                bulk_g2s(smap, gmap, (uint32_t)p.map_bytes, bar);
-                bulk_g2s(sinv, ginv, (uint32_t)p.inv_bytes, bar);
+                bulk_g2s(dst, p.map + t0 * p.cells, (uint32_t)p.map_bytes, &bars[it]);
+                bulk_g2s(dst + p.map_bytes, p.inv + t0 * p.inv_stride, (uint32_t)p.inv_bytes, &bars[it]);
             }
         }
-    } else {
-        const uint4* s4 = reinterpret_cast<const uint4*>(gmap);
-        uint4* d4 = reinterpret_cast<uint4*>(smap);
-        for (int i = threadIdx.x; i < (p.map_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
-        s4 = reinterpret_cast<const uint4*>(ginv);
-        d4 = reinterpret_cast<uint4*>(sinv);
-        for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
     }
 
-    // ---- while the copies fly: per-lane scalars
-    const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[e];
-    const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
-    const ngw_config& cfg = dc.c;
-    uchar4 ps = make_uchar4(0, 0, 0, 0);
-    int action = 0;
-    if (g == 0) {
-        ps = p.pose[e];
-        const bool given_actions = !(kMulti && (p.random_policy || p.policy_w != nullptr));   // else `actions` is a marker
-        if (stepping && valid && given_actions) action = p.actions[e];
-    }
+    for (int it = 0; it < n_iter; it++) {
+        const int stage = it % p.in_stages, ostage = it % p.obs_stages;
+        const long long e0 = p.env_begin + ((long long)blockIdx.x + (long long)it * gridDim.x) * 32;
+        const long long e = e0 + lane;
+        const bool valid = e < p.env_end;
+        const bool full_tile = e0 + 32 <= p.env_end;
+        int8_t* smap = reinterpret_cast<int8_t*>(smem + p.off_in + stage * in_bytes);
+        int32_t* sinv = reinterpret_cast<int32_t*>(smem + p.off_in + stage * in_bytes + p.map_bytes);
+        unsigned char* sobs = smem + p.off_obs + ostage * p.obs_bytes;
+        const int8_t* gmap = p.map + e0 * p.cells;
+        int32_t* ginv = p.inv + e0 * p.inv_stride;
 
-    if (kTma) mbar_wait(bar, 0);
-    else __syncthreads();
-
-    StepOut st_out;                                                  // one-step kernel: statistics are folded after the lidar,
-    st_out.reward = 0; st_out.done = 0; st_out.result = 0; st_out.cost = 0.0f; st_out.msg = 0;   // off the path to the barrier
-    int st_success = 0, st_reset = 0, st_invalid = 0;
-    EnvRow env;
-    env.m = smap + lane * p.cells;
-    env.gm = p.map + e * p.cells;
-    env.inv = sinv + lane * p.inv_stride;
-    env.ms = p.ms;
-
-    if (g == 0) {
-        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
-        if (stepping) {
-            StepOut o;
-            o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0;
-            float reward_sum = 0.0f, cost_sum = 0.0f;
-            int done_count = 0;
-            const int n_steps = kMulti ? p.n_steps : 1;               // kMulti == false: the plain one-step kernel
-            const bool random_policy = kMulti && p.random_policy;
-            for (int t = 0; t < n_steps; t++) {
-                int next_action = 0;                                  // prefetch the next step's action behind this step
-                if (!random_policy && !(kMulti && p.policy_w != nullptr) && t + 1 < n_steps && valid)
-                    next_action = p.actions[(t + 1) * p.act_stride + e];
-                if (kMulti && p.policy_w != nullptr) {                // closed loop: observe, then greedy linear policy
-                    int32_t* row = sobs + lane * p.obs_dim;
-                    for (int j = 0; j < p.obs_dim; j++) row[j] = 0;
-                    if (valid && cfg.n_beams > 0) lidar_observe(env, dc, dc.lidar, row, szero, 0, 1, true);
-                    if (valid) {
-                        int acc[16];
-                        const int A = p.policy_actions;
-#pragma unroll
-                        for (int a = 0; a < 16; a++) acc[a] = a < A ? p.policy_b[a] : 0;
-                        const int D = cfg.n_lidar_items * cfg.n_beams + cfg.n_inv_obs;
-                        for (int j = 0; j < D; j++) {
-                            const int v = row[j];
-                            if (v == 0) continue;                      // the observation is sparse (<= 8 hits + inventory)
-                            const int32_t* w = p.policy_w + (size_t)j * A;
-#pragma unroll
-                            for (int a = 0; a < 16; a++) if (a < A) acc[a] += v * w[a];
-                        }
-                        int best = 0, best_v = acc[0];
-                        const int n_valid_actions = cfg.n_actions < A ? cfg.n_actions : A;
-#pragma unroll
-                        for (int a = 1; a < 16; a++) if (a < n_valid_actions && acc[a] > best_v) { best_v = acc[a]; best = a; }
-                        action = best;
-                    }
-                } else if (random_policy && valid) {                  // uniform over the config's action ids
-                    Philox pr;
-                    pr.init(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, 0xFFF);
-                    action = (int)pr.below((uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
-                }
-                if (kMulti && p.actions_out != nullptr && valid) p.actions_out[t * p.act_stride + e] = action;
-                o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0;
-                int invalid = 0, did_reset = 0, success = 0;
-                if (valid) {
-                    ngw_action_entry a;
-                    a.op = NGW_OP_INVALID;
-                    if (action >= 0 && action < cfg.n_actions) {
-                        uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
-                        memcpy(&a, &raw, sizeof(a));
-                    }
-                    if (a.op == NGW_OP_INVALID) {                     // wrappers.py:76 / pogostick_v1_env.py:236 would raise
-                        invalid = 1;
-                        p.err[e] |= NGW_ERR_INVALID_ACTION;
-                    } else {
-                        step_env(env, cfg, a, o);
-                        success = o.done && env.inv[cfg.id_goal] >= 1;
-                        int finished = o.done;
-                        if (p.max_episode_steps > 0) {
-                            int len = p.ep_len[e] + 1;
-                            if (len >= p.max_episode_steps) { finished = 1; o.done = 1; } // harness truncation knob
-                            p.ep_len[e] = finished && p.auto_reset ? 0 : len;
-                        }
-                        if (finished && p.auto_reset) { did_reset = 1; }
-                    }
-                    ps = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
-                                     (unsigned char)env.sel);
-                    reward_sum += (float)o.reward; cost_sum += o.cost; done_count += o.done;
-                }
-                if (p.auto_reset) {
-                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, did_reset);
-                    if (bal != 0 && !kMulti) {
-                        // single step: queue the finished envs; reset_list_kernel (next in the stream, one warp per env at
-                        // full occupancy) regenerates them and overwrites their observation rows
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(p.reset_count, __popc(bal));
-                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                        if (did_reset) p.reset_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)e;
-                    } else if (bal != 0) {
-                        // rollout: the next step needs the new episode now -> regenerate in place, warp-cooperatively
-                        auto_reset_warp(p, p.dcfgs, cfg_i, did_reset != 0, smap, sinv, sscratch, e0, ps);
-                        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
-                    }
-                }
-                if (kMulti && p.stats != nullptr)
-                    tile_stats(p.stats, lane, valid, o.done, success, did_reset, invalid, o.reward, o.cost);
-                if (!kMulti) { st_success = success; st_reset = did_reset; st_invalid = invalid; }
-                action = next_action;
+        if (it > 0 && (it >= p.obs_stages || it + 1 >= p.in_stages)) {
+            // ring reuse: the bulk stores of an earlier tile must have finished READING their buffers before this tile's
+            // observation buffer is zeroed again and before the load of tile it+1 lands in that tile's input stage.
+            // With 3 input / 2 observation stages that is tile it-2 (the stores of tile it-1 may still be draining).
+            if (kTma && threadIdx.x == 0) {
+                if (p.in_stages >= 3 && p.obs_stages >= 2) bulk_wait_read<1>();
+                else bulk_wait_read<0>();
             }
-            if (!kMulti) st_out = o;                                  // one-step kernel: outputs are stored after the lidar
-            if (kMulti && valid) {
-                p.pose[e] = ps;
-                p.reward[e] = reward_sum;
-                p.done[e] = (uint8_t)o.done;
-                p.cost[e] = cost_sum;
-                p.result[e] = (uint8_t)o.result;
-                if (p.done_count != nullptr) p.done_count[e] = done_count;
-                if (p.msg != nullptr) p.msg[e] = (uint16_t)o.msg;
+            __syncthreads();
+            if (p.obs != nullptr && it >= p.obs_stages) {
+                const uint4 z = make_uint4(0, 0, 0, 0);
+                uint4* o4 = reinterpret_cast<uint4*>(sobs);
+                for (int i = threadIdx.x; i < (p.obs_bytes >> 4); i += blockDim.x) o4[i] = z;
             }
         }
-        if (G > 1) spose[lane] = ps;
-    }
-    if (G > 1) {
-        __syncthreads();                                             // step results (grid, inventory, pose) visible to all warps
-        ps = spose[lane];
-        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
-    }
-
-    // ---- LidarInFront observation of the (possibly auto-reset) state into the shared-memory tile
-    if (p.obs != nullptr && valid && cfg.n_beams > 0)
-        lidar_observe(env, dc, (NC > 1 && p.lidar_uniform) ? args.cfg[0].lidar : dc.lidar, sobs + lane * p.obs_dim, szero, g,
-                      G, g == G - 1);
-
-    if (!kMulti && g == 0 && stepping) {                             // outputs and statistics, off the path to the barrier
-        if (valid) {
-            p.pose[e] = ps;
-            p.reward[e] = (float)st_out.reward;
-            p.done[e] = (uint8_t)st_out.done;
-            p.cost[e] = st_out.cost;
-            p.result[e] = (uint8_t)st_out.result;
-            if (p.msg != nullptr) p.msg[e] = (uint16_t)st_out.msg;
-        }
-        if (p.stats != nullptr)
-            tile_stats(p.stats, lane, valid, st_out.done, st_success, st_reset, st_invalid, st_out.reward, st_out.cost);
-    }
-
-    // Programmatic dependent launch: this tile's compute is done, let the next kernel of the stream start scheduling its
-    // CTAs; its prologue (up to griddepcontrol.wait) touches no global memory, so it overlaps this kernel's store phase.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
-    // ---- write back: inventory tile (only when stepping) and observation tile
-    __syncthreads();
-    if (kTma && full_tile && !p.plain_store) {
-        if (threadIdx.x < 32) {
-            fence_async_smem();
-            __syncwarp();
-            if (threadIdx.x == 0) {
-                if (p.cache_hints & 2) {
-                    uint64_t pol = policy_evict_first();
-                    if (stepping) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
-                    if (p.obs != nullptr) bulk_s2g_hint(p.obs + e0 * p.obs_dim, sobs, (uint32_t)p.obs_bytes, pol);
+        if (kTma) {
+            // one tile ahead: tile it+1 goes into the stage tile it-2 used (in_stages == 3) unless the prologue staged it
+            const int nx = it + 1;
+            if (threadIdx.x == 0 && nx < n_iter && nx >= p.in_stages) {
+                const int ns = nx % p.in_stages;
+                const long long t0 = p.env_begin + ((long long)blockIdx.x + (long long)nx * gridDim.x) * 32;
+                unsigned char* dst = smem + p.off_in + ns * in_bytes;
+                mbar_expect_tx(&bars[ns], (uint32_t)in_bytes);
+                if (p.cache_hints & 1) {
+                    bulk_g2s_hint(dst, p.map + t0 * p.cells, (uint32_t)p.map_bytes, &bars[ns], pol_first);
+                    bulk_g2s_hint(dst + p.map_bytes, p.inv + t0 * p.inv_stride, (uint32_t)p.inv_bytes, &bars[ns], pol_first);
                 } else {
-                    if (stepping) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
-                    if (p.obs != nullptr) bulk_s2g(p.obs + e0 * p.obs_dim, sobs, (uint32_t)p.obs_bytes);
+                    bulk_g2s(dst, p.map + t0 * p.cells, (uint32_t)p.map_bytes, &bars[ns]);
+                    bulk_g2s(dst + p.map_bytes, p.inv + t0 * p.inv_stride, (uint32_t)p.inv_bytes, &bars[ns]);
                 }
-                bulk_commit();
-                bulk_wait_read0();                                   // shared memory must outlive the reads
             }
-        }
-    } else {
-        if (stepping) {
-            const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
-            uint4* d4 = reinterpret_cast<uint4*>(ginv);
+        } else {
+            const uint4* s4 = reinterpret_cast<const uint4*>(gmap);
+            uint4* d4 = reinterpret_cast<uint4*>(smap);
+            for (int i = threadIdx.x; i < (p.map_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
+            s4 = reinterpret_cast<const uint4*>(ginv);
+            d4 = reinterpret_cast<uint4*>(sinv);
             for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
         }
-        if (p.obs != nullptr) {
-            int n = (int)((p.env_end - e0 < 32 ? p.env_end - e0 : 32)) * p.obs_dim;
-            int32_t* gobs = p.obs + e0 * p.obs_dim;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) gobs[i] = sobs[i];
+
+        // ---- while the copies fly: per-lane scalars
+        const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[e];
+        const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
+        const ngw_config& cfg = dc.c;
+        const LidarDev& beam_tables = (NC > 1 && p.lidar_uniform) ? args.cfg[0].lidar : dc.lidar;
+        LidarLuts luts;
+        if (NC > 0) {
+            luts.slot = sslot + cfg_i * NGW_MAX_ITEMS;
+            luts.firstk = (NC == 1 || p.lidar_uniform) ? sfirstk : nullptr;
+            if (luts.firstk == nullptr) luts.slot = nullptr;          // heterogeneous beam tables: pointer-walking path
+        } else {
+            luts.slot = p.dcfgs[cfg_i].c.lidar_slot;
+            luts.firstk = p.dcfgs[cfg_i].lidar.firstk;
         }
+        ObsRow orow;
+        orow.p = sobs + lane * p.obs_row_bytes;
+        orow.u8 = p.obs_u8;
+        uchar4 ps = make_uchar4(0, 0, 0, 0);
+        int action = 0;
+        if (g == 0) {
+            ps = p.pose[e];
+            const bool given_actions = !(kMulti && (p.random_policy || p.policy_w != nullptr));   // else `actions` is a marker
+            if (stepping && valid && given_actions) action = p.actions[e];
+        }
+
+        if (kTma) mbar_wait(&bars[stage], (uint32_t)((it / p.in_stages) & 1));
+        else __syncthreads();
+
+        StepOut st_out;                                              // one-step kernel: statistics are folded after the lidar,
+        st_out.reward = 0; st_out.done = 0; st_out.result = 0; st_out.cost = 0.0f; st_out.msg = 0;   // off the path to the barrier
+        int st_success = 0, st_reset = 0, st_invalid = 0;
+        EnvRow env;
+        env.m = smap + lane * p.cells;
+        env.gm = p.map + e * p.cells;
+        env.inv = sinv + lane * p.inv_stride;
+        env.ms = p.ms;
+
+        if (g == 0) {
+            env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+            if (stepping) {
+                StepOut o;
+                o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0;
+                float reward_sum = 0.0f, cost_sum = 0.0f;
+                int done_count = 0;
+                const int n_steps = kMulti ? p.n_steps : 1;           // kMulti == false: the plain one-step kernel
+                const bool random_policy = kMulti && p.random_policy;
+                const bool closed_loop = kMulti && p.policy_w != nullptr;
+                for (int t = 0; t < n_steps; t++) {
+                    int next_action = 0;                              // prefetch the next step's action behind this step
+                    if (!random_policy && !closed_loop && t + 1 < n_steps && valid)
+                        next_action = p.actions[(t + 1) * p.act_stride + e];
+                    if (closed_loop) {                                // observe, then greedy linear policy (int32 rows only)
+                        int32_t* row = reinterpret_cast<int32_t*>(orow.p);
+                        for (int j = 0; j < p.obs_dim; j++) row[j] = 0;
+                        if (valid && cfg.n_beams > 0) lidar_observe<false>(env, dc, beam_tables, luts, orow, szero, 0, 1, true);
+                        if (valid) action = linear_policy_action(p, cfg, row);
+                    } else if (random_policy && valid) {              // uniform over the config's action ids
+                        Philox pr;
+                        pr.init(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, 0xFFF);
+                        action = (int)pr.below((uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
+                    }
+                    if (kMulti && p.actions_out != nullptr && valid) p.actions_out[t * p.act_stride + e] = action;
+                    o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0;
+                    int invalid = 0, did_reset = 0, success = 0;
+                    if (valid) {
+                        ngw_action_entry a;
+                        a.op = NGW_OP_INVALID;
+                        if (action >= 0 && action < cfg.n_actions) {
+                            uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
+                            memcpy(&a, &raw, sizeof(a));
+                        }
+                        if (a.op == NGW_OP_INVALID) {                 // wrappers.py:76 / pogostick_v1_env.py:236 would raise
+                            invalid = 1;
+                            p.err[e] |= NGW_ERR_INVALID_ACTION;
+                        } else {
+                            if (!(p.dbg_skip & 1)) step_env(env, cfg, a, o);
+                            success = o.done && env.inv[cfg.id_goal] >= 1;
+                            int finished = o.done;
+                            if (p.max_episode_steps > 0) {
+                                int len = p.ep_len[e] + 1;
+                                if (len >= p.max_episode_steps) { finished = 1; o.done = 1; } // harness truncation knob
+                                p.ep_len[e] = finished && p.auto_reset ? 0 : len;
+                            }
+                            if (finished && p.auto_reset) { did_reset = 1; }
+                        }
+                        ps = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
+                                         (unsigned char)env.sel);
+                        reward_sum += (float)o.reward; cost_sum += o.cost; done_count += o.done;
+                    }
+                    if (p.auto_reset) {
+                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, did_reset);
+                        if (bal != 0 && !kMulti) {
+                            // single step: queue the finished envs; reset_list_kernel (next in the stream, one warp per env at
+                            // full occupancy) regenerates them and overwrites their observation rows
+                            int base = 0;
+                            if (lane == 0) base = atomicAdd(p.reset_count, __popc(bal));
+                            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                            if (did_reset) p.reset_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)e;
+                        } else if (bal != 0) {
+                            // rollout: the next step needs the new episode now -> regenerate in place, warp-cooperatively
+                            auto_reset_warp(p, p.dcfgs, cfg_i, did_reset != 0, smap, sinv, sscratch, e0, ps);
+                            env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+                        }
+                    }
+                    if (kMulti && p.stats != nullptr)
+                        tile_stats(p.stats, (int)blockIdx.x, lane, valid, o.done, success, did_reset, invalid, o.reward, o.cost);
+                    if (!kMulti) { st_success = success; st_reset = did_reset; st_invalid = invalid; }
+                    action = next_action;
+                }
+                if (closed_loop) {                                    // the last policy observation must not leak into the final one
+                    int32_t* row = reinterpret_cast<int32_t*>(orow.p);
+                    for (int j = 0; j < p.obs_dim; j++) row[j] = 0;
+                }
+                if (!kMulti) st_out = o;                              // one-step kernel: outputs are stored after the lidar
+                if (kMulti && valid) {
+                    p.pose[e] = ps;
+                    p.reward[e] = reward_sum;
+                    p.done[e] = (uint8_t)o.done;
+                    p.cost[e] = cost_sum;
+                    p.result[e] = (uint8_t)o.result;
+                    if (p.done_count != nullptr) p.done_count[e] = done_count;
+                    if (p.msg != nullptr) p.msg[e] = (uint16_t)o.msg;
+                }
+            }
+            if (G > 1) spose[lane] = ps;
+        }
+        if (G > 1) {
+            __syncthreads();                                         // step results (grid, inventory, pose) visible to all warps
+            ps = spose[lane];
+            env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+        }
+
+        // ---- LidarInFront observation of the (possibly auto-reset) state into the shared-memory tile
+        if (p.obs != nullptr && valid && cfg.n_beams > 0 && !(p.dbg_skip & 2))
+            lidar_observe<false>(env, dc, beam_tables, luts, orow, szero, g, G, g == G - 1);
+
+        // ---- write back: inventory tile (only when stepping) and observation tile.  Every thread orders its generic-proxy
+        //      writes to the tiles before the async proxy reads them (fence before the barrier), then one thread issues.
+        if (kTma) fence_async_smem();
+        __syncthreads();
+        if (kTma && full_tile && !p.plain_store) {
+            if (threadIdx.x == 0) {
+                if (stepping && !(p.dbg_skip & 16)) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
+                if (p.obs != nullptr && !(p.dbg_skip & 8)) {
+                    unsigned char* gobs = p.obs + e0 * p.obs_row_bytes;
+                    if (p.cache_hints & 2) bulk_s2g_hint(gobs, sobs, (uint32_t)p.obs_bytes, pol_first);
+                    else bulk_s2g(gobs, sobs, (uint32_t)p.obs_bytes);
+                }
+                bulk_commit();
+            }
+        } else {
+            if (stepping) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
+                uint4* d4 = reinterpret_cast<uint4*>(ginv);
+                for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
+            }
+            if (p.obs != nullptr) {
+                const int n = (int)((p.env_end - e0 < 32 ? p.env_end - e0 : 32)) * (p.obs_row_bytes >> 2);
+                uint32_t* gobs = reinterpret_cast<uint32_t*>(p.obs + e0 * p.obs_row_bytes);
+                const uint32_t* so = reinterpret_cast<const uint32_t*>(sobs);
+                for (int i = threadIdx.x; i < n; i += blockDim.x) gobs[i] = so[i];
+            }
+            if (it + 1 < n_iter) __syncthreads();                    // plain copies read the buffers: done before any reuse
+        }
+        if (!kMulti && g == 0 && stepping && !(p.dbg_skip & 4)) {    // outputs and statistics, behind the tile stores
+            if (valid) {
+                p.pose[e] = ps;
+                p.reward[e] = (float)st_out.reward;
+                p.done[e] = (uint8_t)st_out.done;
+                p.cost[e] = st_out.cost;
+                p.result[e] = (uint8_t)st_out.result;
+                if (p.msg != nullptr) p.msg[e] = (uint16_t)st_out.msg;
+            }
+            if (p.stats != nullptr)
+                tile_stats(p.stats, (int)(e0 >> 5), lane, valid, st_out.done, st_success, st_reset, st_invalid, st_out.reward,
+                           st_out.cost);
+        }
+
+        // Programmatic dependent launch: this CTA's compute is done, let the next kernel of the stream start scheduling its
+        // CTAs; its prologue (up to griddepcontrol.wait) touches no global state, so it overlaps this kernel's store phase.
+        if (it == n_iter - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
+    if (n_iter == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (kTma && threadIdx.x == 0) bulk_wait_read<0>();               // shared memory must outlive the bulk stores' reads
 }
 
 

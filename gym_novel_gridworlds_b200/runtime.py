@@ -31,7 +31,7 @@ def _ptr(t):
 
 
 class BatchHandle(object):
-    def __init__(self, compiled, n_envs, device=None, seed=0, first_env_gid=0, cfg_id=None):
+    def __init__(self, compiled, n_envs, device=None, seed=0, first_env_gid=0, cfg_id=None, obs_format='i32'):
         if not torch.cuda.is_available():
             raise RuntimeError("gym_novel_gridworlds_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.lib = capi.load_library()
@@ -49,9 +49,15 @@ class BatchHandle(object):
         self._h = C.c_void_p()
         capi.check(self.lib, self.lib.ngw_create(C.byref(self._h), cfgs, len(self.compiled), self.n, self.map_size,
                                                  self.device.index, int(first_env_gid), int(seed) & (2 ** 64 - 1)))
+        if obs_format not in ('i32', 'u8'):
+            raise ValueError("obs_format must be 'i32' (the reference's vector as int32) or 'u8' (uint8 lidar ranges)")
+        self.obs_format = obs_format
+        if obs_format == 'u8':
+            capi.check(self.lib, self.lib.ngw_set_obs_format(self._h, capi.OBS_U8))
         sv = StateViewC()
         capi.check(self.lib, self.lib.ngw_state(self._h, C.byref(sv)))
         self.inv_stride, self.obs_dim, self.n_padded = sv.inv_stride, sv.obs_dim, sv.n_envs_padded
+        self.obs_row_bytes = sv.obs_row_bytes
         ms = self.map_size
 
         def view(ptr, shape, typestr):
@@ -67,7 +73,10 @@ class BatchHandle(object):
         self.error_flags = view(sv.error_flags, (self.n_padded,), '<i4')[:self.n]
         with torch.cuda.device(self.device):
             d = max(self.obs_dim, 1)
-            self.obs = torch.zeros((self.n, d), dtype=torch.int32, device=self.device)
+            if obs_format == 'u8':       # rows: uint8 lidar ranges | pad to 4 | int32 inventory tail (see split_obs)
+                self.obs = torch.zeros((self.n, max(self.obs_row_bytes, 4)), dtype=torch.uint8, device=self.device)
+            else:
+                self.obs = torch.zeros((self.n, d), dtype=torch.int32, device=self.device)
             self.reward = torch.zeros(self.n, dtype=torch.float32, device=self.device)
             self.done = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
             self.step_cost = torch.zeros(self.n, dtype=torch.float32, device=self.device)
@@ -116,8 +125,31 @@ class BatchHandle(object):
         capi.check(self.lib, self.lib.ngw_load_state(self._h, _ptr(m), _ptr(p), _ptr(v), first, count, self._stream()))
         torch.cuda.current_stream(self.device).synchronize()      # m/p/v may be temporaries
 
-    def export_state(self):
-        return self.map.clone(), self.pose.clone(), self.inventory.clone()
+    def export_state(self, first=0, count=None, host=False):
+        """Copy of `count` env states from env `first` through ngw_export_state: (map int8 [count, ms, ms], pose uint8
+        [count, 4], inventory int32 [count, inv_stride]); host=True exports straight into pinned host memory."""
+        count = self.n - first if count is None else int(count)
+        kw = {'device': 'cpu', 'pin_memory': True} if host else {'device': self.device}
+        m = torch.empty((count, self.map_size * self.map_size), dtype=torch.int8, **kw)
+        p = torch.empty((count, 4), dtype=torch.uint8, **kw)
+        v = torch.empty((count, self.inv_stride), dtype=torch.int32, **kw)
+        capi.check(self.lib, self.lib.ngw_export_state(self._h, _ptr(m), _ptr(p), _ptr(v), int(first), count,
+                                                       self._stream()))
+        if host:
+            torch.cuda.current_stream(self.device).synchronize()
+        return m.view(count, self.map_size, self.map_size), p, v
+
+    def split_obs(self, obs, cfg=0):
+        """(lidar ranges [n, L*B], inventory tail [n, I_obs]) views of an observation buffer of this handle's format
+        (torch tensor or numpy array) for config `cfg` — the two halves of observation_wrappers.py:70-80."""
+        c = self.compiled[cfg].c
+        nl, ni = c.n_lidar_items * c.n_beams, c.n_inv_obs
+        if self.obs_format == 'i32':
+            return obs[:, :nl], obs[:, nl:nl + ni]
+        off = (nl + 3) & ~3
+        tail = obs[:, off:off + 4 * ni]
+        tail = tail.view(torch.int32) if isinstance(tail, torch.Tensor) else tail.view(np.int32)
+        return obs[:, :nl], tail
 
     def reset(self, mask=None, want_obs=True):
         mk = None
@@ -191,9 +223,13 @@ class BatchHandle(object):
             d = max(self.obs_dim, 1)
             n = self.n
             small = torch.zeros(10 * n + 64, dtype=torch.uint8).pin_memory()   # reward | step_cost | done | result
+            if self.obs_format == 'u8':
+                host_obs = torch.zeros((n, max(self.obs_row_bytes, 4)), dtype=torch.uint8).pin_memory()
+            else:
+                host_obs = torch.zeros((n, d), dtype=torch.int32).pin_memory()
             self._host = {
                 'actions': torch.zeros(n, dtype=torch.int32).pin_memory(),
-                'obs': torch.zeros((n, d), dtype=torch.int32).pin_memory(),
+                'obs': host_obs,
                 'small': small,
                 'reward': small[:4 * n].view(torch.float32),
                 'step_cost': small[4 * n:8 * n].view(torch.float32),

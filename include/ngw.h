@@ -20,7 +20,8 @@
  *                                     bow_v1_env.py:228-340, wrappers.py:74-85,
  *                                     observation_wrappers.py:32-80, novelty_wrappers.py step methods)
  *   ngw_observe                   <- LidarInFront.observation                  (observation_wrappers.py:70-80)
- *   ngw_load_state / ngw_state   <- the `env=` restore branch of reset / get_observation's live
+ *   ngw_load_state / ngw_export_state / ngw_state
+ *                                 <- the `env=` restore branch of reset / get_observation's live
  *                                     references                              (pogostick_v1_env.py:89-109,214-228)
  *   ngw_stats                     <- (absent in the reference; episode statistics for the NCCL reduce)
  *
@@ -37,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NGW_ABI_VERSION 8
+#define NGW_ABI_VERSION 9
 
 #define NGW_MAX_ITEMS 24          /* reference asserts len(items) <= 20 (pogostick_v1_env.py:75,220) */
 #define NGW_MAX_ACTIONS 48
@@ -199,6 +200,14 @@ enum ngw_msg {
 enum { NGW_STAT_STEPS = 0, NGW_STAT_EPISODES = 1, NGW_STAT_SUCCESSES = 2, NGW_STAT_REWARD_SUM = 3,
        NGW_STAT_COST_SUM = 4, NGW_STAT_RESETS = 5, NGW_STAT_INVALID = 6, NGW_STAT_RESERVED = 7, NGW_STAT_COUNT = 8 };
 
+/* Observation row layouts (ngw_set_obs_format).  Both carry the reference's vector (observation_wrappers.py:70-80):
+ * L*B lidar ranges (beam-major, L lidar items per beam) followed by the I_obs inventory quantities.
+ *   NGW_OBS_I32 (default): int32 [L*B + I_obs]                         row = 4 * obs_dim bytes
+ *   NGW_OBS_U8           : uint8 [L*B], zero padding to a multiple of 4, int32 [I_obs]
+ *                          (a range is <= max_beam_range <= 90, so the byte is exact; inventory counts are unbounded
+ *                          (quirk Q8) and stay int32).  C2: 56 + 28 = 84 bytes instead of 252. */
+enum { NGW_OBS_I32 = 0, NGW_OBS_U8 = 1 };
+
 /* raw device pointers of the struct-of-arrays state owned by a handle (get_observation's live references) */
 typedef struct {
     int8_t*  map;        /* [n_envs_padded][map_size*map_size] item ids */
@@ -214,6 +223,8 @@ typedef struct {
     int64_t n_envs_padded;
     int32_t map_size;
     int32_t n_configs;
+    int32_t obs_format;  /* NGW_OBS_I32 / NGW_OBS_U8 */
+    int32_t obs_row_bytes; /* bytes per env of the observation buffers handed to ngw_step / ngw_reset / ngw_observe */
 } ngw_state_view;
 
 typedef struct ngw_handle ngw_handle;
@@ -229,6 +240,15 @@ int ngw_abi_version(void);
 
 int ngw_state(ngw_handle* h, ngw_state_view* out);
 
+/* Choose the observation row layout for every following call (default NGW_OBS_I32).  The observation pointers of
+ * ngw_step / ngw_step_host / ngw_reset / ngw_observe / ngw_rollout then address rows of ngw_state_view.obs_row_bytes
+ * bytes.  NGW_OBS_U8 cuts the device-to-host traffic of the host-buffer path from 266 to 94 bytes per env-step on C2. */
+int ngw_set_obs_format(ngw_handle* h, int32_t format);
+
+/* Which LidarInFront path the kernels take for this config on this map size (no GPU needed): 0 no lidar wrapper,
+ * 1 generic LUT walk (beam count != 8), 2 factorised pointer walk, 3 line gather (the reference's 8-beam geometry). */
+int ngw_lidar_path(const ngw_config* cfg, int32_t map_size);
+
 /* cfg_id: DEVICE int32[n_envs] (NULL = all zero). */
 int ngw_set_env_configs(ngw_handle* h, const int32_t* cfg_id_dev, void* stream);
 
@@ -237,16 +257,23 @@ int ngw_set_env_configs(ngw_handle* h, const int32_t* cfg_id_dev, void* stream);
 int ngw_load_state(ngw_handle* h, const int8_t* map, const uint8_t* pose, const int32_t* inventory,
                    int64_t first, int64_t count, void* stream);
 
+/* The inverse: copy `count` env states starting at env `first` out of the batch, same layouts; NULL skips an array.
+ * Destinations may be device or host memory (asynchronous on `stream`; synchronize it before reading host memory). */
+int ngw_export_state(ngw_handle* h, int8_t* map, uint8_t* pose, int32_t* inventory, int64_t first, int64_t count,
+                     void* stream);
+
 /* Reset envs whose mask byte is non-zero (mask DEVICE uint8[n_envs], NULL = all) with the Philox
- * map generator; obs (DEVICE int32[n_envs][obs_dim], NULL = skip) receives the reset observation of
+ * map generator; obs (DEVICE rows of obs_row_bytes, NULL = skip) receives the reset observation of
  * the reset envs, taken after cfg.reset_obs_after_ops ops as the reference does. */
-int ngw_reset(ngw_handle* h, const uint8_t* mask, int32_t* obs, void* stream);
+int ngw_reset(ngw_handle* h, const uint8_t* mask, void* obs, void* stream);
 
 /* One fused step of every env: action semantics + novelties + reward/done/step_cost + LidarInFront
  * observation (+ Philox auto-reset of done envs when auto_reset != 0 — queued by the step kernel and regenerated by
- * a second small kernel of the same call —, + truncation when max_episode_steps > 0).  All pointers are DEVICE
- * pointers, obs 16-byte aligned; obs may be NULL when obs_dim == 0. */
-int ngw_step(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done,
+ * a second small kernel of the same call; the observation row of a regenerated env is the new episode's reset
+ * observation, taken after cfg.reset_obs_after_ops ops like ngw_reset —, + truncation when max_episode_steps > 0).
+ * All pointers are DEVICE pointers, obs = [n_envs] rows of obs_row_bytes (int32 [n_envs][obs_dim] by default),
+ * 16-byte aligned; obs may be NULL when obs_dim == 0. */
+int ngw_step(ngw_handle* h, const int32_t* actions, void* obs, float* reward, uint8_t* done,
              float* step_cost, uint8_t* result, int32_t auto_reset, int32_t max_episode_steps, void* stream);
 
 /* Optional: DEVICE uint16[n_envs] that every following ngw_step / ngw_rollout fills with the step's message code
@@ -255,9 +282,10 @@ int ngw_set_message_buffer(ngw_handle* h, uint16_t* msg_dev);
 
 /* Same call with HOST buffers (the reference-facing path): copies actions in (H2D), steps, copies
  * obs/reward/done/step_cost/result out (D2H) on the handle's own stream; returns after the outputs are valid
- * on the host.  Pinned buffers make the copies true DMA; if step_cost == reward + n, done == step_cost + n and
+ * on the host.  The step is ordered after everything earlier calls on this handle enqueued on the caller's streams
+ * (ngw_reset, ngw_load_state, ngw_step ...), and later device-path calls wait for it.  Pinned buffers make the copies true DMA; if step_cost == reward + n, done == step_cost + n and
  * result == done + n (bytes: reward | step_cost | done | result contiguous) the four small outputs travel in one copy. */
-int ngw_step_host(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done,
+int ngw_step_host(ngw_handle* h, const int32_t* actions, void* obs, float* reward, uint8_t* done,
                   float* step_cost, uint8_t* result, int32_t auto_reset, int32_t max_episode_steps);
 
 /* K-step rollout in ONE launch: every tile stays in shared memory for n_steps consecutive steps.
@@ -265,28 +293,29 @@ int ngw_step_host(ngw_handle* h, const int32_t* actions, int32_t* obs, float* re
  * (policy_seed, global env id, step index) — the tests/random_action.py loop without the host.  reward_sum / cost_sum
  * accumulate over the steps, done_count counts finished episodes, last_done / last_result are the final step's, obs is
  * the observation after the last step; actions_out (DEVICE int32[n_steps][n_envs], NULL = skip) records the actions. */
-int ngw_rollout(ngw_handle* h, const int32_t* actions, int32_t n_steps, uint64_t policy_seed, int32_t* obs,
+int ngw_rollout(ngw_handle* h, const int32_t* actions, int32_t n_steps, uint64_t policy_seed, void* obs,
                 float* reward_sum, float* cost_sum, int32_t* done_count, uint8_t* last_done, uint8_t* last_result,
                 int32_t* actions_out, int32_t auto_reset, int32_t max_episode_steps, void* stream);
 
 /* Closed-loop K-step rollout: at every step the action is argmax_a (bias[a] + sum_j obs[j] * weights[j][a]) over the
  * env's valid action ids, computed on the device from the current LidarInFront observation (lowest id wins ties).
  * weights: DEVICE int32[obs_dim][n_policy_actions], bias: DEVICE int32[n_policy_actions], n_policy_actions <= 16.
- * Integer arithmetic => bit-reproducible on the host.  Outputs as ngw_rollout. */
+ * Integer arithmetic => bit-reproducible on the host.  Outputs as ngw_rollout.  Needs NGW_OBS_I32 rows.  With auto_reset,
+ * an env regenerated inside a rollout is observed after ALL of its reset ops (the next step needs the final state). */
 int ngw_rollout_policy(ngw_handle* h, const int32_t* weights, const int32_t* bias, int32_t n_policy_actions,
-                       int32_t n_steps, int32_t* obs, float* reward_sum, float* cost_sum, int32_t* done_count,
+                       int32_t n_steps, void* obs, float* reward_sum, float* cost_sum, int32_t* done_count,
                        uint8_t* last_done, uint8_t* last_result, int32_t* actions_out, int32_t auto_reset,
                        int32_t max_episode_steps, void* stream);
 
 /* The host-buffer step split in two, so that a caller with several batches can keep PCIe busy: _begin enqueues the
  * H2D copy, the launch and the D2H copies on the handle's own stream and returns; _end blocks until this handle's
  * outputs are valid on the host.  ngw_step_host == _begin + _end. */
-int ngw_step_host_begin(ngw_handle* h, const int32_t* actions, int32_t* obs, float* reward, uint8_t* done,
+int ngw_step_host_begin(ngw_handle* h, const int32_t* actions, void* obs, float* reward, uint8_t* done,
                         float* step_cost, uint8_t* result, int32_t auto_reset, int32_t max_episode_steps);
 int ngw_step_host_end(ngw_handle* h);
 
-/* LidarInFront.observation of the current state into DEVICE int32[n_envs][obs_dim]. */
-int ngw_observe(ngw_handle* h, int32_t* obs, void* stream);
+/* LidarInFront.observation of the current state into DEVICE [n_envs] rows of obs_row_bytes. */
+int ngw_observe(ngw_handle* h, void* obs, void* stream);
 
 /* AgentMap.get_agentView (observation_wrappers.py:98-118): the (2*view+1)^2 zero-padded crop of the grid centred on the
  * agent, DEVICE int8[n_envs][2*view+1][2*view+1]. */

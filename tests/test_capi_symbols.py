@@ -78,3 +78,21 @@ def test_no_gpu_means_a_loud_failure_not_a_fallback():
     env = bench.build_c2_chain()
     with pytest.raises(RuntimeError):
         env.reset()
+
+
+@pytest.mark.skipif(not os.path.exists(capi.LIB_PATH), reason="libngw_b200.so not built")
+def test_lidar_path_selection_needs_no_gpu():
+    """ngw_lidar_path: the reference's 8-beam geometry takes the line-gather path (3) on every grid size; other beam
+    counts walk the generic LUT (1); no LidarInFront wrapper -> 0."""
+    import scenarios
+    from gym_novel_gridworlds_b200.compiler import compile_chain
+    lib = capi.load_library()
+    ns = scenarios.b200_namespace()
+    for ms in (9, 10, 11, 17, 32, 33, 40, 64):
+        cc = compile_chain(scenarios.build_chain(ns, {'env': scenarios.POGO, 'map_size': ms, 'chain': [['lidar', 8]]}))
+        assert lib.ngw_lidar_path(C.byref(cc.c), ms) == 3, ms
+    for beams in (1, 5, 16):
+        cc = compile_chain(scenarios.build_chain(ns, {'env': scenarios.BOW, 'map_size': 12, 'chain': [['lidar', beams]]}))
+        assert lib.ngw_lidar_path(C.byref(cc.c), 12) == 1, beams
+    cc = compile_chain(scenarios.build_chain(ns, {'env': scenarios.POGO, 'map_size': 10, 'chain': []}))
+    assert lib.ngw_lidar_path(C.byref(cc.c), 10) == 0

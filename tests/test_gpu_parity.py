@@ -371,3 +371,190 @@ def test_closed_loop_policy_rollout_matches_host_replay():
     assert np.array_equal(h.map.cpu().numpy().reshape(n, -1), ob.map) and np.array_equal(h.pose.cpu().numpy(), ob.pose)
     assert np.array_equal(h.inventory.cpu().numpy(), ob.inv)
     assert np.array_equal(out[0].cpu().numpy()[:, :cc.obs_dim], o_obs) and np.array_equal(out[1].cpu().numpy(), rew)
+
+
+# ---------------------------------------------------------------------------------------------- round 2 additions
+C2_DESC = {'env': scenarios.POGO, 'map_size': 10, 'chain': [['limit', scenarios.C2_SET], ['lidar', 8]]}
+
+
+def _u8_rows_to_vector(h, rows, cfg_ids=None):
+    """NGW_OBS_U8 rows -> the reference's int32 vector (lidar ranges then inventory tail), per env."""
+    rows = rows.cpu().numpy() if hasattr(rows, 'cpu') else rows
+    out = np.zeros((rows.shape[0], h.obs_dim), np.int32)
+    ids = np.zeros(rows.shape[0], np.int64) if cfg_ids is None else np.asarray(cfg_ids, np.int64)
+    for k, cc in enumerate(h.compiled):
+        sel = ids == k
+        if not sel.any():
+            continue
+        lidar, tail = h.split_obs(rows, cfg=k)
+        nl, ni = lidar.shape[1], tail.shape[1]
+        out[sel, :nl] = lidar[sel]
+        out[sel, nl:nl + ni] = np.ascontiguousarray(tail)[sel]
+    return out
+
+
+@pytest.mark.parametrize('case', ['C2', 'C4', 'C5', 'generic16'])
+def test_compact_u8_observation_rows_equal_the_int32_vector(case):
+    """NGW_OBS_U8 (uint8 lidar ranges + int32 inventory tail) carries exactly the reference's vector: every step
+    compared with the oracle, device path and host-buffer path, single and mixed configs, map 40 with auto-reset."""
+    cfg_id = None
+    if case == 'C2':
+        compiled, n, steps = [_compiled(C2_DESC)], 3000 + 11, 48
+    elif case == 'C4':
+        descs = [dict(C2_DESC, chain=[['limit', scenarios.C2_SET + ex], ['lidar', 8], nov]) for ex, nov in (
+            (['Chop'], ['novelty', 'addchop', 'hard', '', '']), (['Jump'], ['novelty', 'addjump', 'hard', '', '']),
+            ([], ['novelty', 'additem', 'medium', 'spring', '']), ([], ['novelty', 'remapaction', 'hard', '', '']))]
+        compiled, n, steps = [_compiled(d) for d in descs], 2048 + 9, 40
+        cfg_id = (np.arange(n) % 4).astype(np.uint8)
+    elif case == 'C5':
+        compiled, n, steps = [_compiled(golden_util.get('pogo_ms40_additem_hard')['meta'])], 200, 40
+    else:
+        compiled, n, steps = [_compiled({'env': scenarios.BOW, 'map_size': 12, 'chain': [['lidar', 16]]})], 500, 32
+    ob = OracleBatch(compiled, n, cfg_id=cfg_id)
+    ob.reset_legacy(808)
+    hd = BatchHandle(compiled, n, cfg_id=None if cfg_id is None else cfg_id.astype(np.int32), obs_format='u8')
+    hh = BatchHandle(compiled, n, cfg_id=None if cfg_id is None else cfg_id.astype(np.int32), obs_format='u8')
+    for h in (hd, hh):
+        h.load_state(ob.map, ob.pose, ob.inv)
+    assert hd.obs.dtype == torch.uint8 and hd.obs_row_bytes < 4 * hd.obs_dim
+    assert np.array_equal(_u8_rows_to_vector(hd, hd.observe(), cfg_id), ob.observe())
+    n_act = np.array([cc.c.n_actions for cc in compiled])[ob.cfg_id.astype(np.int64)]
+    rng = np.random.RandomState(4)
+    for t in range(steps):
+        a = (rng.randint(0, 1 << 30, size=n) % n_act).astype(np.int32)
+        o_obs, o_rew, o_done, o_cost, o_res = ob.step(a, n_threads=8)
+        obs, rew, done, cost, res = hd.step(torch.from_numpy(a).cuda())
+        assert np.array_equal(_u8_rows_to_vector(hd, obs, cfg_id), o_obs), "device step %d" % t
+        assert np.array_equal(rew.cpu().numpy(), o_rew) and np.array_equal(done.cpu().numpy(), o_done)
+        hobs, hrew, hdone, hcost, hres = hh.step_host(a)
+        assert np.array_equal(_u8_rows_to_vector(hh, hobs, cfg_id), o_obs), "host step %d" % t
+        assert np.array_equal(hrew, o_rew) and np.array_equal(hres, o_res)
+    assert np.array_equal(hd.map.cpu().numpy().reshape(n, -1), ob.map) and np.array_equal(hh.inventory.cpu().numpy(), ob.inv)
+    if case == 'C5':                                                  # the queued auto-reset writes u8 rows too
+        hi = BatchHandle(compiled, n)                                 # int32 twin: same seed, same state, same steps
+        hi.load_state(*hd.export_state())
+        hi.episode.copy_(hd.episode)
+        for t in range(6):
+            a = torch.zeros(n, dtype=torch.int32, device='cuda')
+            obs = hd.step(a, auto_reset=True, max_episode_steps=3)[0]
+            ref = hi.step(a, auto_reset=True, max_episode_steps=3)[0]
+            assert np.array_equal(_u8_rows_to_vector(hd, obs), ref.cpu().numpy()[:, :hd.obs_dim]), "auto-reset step %d" % t
+        assert (hd.episode.cpu().numpy() == 2).all() and torch.equal(hd.map, hi.map)
+
+
+@pytest.mark.parametrize('tiles,warps', [(2, 2), (3, 1), (5, 2), (8, 4), (64, 2)])
+def test_multi_tile_ring_matches_one_tile_per_cta(tiles, warps):
+    """NGW_TILES: a CTA walks several tiles through the ring of shared-memory stages (loads one tile ahead, stores
+    draining behind).  Same results as the oracle for 2 (no reuse), 3..64 (stage reuse) tiles per CTA, partial last tile."""
+    os.environ['NGW_TILES'], os.environ['NGW_WARPS'] = str(tiles), str(warps)
+    try:
+        _parity_vs_oracle([_compiled(C2_DESC)], 32 * 37 + 5, 40, seed0=tiles * 100)
+        cc = _compiled(golden_util.get('bow_C3_axe_medium_fence_hard')['meta'])
+        _parity_vs_oracle([cc], 32 * 21 + 1, 24, seed0=tiles)
+        if tiles in (3, 8):
+            _parity_vs_oracle([_compiled(golden_util.get('pogo_ms40_additem_hard')['meta'])], 32 * 9 + 3, 16, seed0=7)
+    finally:
+        del os.environ['NGW_TILES'], os.environ['NGW_WARPS']
+
+
+@pytest.mark.parametrize('knob', ['NGW_NO_LINE_LIDAR', 'NGW_NO_FAST_LIDAR'])
+def test_older_lidar_paths_still_match(knob):
+    os.environ[knob] = '1'
+    try:
+        _parity_vs_oracle([_compiled(C2_DESC)], 1500, 32, seed0=5)
+        _parity_vs_oracle([_compiled(golden_util.get('pogo_ms40_additem_hard')['meta'])], 100, 16, seed0=6)
+    finally:
+        del os.environ[knob]
+
+
+def test_reset_then_host_step_is_ordered_after_the_reset():
+    """env.reset(); env.step(numpy_actions) — the host-buffer step runs on the handle's own stream and
+    must see the reset that was enqueued on the caller's stream.  Large batch, many rounds, compared with a handle
+    driven through the device path with explicit synchronisation."""
+    cc = _compiled(golden_util.get('pogo_ms40_additem_hard')['meta'])     # 1600-cell grids: a slow reset
+    n = 20000
+    a_host = np.random.RandomState(0).randint(0, cc.c.n_actions, size=n).astype(np.int32)
+    h1, h2 = BatchHandle([cc], n, seed=5), BatchHandle([cc], n, seed=5)
+    for rnd in range(4):
+        h1.reset()                                                    # no synchronize: step_host must order itself
+        got = [np.array(x) for x in h1.step_host(a_host)]
+        h2.reset()
+        torch.cuda.synchronize()
+        ref = [x.cpu().numpy() for x in h2.step(torch.from_numpy(a_host).cuda())]
+        torch.cuda.synchronize()
+        for x, y in zip(got, ref):
+            assert np.array_equal(x, y), "round %d" % rnd
+        assert torch.equal(h1.map, h2.map) and torch.equal(h1.inventory, h2.inventory) and torch.equal(h1.pose, h2.pose)
+        # and the other direction: a device-path call right after an unfinished host-path call
+        h1.step_host_begin(a_host)
+        d1 = [x.clone() for x in h1.step(torch.from_numpy(a_host).cuda())]
+        h1.step_host_end()
+        h2.step(torch.from_numpy(a_host).cuda())
+        d2 = h2.step(torch.from_numpy(a_host).cuda())
+        for x, y in zip(d1, d2):
+            assert torch.equal(x, y)
+
+
+def test_export_state_device_and_host_subrange():
+    cc = _compiled(C2_DESC)
+    n = 700
+    h = BatchHandle([cc], n, seed=9)
+    h.reset()
+    m, p, v = h.export_state()
+    assert torch.equal(m, h.map) and torch.equal(p, h.pose) and torch.equal(v, h.inventory)
+    m2, p2, v2 = h.export_state(first=100, count=333, host=True)
+    assert not m2.is_cuda and np.array_equal(m2.numpy(), h.map[100:433].cpu().numpy())
+    assert np.array_equal(p2.numpy(), h.pose[100:433].cpu().numpy()) and np.array_equal(v2.numpy(), h.inventory[100:433].cpu().numpy())
+    h2 = BatchHandle([cc], 333)
+    h2.load_state(m2, p2, v2)                                         # export -> load round trip
+    assert torch.equal(h2.map, h.map[100:433]) and torch.equal(h2.pose, h.pose[100:433])
+    with pytest.raises(RuntimeError):
+        h.export_state(first=600, count=200)
+
+
+def test_auto_reset_observation_is_the_reference_reset_observation():
+    """Quirk Q3 under auto-reset: AxeEasy wrapped outside LidarInFront patches the inventory AFTER the reset observation
+    was computed (novelty_wrappers.py:29-35), so the observation row of a regenerated env shows axe count 0 while the
+    state has 1 — the queued auto-reset must return what ngw_reset (and the reference's reset()) returns."""
+    cc = _compiled(golden_util.get('pogo_A_axe_easy_wooden')['meta'])
+    assert cc.c.reset_obs_after_ops < cc.c.n_reset_ops
+    n = 600
+    h = BatchHandle([cc], n, seed=21)
+    h.reset()
+    axe = [i for i, nm in enumerate(cc.item_names) if nm == 'wooden_axe'][0]
+    tail_pos = cc.c.n_lidar_items * cc.c.n_beams + [cc.c.inv_obs_item[i] for i in range(cc.c.n_inv_obs)].index(axe)
+    for t in range(4):
+        obs = h.step(torch.full((n,), 1, dtype=torch.int32, device='cuda'), auto_reset=True, max_episode_steps=2)[0]
+    o = obs.cpu().numpy()
+    assert (h.episode.cpu().numpy() == 3).all()
+    assert (h.inventory.cpu().numpy()[:, axe] == 1).all() and (o[:, tail_pos] == 0).all()
+    # the same rows from ngw_reset on a twin handle whose Philox counters are at the same episode
+    twin = BatchHandle([cc], n, seed=21)
+    for _ in range(3):
+        robs = twin.reset()
+    assert torch.equal(twin.map, h.map) and torch.equal(twin.pose, h.pose)
+    assert np.array_equal(robs.cpu().numpy(), o)
+
+
+def test_closed_loop_rollout_final_observation_is_clean():
+    """the observation returned by ngw_rollout_policy must not keep lidar slots of the previous
+    step's policy observation.  T is short so that most envs still move on the last step."""
+    cc = _compiled(C2_DESC)
+    n, A = 2000, cc.c.n_actions
+    rng = np.random.RandomState(8)
+    W = rng.randint(-9, 10, size=(cc.obs_dim, A)).astype(np.int32)
+    b = rng.randint(-30, 31, size=A).astype(np.int32)
+    for T in (1, 2, 3, 5):
+        ob = OracleBatch([cc], n)
+        ob.reset_legacy(4000 + T)
+        h = BatchHandle([cc], n)
+        h.load_state(ob.map, ob.pose, ob.inv)
+        out = h.rollout(T, policy=(W, b), record_actions=True)
+        changed = 0
+        for t in range(T):
+            before = ob.observe().astype(np.int64)
+            a = np.argmax(before @ W.astype(np.int64) + b, axis=1).astype(np.int32)
+            after = ob.step(a)[0]
+            changed = int((after != before).any(axis=1).sum())
+        assert changed > 20, "the last step must still change observations for this test to bite"
+        assert np.array_equal(out[0].cpu().numpy()[:, :cc.obs_dim], after), "T=%d" % T

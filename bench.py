@@ -411,8 +411,10 @@ def time_regions(wl, K, dev, world, floor_ms=VALUE_FLOOR_MS, n_streams=1, max_re
     import torch
     import torch.distributed as dist
     n_b = wl.n_batches
-    g_steps = min(K, GRAPH_STEPS)
-    g_steps -= g_steps % n_b if g_steps >= n_b else 0                   # whole rotations per replay
+    if K <= GRAPH_STEPS:
+        g_steps = K                                                     # the whole region is ONE graph of exactly K launches
+    else:
+        g_steps = GRAPH_STEPS - GRAPH_STEPS % n_b                       # whole rotations per replay
     g_steps = max(g_steps, 1)
     stream = torch.cuda.Stream(dev)
 

@@ -6,7 +6,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "ngw_reset.cuh"
@@ -28,11 +30,11 @@ struct ngw_handle {
     long long n = 0, np = 0, first_gid = 0;
     unsigned long long seed = 0;
     int ms = 0, cells = 0, inv_stride = 0, obs_dim = 0, n_cfgs = 0;
-    int map_bytes = 0, inv_bytes = 0, obs_bytes = 0, warps = 2, tiles_per_cta = 1;
+    int map_bytes = 0, inv_bytes = 0, obs_bytes = 0, warps = 2, tiles_per_cta = 0, lidar_mode = 0;
     int obs_u8 = 0, obs_row_bytes = 0;             // observation row layout (ngw_set_obs_format)
     int cache_hints = 3, dbg_skip = 0;
     bool use_tma = true, collect_stats = true, force_global_cfg = false, plain_store = false, use_pdl = true;
-    bool pdl_in_graph = true;
+    bool pdl_in_graph = true, early_state = true, pdl_early = true;
     bool lidar_uniform = false;
     DevConfig* d_cfgs = nullptr;
     std::vector<int16_t*> d_luts;
@@ -57,6 +59,34 @@ struct ngw_handle {
 // Device-path entry points run on the caller's stream, the host-buffer path on the handle's own non-blocking stream.
 // These two keep them ordered: a device-path call first waits for unfinished host-path work, and the host path waits
 // (on the device, through an event) for everything the latest device-path stream had been given.
+// Which handle issued the latest state-WRITING launch on a stream (step / rollout / reset / load_state / set_env_configs).
+// A one-step launch whose predecessor on its stream belongs to another handle may load its state before
+// griddepcontrol.wait (see step1_kernel): its own last writer is at least two launches back, and the predecessor — one
+// of this library's kernels, which trigger their dependents only after their own wait — cannot have started its body
+// before that writer had completed.  Launches the library cannot see (the caller's own kernels, copies) only add
+// distance.  The first launch of a stream capture is always conservative: a graph can be replayed after anything.
+static std::mutex g_order_mu;
+static std::unordered_map<cudaStream_t, std::pair<ngw_handle*, unsigned long long>> g_last_writer;   // stream -> (handle, capture id)
+
+static bool claim_stream(ngw_handle* h, cudaStream_t s, bool want_early) {
+    unsigned long long cap_id = 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamGetCaptureInfo(s, &cap, &cap_id) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    if (cap == cudaStreamCaptureStatusNone) cap_id = 0;
+    std::lock_guard<std::mutex> lk(g_order_mu);
+    auto it = g_last_writer.find(s);
+    const bool early = want_early && it != g_last_writer.end() && it->second.first != nullptr && it->second.first != h &&
+                       it->second.second == cap_id;
+    g_last_writer[s] = std::make_pair(h, cap_id);
+    return early;
+}
+
+static void forget_handle(ngw_handle* h) {
+    std::lock_guard<std::mutex> lk(g_order_mu);
+    for (auto& kv : g_last_writer)
+        if (kv.second.first == h) kv.second.first = nullptr;
+}
+
 static int before_device_call(ngw_handle* h, cudaStream_t s) {
     if (h->host_dirty) {
         if (cudaStreamSynchronize(h->hs) != cudaSuccess) { cudaGetLastError(); }
@@ -67,6 +97,10 @@ static int before_device_call(ngw_handle* h, cudaStream_t s) {
     return 0;
 }
 
+// for the entry points that write state with plain kernels / copies (no programmatic launch): the next step on this
+// stream must not load early if it belongs to the same handle
+static void note_state_writer(ngw_handle* h, cudaStream_t s) { claim_stream(h, s, false); }
+
 extern "C" {
 
 const char* ngw_last_error(void) { return g_err.c_str(); }
@@ -74,6 +108,7 @@ int ngw_abi_version(void) { return NGW_ABI_VERSION; }
 
 void ngw_destroy(ngw_handle* h) {
     if (!h) return;
+    forget_handle(h);
     cudaSetDevice(h->device);
     if (h->hs) cudaStreamSynchronize(h->hs);
     for (auto p : h->d_luts) cudaFree(p);
@@ -206,6 +241,8 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     h->plain_store = getenv("NGW_PLAIN_STORE") != nullptr;
     h->use_pdl = getenv("NGW_NO_PDL") == nullptr;
     h->pdl_in_graph = getenv("NGW_NO_PDL_GRAPH") == nullptr;
+    h->early_state = getenv("NGW_NO_EARLY_STATE") == nullptr;
+    h->pdl_early = getenv("NGW_NO_PDL_EARLY") == nullptr;   // trigger right after the wait: C2 7.70 -> 7.60 us/step
     // streaming data (each tile is read once and its observations written once per step) should not linger in L2:
     // measured on C2 9.15 -> 8.82 us/step, C3 29.3 -> 28.0, C5 278 -> 274 (hinting the inventory store as well: 9.0)
     h->cache_hints = getenv("NGW_HINTS") ? atoi(getenv("NGW_HINTS")) : 3;
@@ -278,37 +315,34 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     h->obs_bytes = 32 * h->obs_row_bytes;
     const int one_tile = NGW_SMEM_HDR + 512 + 1024 + h->map_bytes + h->inv_bytes + 128 * h->obs_dim;
     if (one_tile > 227 * 1024) return fail("ngw_create: map too large for shared memory");
-    // G warps share one tile (warp 0 steps, all G cast the lidar lines): 2 for small grids, 4 when shared memory
-    // limits the tiles per SM to a few
+    // G warps share one tile (the first two split the step by action class, all G cast the lidar lines): 2 for small
+    // grids, 4 when shared memory limits the tiles per SM to a few
     int tiles_per_sm = (227 * 1024) / (one_tile + 1024);
     int warps = tiles_per_sm >= 6 ? 2 : 4;
     if (const char* w = getenv("NGW_WARPS")) {                      // tuning knob: warps per tile
         int v = atoi(w);
-        if (v == 1 || v == 2 || v == 3 || v == 4 || v == 8) warps = v;
+        if (v == 1 || v == 2 || v == 4) warps = v;
     }
     h->warps = warps;
-    // tiles per CTA: a CTA walks several tiles through a ring of shared-memory stages (see step_kernel)
-    h->tiles_per_cta = 1;
-    if (const char* t = getenv("NGW_TILES")) {
+    h->tiles_per_cta = 0;                                           // 0 = chosen per launch (see launch_step1_nc)
+    if (const char* t = getenv("NGW_CTILES")) {                     // tuning knob: tile groups per CTA, 1..15
         int v = atoi(t);
-        if (v >= 1 && v <= 64) h->tiles_per_cta = v;
+        if (v >= 1 && v <= 15) h->tiles_per_cta = v;
     }
-    CK(cudaFuncSetAttribute(step_kernel<true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<true, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<true, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<true, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<false, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(step_kernel<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // line-gather lidar with one geometry for the whole batch (the common case): the kernel skips the per-lane dispatch
+    h->lidar_mode = 1;
+    for (int i = 0; i < n_cfgs; i++) {
+        const DevConfig& dc = h->h_cfgs[i];
+        if (dc.c.n_beams <= 0 || !dc.lidar.lines) h->lidar_mode = 0;
+    }
+    if (n_cfgs > 1 && !h->lidar_uniform) h->lidar_mode = 0;
+#define NGW_SMEM_ATTR(K) CK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+#define NGW_SMEM_ATTR4(K, T, O) NGW_SMEM_ATTR((K<T, 0, O>)); NGW_SMEM_ATTR((K<T, 1, O>)); NGW_SMEM_ATTR((K<T, 4, O>)); NGW_SMEM_ATTR((K<T, 16, O>))
+    NGW_SMEM_ATTR4(step1_kernel, true, true); NGW_SMEM_ATTR4(step1_kernel, true, false);
+    NGW_SMEM_ATTR4(step1_kernel, false, true);
+    NGW_SMEM_ATTR4(step_kernel, true, true); NGW_SMEM_ATTR4(step_kernel, false, true);
+#undef NGW_SMEM_ATTR4
+#undef NGW_SMEM_ATTR
     return 0;
 }
 
@@ -339,6 +373,7 @@ int ngw_set_env_configs(ngw_handle* h, const int32_t* cfg_id_dev, void* stream) 
     if (!h) return fail("null handle");
     CK(cudaSetDevice(h->device));
     before_device_call(h, (cudaStream_t)stream);
+    note_state_writer(h, (cudaStream_t)stream);
     int blocks = (int)((h->n + 255) / 256);
     set_cfg_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cfg_id_dev, h->cfg_id, h->n, h->n_cfgs, h->err);
     h->launches++;
@@ -353,6 +388,7 @@ int ngw_load_state(ngw_handle* h, const int8_t* map, const uint8_t* pose, const 
     CK(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     before_device_call(h, s);
+    note_state_writer(h, s);
     if (map) CK(cudaMemcpyAsync(h->map + first * h->cells, map, (size_t)count * h->cells, cudaMemcpyDeviceToDevice, s));
     if (pose) CK(cudaMemcpyAsync(h->pose + first, pose, (size_t)count * 4, cudaMemcpyDeviceToDevice, s));
     if (inventory)
@@ -393,6 +429,7 @@ int ngw_reset(ngw_handle* h, const uint8_t* mask, void* obs, void* stream) {
     CK(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     before_device_call(h, s);
+    note_state_writer(h, s);
     int blocks = (int)((h->n + 127) / 128);
     int rblocks = (int)((h->n + NGW_RESET_WARPS - 1) / NGW_RESET_WARPS);
     bool split = false;
@@ -446,42 +483,11 @@ static bool is_multi(const StepParams& p) {
     return p.n_steps > 1 || p.random_policy || p.done_count != nullptr || p.actions_out != nullptr || p.policy_w != nullptr;
 }
 
-template <int NC>
-static cudaError_t launch_step_nc(ngw_handle* h, StepParams p, cudaStream_t s) {
-    static thread_local StepArgs<NC> args;          // host staging of the argument block (copied by the launch); per thread,
-                                                    // so distinct handles stay independent across host threads
-    const bool multi = is_multi(p);
-    // ---- shared-memory plan: header | lidar tables | [reset scratch] | in_stages x (grid + inventory) | obs_stages x observation
-    const int in_bytes = p.map_bytes + p.inv_bytes;
-    const int luts = (NGW_MAX_MAP_SIZE + NGW_MAX_ITEMS * (NC > 0 ? NC : 0) + 127) & ~127;
-    p.off_luts = NGW_SMEM_HDR;
-    p.off_scratch = p.off_luts + luts;
-    p.off_in = p.off_scratch + (multi ? 1024 : 0);
-    const long long tiles = (p.env_end - p.env_begin + 31) / 32;
-    int T = multi ? 1 : h->tiles_per_cta;
-    if (T > tiles) T = (int)tiles;
-    int S = T <= 1 ? 1 : (T == 2 ? 2 : NGW_MAX_IN_STAGES), O = T <= 1 ? 1 : NGW_MAX_OBS_STAGES;
-    auto total = [&](int s_, int o_) { return (size_t)p.off_in + (size_t)s_ * in_bytes + (size_t)o_ * p.obs_bytes; };
-    if (total(S, O) > 227 * 1024) { S = 2; O = 1; }
-    if (total(S, O) > 227 * 1024) { S = 1; O = 1; T = 1; }
-    p.in_stages = S; p.obs_stages = O; p.tiles_per_cta = T;
-    p.off_obs = p.off_in + S * in_bytes;
-    p.n_tiles = (int)tiles;
-    const size_t smem = total(S, O);
-    const int blocks = (int)((tiles + T - 1) / T);
-    // the K-step rollout is all step logic (one lidar pass at the end): one warp per tile keeps more tiles resident
-    const int warps = (multi && smem * 12 <= 227 * 1024) ? 1 : h->warps;
-    args.p = p;
-    for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
-    cudaLaunchConfig_t lc;
-    memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3(blocks); lc.blockDim = dim3(32 * warps); lc.dynamicSmemBytes = smem;
-    lc.stream = s;
-    cudaLaunchAttribute attr[1];
+static void pdl_attr(ngw_handle* h, cudaStream_t s, cudaLaunchConfig_t& lc, cudaLaunchAttribute* attr) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    // PDL (trigger after the CTA's last tile, see the kernel): eager python loop 12.3 -> 10.2 us/step, CUDA-graph replay
-    // 9.95 -> 9.73 us/step on C2.  (An early trigger at kernel entry measured slower inside graphs.)
+    // PDL (trigger once a CTA's stores are issued, see the kernels): the next launch's prologue overlaps this launch's
+    // store phase; C2 CUDA-graph replay 9.3 -> 8.6 us/step.  (An early trigger at kernel entry measured slower.)
     bool pdl = h->use_pdl;
     if (pdl && !h->pdl_in_graph) {                  // A/B knob only: the capture query costs a driver call per launch
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -489,22 +495,109 @@ static cudaError_t launch_step_nc(ngw_handle* h, StepParams p, cudaStream_t s) {
         pdl = cap == cudaStreamCaptureStatusNone;
     }
     lc.attrs = attr; lc.numAttrs = pdl ? 1 : 0;
-    if (h->use_tma) {
-        if (multi) return cudaLaunchKernelEx(&lc, step_kernel<true, NC, true>, args);
-        return cudaLaunchKernelEx(&lc, step_kernel<true, NC, false>, args);
+}
+
+// K-step rollout launches (ngw_rollout / ngw_rollout_policy): one tile per CTA, tile resident across the steps
+template <int NC>
+static cudaError_t launch_rollout_nc(ngw_handle* h, StepParams p, cudaStream_t s) {
+    static thread_local StepArgs<NC> args;          // host staging of the argument block (copied by the launch); per thread,
+                                                    // so distinct handles stay independent across host threads
+    // ---- shared-memory plan: header | lidar tables | reset scratch | grid + inventory tile | observation tile
+    const int in_bytes = p.map_bytes + p.inv_bytes;
+    const int luts = (NGW_MAX_MAP_SIZE + NGW_MAX_ITEMS * (NC > 0 ? NC : 0) + 127) & ~127;
+    p.off_luts = NGW_SMEM_HDR;
+    p.off_scratch = p.off_luts + luts;
+    p.off_in = p.off_scratch + 1024;
+    const long long tiles = (p.env_end - p.env_begin + 31) / 32;
+    p.off_obs = p.off_in + in_bytes;
+    const size_t smem = (size_t)p.off_obs + p.obs_bytes;
+    // the K-step rollout is all step logic (one lidar pass at the end): one warp per tile keeps more tiles resident
+    const int warps = (smem * 12 <= 227 * 1024) ? 1 : h->warps;
+    claim_stream(h, s, false);
+    args.p = p;
+    for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)tiles); lc.blockDim = dim3(32 * warps); lc.dynamicSmemBytes = smem;
+    lc.stream = s;
+    cudaLaunchAttribute attr[1];
+    pdl_attr(h, s, lc, attr);
+    if (h->use_tma) return cudaLaunchKernelEx(&lc, step_kernel<true, NC, true>, args);
+    return cudaLaunchKernelEx(&lc, step_kernel<false, NC, true>, args);
+}
+
+// one-step launches (ngw_step / ngw_step_host / ngw_observe): several tile groups per CTA
+template <int NC>
+static cudaError_t launch_step1_nc(ngw_handle* h, StepParams p, cudaStream_t s) {
+    static thread_local StepArgs<NC> args;
+    // ---- shared-memory plan: CTA header | lidar tables | tiles_per_cta x (group header | grid | inventory | observation)
+    const int luts = (NGW_MAX_MAP_SIZE + NGW_MAX_ITEMS * (NC > 0 ? NC : 0) + 127) & ~127;
+    p.off_luts = NGW_CTA_HDR;
+    p.off_groups = p.off_luts + luts;
+    p.group_bytes = (NGW_GROUP_HDR + p.map_bytes + p.inv_bytes + p.obs_bytes + 127) & ~127;
+    const int G = h->warps;
+    p.g_shift = G == 4 ? 2 : (G == 2 ? 1 : 0);
+    const long long tiles = (p.env_end - p.env_begin + 31) / 32;
+    // Tile groups per CTA.  A launch that fits the GPU in ONE wave (C2: 2048 tiles, 14 per SM) is bound by launch and
+    // phase latency: an empty launch of 2048 one-tile CTAs costs 2.5 us, of 293 seven-tile CTAs 0.7 us — so the tiles are
+    // packed into two CTAs per SM.  A launch of several waves runs one tile per CTA: small CTAs retire independently,
+    // which staggers the load / compute / store phases of neighbouring tiles (C3 28.5 vs 31.7 us).
+    const long long per_sm = (227 * 1024 - p.off_groups) / p.group_bytes;
+    int C = h->tiles_per_cta;
+    if (C <= 0) {
+        if (tiles <= per_sm * h->sm_count && per_sm >= 4) {
+            C = (int)((tiles + 2 * h->sm_count - 1) / (2 * h->sm_count));
+            const int c_cap = (int)((113 * 1024 - p.off_groups) / p.group_bytes);
+            if (C > c_cap) C = c_cap;
+            if (C > 512 / (32 * G)) C = 512 / (32 * G);
+        } else {
+            C = 1;
+        }
     }
-    if (multi) return cudaLaunchKernelEx(&lc, step_kernel<false, NC, true>, args);
-    return cudaLaunchKernelEx(&lc, step_kernel<false, NC, false>, args);
+    if (!h->use_tma) C = 1;                         // the plain-copy A/B kernel exists as one tile per CTA only
+    if (C > 15) C = 15;
+    if (C > 512 / (32 * G)) C = 512 / (32 * G);
+    while (C > 1 && (size_t)p.off_groups + (size_t)C * p.group_bytes > 227 * 1024) C--;
+    if (C < 1) C = 1;
+    if (C > tiles) C = (int)tiles;
+    p.tiles_per_cta = C;
+    p.n_tiles = (int)tiles;
+    p.lidar_mode = h->lidar_mode;
+    // state loads before griddepcontrol.wait when the stream's previous state writer is another handle (observe-only
+    // launches write no state, but they are ordered like steps: they read it)
+    p.early_state = claim_stream(h, s, h->early_state && h->use_pdl) ? 1 : 0;
+    p.pdl_early = h->pdl_early ? 1 : 0;
+    const size_t smem = (size_t)p.off_groups + (size_t)C * p.group_bytes;
+    args.p = p;
+    for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)((tiles + C - 1) / C)); lc.blockDim = dim3(32 * G * C); lc.dynamicSmemBytes = smem;
+    lc.stream = s;
+    cudaLaunchAttribute attr[1];
+    pdl_attr(h, s, lc, attr);
+    if (C == 1) {
+        if (h->use_tma) return cudaLaunchKernelEx(&lc, step1_kernel<true, NC, true>, args);
+        return cudaLaunchKernelEx(&lc, step1_kernel<false, NC, true>, args);
+    }
+    return cudaLaunchKernelEx(&lc, step1_kernel<true, NC, false>, args);
 }
 
 static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
     if (p.env_end <= p.env_begin) return 0;
     int nc = h->force_global_cfg ? 0 : h->n_cfgs;
     cudaError_t e;
-    if (nc == 0 || nc > 16) e = launch_step_nc<0>(h, p, s);
-    else if (nc == 1) e = launch_step_nc<1>(h, p, s);
-    else if (nc <= 4) e = launch_step_nc<4>(h, p, s);
-    else e = launch_step_nc<16>(h, p, s);
+    if (is_multi(p)) {
+        if (nc == 0 || nc > 16) e = launch_rollout_nc<0>(h, p, s);
+        else if (nc == 1) e = launch_rollout_nc<1>(h, p, s);
+        else if (nc <= 4) e = launch_rollout_nc<4>(h, p, s);
+        else e = launch_rollout_nc<16>(h, p, s);
+    } else {
+        if (nc == 0 || nc > 16) e = launch_step1_nc<0>(h, p, s);
+        else if (nc == 1) e = launch_step1_nc<1>(h, p, s);
+        else if (nc <= 4) e = launch_step1_nc<4>(h, p, s);
+        else e = launch_step1_nc<16>(h, p, s);
+    }
     if (e != cudaSuccess) return fail(std::string("step kernel launch: ") + cudaGetErrorString(e));
     h->launches++;
     if (p.actions != nullptr && p.auto_reset && !is_multi(p)) {     // regenerate the episodes the step kernel queued

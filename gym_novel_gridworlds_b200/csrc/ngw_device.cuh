@@ -71,6 +71,7 @@ struct StepOut {
     int result;
     float cost;
     int msg;        // enum ngw_msg | argument << 5
+    int goal;       // the goal item is in the inventory after the step (done by success, not by fire / truncation)
 };
 
 __device__ __forceinline__ int msg_of(int code, int arg) { return code | (arg << 5); }
@@ -256,8 +257,8 @@ __device__ __forceinline__ void terminal_op(EnvRow& e, const ngw_config& cfg, co
 // "Update after each step" (pogostick_v1_env.py:349-357 and its copies in every intercepting novelty)
 __device__ __forceinline__ void post_step(EnvRow& e, const ngw_config& cfg, StepOut& o) {
     grab_entities(e, cfg);
-    o.done = 0;
-    if (e.inv[cfg.id_goal] >= 1) { o.reward = cfg.reward_done; o.done = 1; }
+    o.done = 0; o.goal = 0;
+    if (e.inv[cfg.id_goal] >= 1) { o.reward = cfg.reward_done; o.done = 1; o.goal = 1; }
 }
 
 // One full reference step() through the flattened wrapper chain.  Layers are walked outermost-first
@@ -307,7 +308,7 @@ __device__ __forceinline__ void step_env(EnvRow& e, const ngw_config& cfg, const
         post_step(e, cfg, o);
         first_post = n - 1;
     } else {
-        o.reward = -1; o.result = 0; o.cost = 3600.0f; o.done = 0; o.msg = 0;
+        o.reward = -1; o.result = 0; o.cost = 3600.0f; o.done = 0; o.msg = 0; o.goal = 0;
         first_post = stop;
     }
     for (int i = first_post; i >= 0; i--) {
@@ -382,32 +383,53 @@ template <> __device__ __forceinline__ int mask_msb<uint32_t>(uint32_t x) { retu
 template <> __device__ __forceinline__ int mask_msb<uint64_t>(uint64_t x) { return 63 - __clzll((long long)x); }
 
 // occupancy of the four lines through (r, c); bit i = cell of the line in grid row i (row line: grid column i).
-// kSafe clamps the diagonal addresses into the row (cold kernels on global memory); the step kernel's shared-memory
-// rows have >= ms bytes of readable padding on both sides, and out-of-grid bits are masked off either way.
-template <typename MaskT, int MS, bool kSafe>
-__device__ __forceinline__ void gather_lines(const int8_t* m, int ms_rt, int r, int c, int sel, MaskT& row, MaskT& col,
+// MS > 0 / SEL >= 0 fix the map size / the set of lines at compile time (fully unrolled, immediate offsets, no
+// predication); kSafe clamps the diagonal addresses into the row (cold kernels on global memory) — the step kernel's
+// shared-memory rows have >= ms bytes of readable padding on both sides, and out-of-grid bits are masked off either way.
+template <typename MaskT, int MS, int SEL, bool kSafe>
+__device__ __forceinline__ void gather_lines(const int8_t* m, int ms_rt, int r, int c, int sel_rt, MaskT& row, MaskT& col,
                                              MaskT& dg, MaskT& an) {
     const int ms = MS > 0 ? MS : ms_rt;
-    const int8_t* prow = m + r * ms;
-    const int8_t* pcol = m + c;
-    const int8_t* pdg = m + (c - r);                                  // row i: column c - r + i
-    const int8_t* pan = m + (c + r);                                  // row i: column c + r - i
+    const int sel = SEL >= 0 ? SEL : sel_rt;
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(m);
+    const uint8_t* prow = base + r * ms;
+    const uint8_t* pcol = base + c;
+    const uint8_t* pdg = base + (c - r);                              // row i: column c - r + i
+    const uint8_t* pan = base + (c + r);                              // row i: column c + r - i
     row = 0; col = 0; dg = 0; an = 0;
-    const bool s0 = sel & 1, s1 = sel & 2, s2 = sel & 4, s3 = sel & 8;
+    if (SEL >= 0) {                                                   // one fused, fully unrolled pass over the chosen lines
 #pragma unroll
-    for (int i = 0; i < ms; i++) {
-        const MaskT bit = (MaskT)1 << i;
-        if (s0 && prow[i] != 0) row |= bit;
-        if (s1 && pcol[i * ms] != 0) col |= bit;
-        if (kSafe) {
-            int cd = c - r + i, ca = c + r - i;
-            cd = cd < 0 ? 0 : (cd > ms - 1 ? ms - 1 : cd);
-            ca = ca < 0 ? 0 : (ca > ms - 1 ? ms - 1 : ca);
-            if (s2 && m[i * ms + cd] != 0) dg |= bit;
-            if (s3 && m[i * ms + ca] != 0) an |= bit;
-        } else {
-            if (s2 && pdg[i * (ms + 1)] != 0) dg |= bit;
-            if (s3 && pan[i * (ms - 1)] != 0) an |= bit;
+        for (int i = 0; i < ms; i++) {
+            const MaskT bit = (MaskT)1 << i;
+            if (sel & 1) { if (prow[i] != 0) row |= bit; }
+            if (sel & 2) { if (pcol[i * ms] != 0) col |= bit; }
+            if (sel & 4) { if (pdg[i * (ms + 1)] != 0) dg |= bit; }
+            if (sel & 8) { if (pan[i * (ms - 1)] != 0) an |= bit; }
+        }
+    } else {                                                          // any size / any subset: one loop per line, `sel` is warp-uniform
+        if (sel & 1) {
+#pragma unroll 8
+            for (int i = 0; i < ms; i++) if (prow[i] != 0) row |= (MaskT)1 << i;
+        }
+        if (sel & 2) {
+#pragma unroll 8
+            for (int i = 0; i < ms; i++) if (pcol[i * ms] != 0) col |= (MaskT)1 << i;
+        }
+        if (sel & 4) {
+#pragma unroll 8
+            for (int i = 0; i < ms; i++) {
+                int cd = c - r + i;
+                if (kSafe) cd = cd < 0 ? 0 : (cd > ms - 1 ? ms - 1 : cd);
+                if (base[i * ms + cd] != 0) dg |= (MaskT)1 << i;
+            }
+        }
+        if (sel & 8) {
+#pragma unroll 8
+            for (int i = 0; i < ms; i++) {
+                int ca = c + r - i;
+                if (kSafe) ca = ca < 0 ? 0 : (ca > ms - 1 ? ms - 1 : ca);
+                if (base[i * ms + ca] != 0) an |= (MaskT)1 << i;
+            }
         }
     }
     // rows whose diagonal cell lies outside the grid: r - c <= i <= r - c + ms - 1, resp. c + r - ms + 1 <= i <= c + r
@@ -426,25 +448,25 @@ __device__ __forceinline__ void line_beams(MaskT occ, int p, int stride, const i
     const MaskT lo = occ & (((MaskT)1 << p) - 1);
     const int n_pos = mask_ffs<MaskT>(hi);                            // cells to the first non-air cell, 0 = none
     const int n_neg = lo != 0 ? p - mask_msb<MaskT>(lo) : 0;
+    // no early-outs: a beam that sees nothing (n == 0) reads the agent's own cell — air, whose slot is -1
 #pragma unroll
     for (int side = 0; side < 2; side++) {
         const int n = side ? n_neg : n_pos;
         const int a = side ? a_neg : a_pos;
-        if (n == 0) continue;
-        const int k = diagonal ? (int)luts.firstk[n - 1] : (n <= K ? n : 0);   // obsw:52-58: sample index of that cell
-        if (k == 0) continue;                                         // beyond max_beam_range
+        const int k = diagonal ? (int)luts.firstk[n - 1] : (n <= K ? n : 0);   // obsw:52-58: sample index of that cell, 0 = beyond max_beam_range
         const int id = here[side ? -n * stride : n * stride];
         const int slot = luts.slot[id];                               // -1: occludes but is not a lidar item (Q2)
-        if (slot >= 0) obs.put(((a - rot) & 7) * L + slot, k);
+        if (slot >= 0 && n != 0 && k != 0) obs.put(((a - rot) & 7) * L + slot, k);
     }
 }
 
-template <typename MaskT, int MS, bool kSafe>
+template <typename MaskT, int MS, int SEL, bool kSafe>
 __device__ __forceinline__ void lidar_lines_t(const EnvRow& e, const ngw_config& cfg, const LidarDev& t,
-                                              const LidarLuts& luts, const ObsRow& obs, int sel) {
+                                              const LidarLuts& luts, const ObsRow& obs, int sel_rt) {
     MaskT row, col, dg, an;
-    gather_lines<MaskT, MS, kSafe>(e.m, e.ms, e.r, e.c, sel, row, col, dg, an);
+    gather_lines<MaskT, MS, SEL, kSafe>(e.m, e.ms, e.r, e.c, sel_rt, row, col, dg, an);
     const int ms = MS > 0 ? MS : e.ms;
+    const int sel = SEL >= 0 ? SEL : sel_rt;
     const int K = cfg.max_range, L = cfg.n_lidar_items;
     const int rot = (int)((*reinterpret_cast<const uint32_t*>(t.rot) >> (8 * e.facing)) & 7u);   // one uniform table read
     const int8_t* here = e.m + e.r * ms + e.c;
@@ -455,13 +477,16 @@ __device__ __forceinline__ void lidar_lines_t(const EnvRow& e, const ngw_config&
     if (sel & 8) line_beams<MaskT>(an, e.r, ms - 1, here, true, 7, 3, K, L, rot, luts, obs);
 }
 
+// `sel` is warp-uniform.  The hot shapes (the reference's 10x10 grid; all four lines, or the axis / diagonal halves of
+// a two-warp tile) get fully unrolled, unpredicated code; everything else shares two generic loops.
 template <bool kSafe>
 __device__ __forceinline__ void lidar_lines(const EnvRow& e, const ngw_config& cfg, const LidarDev& t,
                                             const LidarLuts& luts, const ObsRow& obs, int sel) {
-    if (e.ms == 10) lidar_lines_t<uint32_t, 10, kSafe>(e, cfg, t, luts, obs, sel);      // the reference's default grid
-    else if (e.ms <= 32) lidar_lines_t<uint32_t, 0, kSafe>(e, cfg, t, luts, obs, sel);
-    else if (e.ms == 40) lidar_lines_t<uint64_t, 40, kSafe>(e, cfg, t, luts, obs, sel);
-    else lidar_lines_t<uint64_t, 0, kSafe>(e, cfg, t, luts, obs, sel);
+    if (!kSafe && e.ms == 10 && sel == 0xF) lidar_lines_t<uint32_t, 10, 0xF, false>(e, cfg, t, luts, obs, sel);
+    else if (!kSafe && e.ms == 10 && sel == 0x3) lidar_lines_t<uint32_t, 10, 0x3, false>(e, cfg, t, luts, obs, sel);
+    else if (!kSafe && e.ms == 10 && sel == 0xC) lidar_lines_t<uint32_t, 10, 0xC, false>(e, cfg, t, luts, obs, sel);
+    else if (e.ms <= 32) lidar_lines_t<uint32_t, 0, -1, kSafe>(e, cfg, t, luts, obs, sel);
+    else lidar_lines_t<uint64_t, 0, -1, kSafe>(e, cfg, t, luts, obs, sel);
 }
 
 // which of the four lines warp g of G handles (bit 0 row, 1 column, 2 diagonal, 3 anti-diagonal)
@@ -519,6 +544,33 @@ __device__ __forceinline__ void lidar_fast(const EnvRow& e, const ngw_config& cf
     }
 }
 
+// inventory tail of the observation (observation_wrappers.py:77-78): quantities in sorted-name order minus unbreakables (Q7)
+__device__ __forceinline__ void obs_tail(const EnvRow& e, const ngw_config& cfg, const ObsRow& obs) {
+    const int n_tail = cfg.n_inv_obs;
+    int32_t* tail = obs.tail(cfg.n_lidar_items * cfg.n_beams);
+    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(&cfg.inv_obs_item[0]);     // four item ids per table read
+    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(&cfg.inv_obs_item[4]);
+    const int first = (int)(w0 & 0xFF);
+    // item ids follow the sorted names (pogostick_v1_env.py:200-212), so without late-injected items the tail is the
+    // id range first .. first + n - 1: then the copy needs no table
+    const bool contiguous = n_tail <= 8 && ((w0 - 0x01010101u * (uint32_t)first) == 0x03020100u) &&
+                            (n_tail <= 4 || ((w1 - 0x01010101u * (uint32_t)first) & (0xFFFFFFFFu >> (8 * (8 - n_tail)))) ==
+                                                (0x07060504u & (0xFFFFFFFFu >> (8 * (8 - n_tail)))));
+    if (contiguous && n_tail >= 4) {
+        const int32_t* src = e.inv + first;
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (i < n_tail) tail[i] = src[i];
+        return;
+    }
+    int i = 0;
+    for (; i + 4 <= n_tail; i += 4) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(&cfg.inv_obs_item[i]);
+        const int v0 = e.inv[w & 0xFF], v1 = e.inv[(w >> 8) & 0xFF], v2 = e.inv[(w >> 16) & 0xFF], v3 = e.inv[w >> 24];
+        tail[i] = v0; tail[i + 1] = v1; tail[i + 2] = v2; tail[i + 3] = v3;
+    }
+    for (; i < n_tail; i++) tail[i] = e.inv[cfg.inv_obs_item[i]];
+}
+
 // `tables`: the beam tables to walk with — the env's own config, or (mixed batches whose configs all share one lidar
 // geometry) config 0's, so that the table reads stay warp-uniform even when the lanes of a warp differ in config.
 // `luts` (line path only): where the per-lane indexed slot / firstk tables live; luts.slot == nullptr selects the
@@ -555,11 +607,7 @@ __device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& 
             }
         }
     }
-    if (with_tail) {
-        const int n_tail = cfg.n_inv_obs;
-        int32_t* tail = obs.tail(L * B);
-        for (int i = 0; i < n_tail; i++) tail[i] = e.inv[cfg.inv_obs_item[i]];   // sorted-name order (Q7)
-    }
+    if (with_tail) obs_tail(e, cfg, obs);
 }
 
 // ------------------------------------------------------------------ reset (pogostick_v1_env.py:86-181 + novelty resets)

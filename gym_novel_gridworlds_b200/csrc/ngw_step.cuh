@@ -103,16 +103,19 @@ struct StepParams {
     int map_bytes, inv_bytes, obs_bytes;                 // bytes of one 32-env tile of each array
     int obs_row_bytes, obs_u8;                           // observation row layout (NGW_OBS_I32 / NGW_OBS_U8)
     // shared-memory carve-up (bytes from the start of dynamic shared memory), all multiples of 128
-    int off_luts, off_scratch, off_in, off_obs;
-    int in_stages, obs_stages;  // input (grid + inventory) buffers / observation buffers per CTA
-    int tiles_per_cta;          // a CTA handles tiles blockIdx.x, blockIdx.x + gridDim.x, ... (tiles_per_cta of them at most)
-    int n_tiles;
+    int off_luts, off_scratch, off_in, off_obs;          // rollout kernel (one tile per CTA)
+    int off_groups, group_bytes;                         // one-step kernel: tile group k lives at off_groups + k * group_bytes
+    int tiles_per_cta, g_shift, n_tiles;                 // one-step kernel: tile groups per CTA, log2(warps per tile), tiles
+    int lidar_mode;             // 1: every config takes the line-gather path with one shared geometry (the common case)
+    int early_state;            // 1: this handle's state is complete already, state loads may precede griddepcontrol.wait
+    int pdl_early;              // 1: trigger the dependent launch right after the wait (A/B knob NGW_PDL_EARLY)
     int auto_reset, max_episode_steps;
     int lidar_uniform;          // every config has the same beam tables (then config 0's are read, warp-uniformly)
     int cache_hints;            // bit 0: state tiles are loaded L2::evict_first, bit 1: the observation tile is stored evict_first
     int plain_store;            // 1 => write tiles back with ordinary coalesced stores instead of TMA bulk stores
     int dbg_skip;               // attribution knob (NGW_SKIP, results are then WRONG): 1 step, 2 lidar, 4 outputs + statistics,
-                                // 8 observation store, 16 inventory store
+                                // 8 observation store, 16 inventory store, 64 return after griddepcontrol.wait,
+                                // 128 return once the tile has landed
     // K-step rollout (n_steps > 1 or random policy): the tile stays in shared memory across the steps
     int n_steps;                // steps per launch (1 for ngw_step)
     int random_policy;          // 1 => actions drawn on the device (Philox), `actions` is only a non-null marker
@@ -138,8 +141,6 @@ struct StepArgs {
 
 #define NGW_STAT_SLOTS 512
 #define NGW_SMEM_HDR 256            // mbarriers, zero pad, pose hand-over
-#define NGW_MAX_IN_STAGES 3
-#define NGW_MAX_OBS_STAGES 2
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -222,36 +223,48 @@ __device__ __forceinline__ int linear_policy_action(const StepParams& p, const n
 }
 
 // ------------------------------------------------------------------ the fused step + LidarInFront kernel
-// A tile = 32 consecutive envs; lane l of every warp owns env l of the tile; G = blockDim.x / 32 warps share a tile:
-// warp 0 runs the flattened step, then all G warps cast the LidarInFront beams of their lane's env (G = 1: one warp
-// does everything).  A CTA handles up to tiles_per_cta tiles (blockIdx.x, blockIdx.x + gridDim.x, ...) through a ring of
-// in_stages input buffers (grid + inventory rows, TMA loads one tile ahead) and obs_stages observation buffers, so the
-// loads of the next tile and the stores of the previous one overlap this tile's compute INSIDE one launch.
+// One CTA = one tile of 32 consecutive envs; lane l of every warp owns env l of the tile; G = blockDim.x / 32 warps
+// share the tile.  With G >= 2 the step itself is split by ACTION CLASS: warp 0 executes the lanes whose action is a
+// turn / craft / select, warp 1 the lanes that move or touch the block in front — each warp then walks only half of
+// the divergent per-action paths, on disjoint envs.  After one barrier all G warps cast the LidarInFront lines of their
+// lane's env (G = 2: axis lines / diagonal lines).  (Measured and rejected, see profiles/README.md: several tiles per
+// CTA through a ring of staged buffers — the kernel is bound by per-tile latency, not by bandwidth.)
+#define NGW_CLASS1_OPS ((1u << NGW_OP_FORWARD) | (1u << NGW_OP_BREAK) | (1u << NGW_OP_PLACE_TREE_TAP) | \
+                        (1u << NGW_OP_EXTRACT_RUBBER) | (1u << NGW_OP_EXTRACT_STRING) | (1u << NGW_OP_CHOP) | (1u << NGW_OP_JUMP))
+
 template <bool kTma, int NC, bool kMulti>
 __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepArgs<NC> args) {
     extern __shared__ __align__(128) unsigned char smem[];
     const StepParams& p = args.p;
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, G = blockDim.x >> 5;
+    const long long e0 = p.env_begin + (long long)blockIdx.x * 32;
+    const long long e = e0 + lane;
+    const bool valid = e < p.env_end;
+    const bool full_tile = e0 + 32 <= p.env_end;
     const bool stepping = p.actions != nullptr;
 
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);              // [NGW_MAX_IN_STAGES] "tile landed" barriers
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);               // "tile landed" barrier
     int8_t* szero = reinterpret_cast<int8_t*>(smem + 32);            // 8 bytes that always read 0 (landed lidar beams park here)
     uchar4* spose = reinterpret_cast<uchar4*>(smem + 64);            // pose after the step, for the other warps
     uint8_t* sfirstk = smem + p.off_luts;                            // lidar tables read with per-lane indices
     int8_t* sslot = reinterpret_cast<int8_t*>(smem + p.off_luts + NGW_MAX_MAP_SIZE);
     uint32_t* sscratch = reinterpret_cast<uint32_t*>(smem + p.off_scratch);   // radix-select histogram (rollout only)
-    const int in_bytes = p.map_bytes + p.inv_bytes;
+    int8_t* smap = reinterpret_cast<int8_t*>(smem + p.off_in);
+    int32_t* sinv = reinterpret_cast<int32_t*>(smem + p.off_in + p.map_bytes);
+    unsigned char* sobs = smem + p.off_obs;
 
-    // ---- prologue without global state: barriers, zero pad, lidar tables, zeroed observation tiles
+    // ---- prologue without global state: barrier, zero pad, lidar tables, zeroed observation tile
+    const int8_t* gmap = p.map + e0 * p.cells;
+    int32_t* ginv = p.inv + e0 * p.inv_stride;
     if (threadIdx.x == 0) {
-        if (kTma)
-            for (int s = 0; s < p.in_stages; s++) mbar_init(&bars[s], 1);
+        if (kTma) mbar_init(bar, 1);
         *reinterpret_cast<uint64_t*>(szero) = 0ull;
     }
     if (NC > 0) {                                                    // config tables are kernel arguments (constant bank)
         if (threadIdx.x < NGW_MAX_MAP_SIZE / 4)
             reinterpret_cast<uint32_t*>(sfirstk)[threadIdx.x] =
                 reinterpret_cast<const uint32_t*>(args.cfg[0].lidar.firstk)[threadIdx.x];
+#pragma unroll
         for (int k = 0; k < NC; k++)
             if (threadIdx.x < NGW_MAX_ITEMS / 4)
                 reinterpret_cast<uint32_t*>(sslot + k * NGW_MAX_ITEMS)[threadIdx.x] =
@@ -259,270 +272,540 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
     }
     if (p.obs != nullptr) {
         const uint4 z = make_uint4(0, 0, 0, 0);
-        uint4* o4 = reinterpret_cast<uint4*>(smem + p.off_obs);
-        for (int i = threadIdx.x; i < ((p.obs_bytes * p.obs_stages) >> 4); i += blockDim.x) o4[i] = z;
+        uint4* o4 = reinterpret_cast<uint4*>(sobs);
+        const int n16 = p.obs_bytes >> 4;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) o4[i] = z;
     }
     __syncthreads();                                                 // barrier init visible before anyone waits on it
     asm volatile("griddepcontrol.wait;" ::: "memory");               // previous kernel of the stream done + visible
+    if (p.dbg_skip & 64) { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); return; }
 
-    const int n_mine = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int n_iter = n_mine < p.tiles_per_cta ? n_mine : p.tiles_per_cta;
+    // ---- stage the tile: grid rows + inventory rows (state arrays are padded, a full tile is always readable)
     uint64_t pol_first = 0;
-    if (kTma && threadIdx.x == 0) {
-        if (p.cache_hints) pol_first = policy_evict_first();
-        // stage the first tiles: grid rows + inventory rows (state arrays are padded, a full tile is always readable)
-        const int n_pre = n_iter < p.in_stages ? n_iter : p.in_stages;
-        for (int it = 0; it < n_pre; it++) {
-            const long long t0 = p.env_begin + ((long long)blockIdx.x + (long long)it * gridDim.x) * 32;
-            unsigned char* dst = smem + p.off_in + it * in_bytes;
-            mbar_expect_tx(&bars[it], (uint32_t)in_bytes);
+    if (kTma) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, (uint32_t)(p.map_bytes + p.inv_bytes));
+            if (p.cache_hints) pol_first = policy_evict_first();
             if (p.cache_hints & 1) {
-                bulk_g2s_hint(dst, p.map + t0 * p.cells, (uint32_t)p.map_bytes, &bars[it], pol_first);
-                bulk_g2s_hint(dst + p.map_bytes, p.inv + t0 * p.inv_stride, (uint32_t)p.inv_bytes, &bars[it], pol_first);
+                bulk_g2s_hint(smap, gmap, (uint32_t)p.map_bytes, bar, pol_first);
+                bulk_g2s_hint(sinv, ginv, (uint32_t)p.inv_bytes, bar, pol_first);
             } else {
-                bulk_g2s(dst, p.map + t0 * p.cells, (uint32_t)p.map_bytes, &bars[it]);
-                bulk_g2s(dst + p.map_bytes, p.inv + t0 * p.inv_stride, (uint32_t)p.inv_bytes, &bars[it]);
+                bulk_g2s(smap, gmap, (uint32_t)p.map_bytes, bar);
+                bulk_g2s(sinv, ginv, (uint32_t)p.inv_bytes, bar);
             }
+        }
+    } else {
+        const uint4* s4 = reinterpret_cast<const uint4*>(gmap);
+        uint4* d4 = reinterpret_cast<uint4*>(smap);
+        for (int i = threadIdx.x; i < (p.map_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
+        s4 = reinterpret_cast<const uint4*>(ginv);
+        d4 = reinterpret_cast<uint4*>(sinv);
+        for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
+    }
+
+    // ---- while the copies fly: per-lane scalars
+    const int n_cls = (!kMulti && G >= 2) ? 2 : 1;                   // warps that take part in the step
+    const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[e];
+    const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
+    const ngw_config& cfg = dc.c;
+    const LidarDev& beam_tables = (NC > 1 && p.lidar_uniform) ? args.cfg[0].lidar : dc.lidar;
+    LidarLuts luts;
+    if (NC > 0) {
+        luts.slot = sslot + cfg_i * NGW_MAX_ITEMS;
+        luts.firstk = (NC == 1 || p.lidar_uniform) ? sfirstk : nullptr;
+        if (luts.firstk == nullptr) luts.slot = nullptr;              // heterogeneous beam tables: pointer-walking path
+    } else {
+        luts.slot = p.dcfgs[cfg_i].c.lidar_slot;
+        luts.firstk = p.dcfgs[cfg_i].lidar.firstk;
+    }
+    ObsRow orow;
+    orow.p = sobs + lane * p.obs_row_bytes;
+    orow.u8 = p.obs_u8;
+    uchar4 ps = make_uchar4(0, 0, 0, 0);
+    int action = 0;
+    if (g < n_cls) {
+        ps = p.pose[e];
+        const bool given_actions = !(kMulti && (p.random_policy || p.policy_w != nullptr));   // else `actions` is a marker
+        if (stepping && valid && given_actions) action = p.actions[e];
+    }
+
+    if (kTma) mbar_wait(bar, 0);
+    else __syncthreads();
+    if (p.dbg_skip & 128) { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); return; }
+
+    StepOut st_out;                                                  // one-step kernel: outputs and statistics are written
+    st_out.reward = 0; st_out.done = 0; st_out.result = 0; st_out.cost = 0.0f; st_out.msg = 0; st_out.goal = 0;   // after the tile stores
+    int st_success = 0, st_reset = 0, st_invalid = 0;
+    bool mine = false;                                               // this warp stepped this lane's env
+    EnvRow env;
+    env.m = smap + lane * p.cells;
+    env.gm = p.map + e * p.cells;
+    env.inv = sinv + lane * p.inv_stride;
+    env.ms = p.ms;
+
+    if (g < n_cls) {
+        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+        if (stepping) {
+            StepOut o;
+            o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0; o.goal = 0;
+            float reward_sum = 0.0f, cost_sum = 0.0f;
+            int done_count = 0;
+            const int n_steps = kMulti ? p.n_steps : 1;               // kMulti == false: the plain one-step kernel
+            const bool random_policy = kMulti && p.random_policy;
+            const bool closed_loop = kMulti && p.policy_w != nullptr;
+            for (int t = 0; t < n_steps; t++) {
+                int next_action = 0;                                  // prefetch the next step's action behind this step
+                if (!random_policy && !closed_loop && t + 1 < n_steps && valid)
+                    next_action = p.actions[(t + 1) * p.act_stride + e];
+                if (closed_loop) {                                    // observe, then greedy linear policy (int32 rows only)
+                    int32_t* row = reinterpret_cast<int32_t*>(orow.p);
+                    for (int j = 0; j < p.obs_dim; j++) row[j] = 0;
+                    if (valid && cfg.n_beams > 0) lidar_observe<false>(env, dc, beam_tables, luts, orow, szero, 0, 1, true);
+                    if (valid) action = linear_policy_action(p, cfg, row);
+                } else if (random_policy && valid) {                  // uniform over the config's action ids
+                    Philox pr;
+                    pr.init(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, 0xFFF);
+                    action = (int)pr.below((uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
+                }
+                if (kMulti && p.actions_out != nullptr && valid) p.actions_out[t * p.act_stride + e] = action;
+                o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0; o.goal = 0;
+                int invalid = 0, did_reset = 0, success = 0;
+                ngw_action_entry a;
+                a.op = NGW_OP_INVALID;
+                if (valid && action >= 0 && action < cfg.n_actions) {
+                    uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
+                    memcpy(&a, &raw, sizeof(a));
+                }
+                // action class of the lane: which of the stepping warps executes it
+                mine = valid && (n_cls == 1 || (int)((NGW_CLASS1_OPS >> a.op) & 1u) == g);
+                if (mine) {
+                    if (a.op == NGW_OP_INVALID) {                     // wrappers.py:76 / pogostick_v1_env.py:236 would raise
+                        invalid = 1;
+                        p.err[e] |= NGW_ERR_INVALID_ACTION;
+                    } else {
+                        if (!(p.dbg_skip & 1)) step_env(env, cfg, a, o);
+                        success = o.done && env.inv[cfg.id_goal] >= 1;
+                        int finished = o.done;
+                        if (p.max_episode_steps > 0) {
+                            int len = p.ep_len[e] + 1;
+                            if (len >= p.max_episode_steps) { finished = 1; o.done = 1; } // harness truncation knob
+                            p.ep_len[e] = finished && p.auto_reset ? 0 : len;
+                        }
+                        if (finished && p.auto_reset) { did_reset = 1; }
+                    }
+                    ps = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
+                                     (unsigned char)env.sel);
+                    reward_sum += (float)o.reward; cost_sum += o.cost; done_count += o.done;
+                }
+                if (p.auto_reset) {
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, did_reset);
+                    if (bal != 0 && !kMulti) {
+                        // single step: queue the finished envs; reset_list_kernel (next in the stream, one warp per env at
+                        // full occupancy) regenerates them and overwrites their observation rows
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(p.reset_count, __popc(bal));
+                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                        if (did_reset) p.reset_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)e;
+                    } else if (bal != 0) {
+                        // rollout: the next step needs the new episode now -> regenerate in place, warp-cooperatively
+                        auto_reset_warp(p, p.dcfgs, cfg_i, did_reset != 0, smap, sinv, sscratch, e0, ps);
+                        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+                    }
+                }
+                if (kMulti && p.stats != nullptr)
+                    tile_stats(p.stats, (int)blockIdx.x, lane, valid, o.done, success, did_reset, invalid, o.reward, o.cost);
+                if (!kMulti) { st_success = success; st_reset = did_reset; st_invalid = invalid; }
+                action = next_action;
+            }
+            if (closed_loop) {                                        // the last policy observation must not leak into the final one
+                int32_t* row = reinterpret_cast<int32_t*>(orow.p);
+                for (int j = 0; j < p.obs_dim; j++) row[j] = 0;
+            }
+            if (!kMulti) st_out = o;                                  // one-step kernel: outputs are stored after the tile stores
+            if (kMulti && valid) {
+                p.pose[e] = ps;
+                p.reward[e] = reward_sum;
+                p.done[e] = (uint8_t)o.done;
+                p.cost[e] = cost_sum;
+                p.result[e] = (uint8_t)o.result;
+                if (p.done_count != nullptr) p.done_count[e] = done_count;
+                if (p.msg != nullptr) p.msg[e] = (uint16_t)o.msg;
+            }
+        }
+        // hand the pose over: the warp that stepped the lane (or, when nothing was stepped, warp 0) publishes it
+        if (G > 1 && (stepping ? (mine || (g == 0 && !valid)) : g == 0)) spose[lane] = ps;
+    }
+    if (G > 1) {
+        __syncthreads();                                             // step results (grid, inventory, pose) visible to all warps
+        ps = spose[lane];
+        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+    }
+
+    // ---- LidarInFront observation of the (possibly auto-reset) state into the shared-memory tile
+    if (p.obs != nullptr && valid && cfg.n_beams > 0 && !(p.dbg_skip & 2))
+        lidar_observe<false>(env, dc, beam_tables, luts, orow, szero, g, G, g == G - 1);
+
+    // ---- write back: inventory tile (only when stepping) and observation tile.  Every thread orders its generic-proxy
+    //      writes to the tiles before the async proxy reads them (fence before the barrier), then one thread issues.
+    if (kTma) fence_async_smem();
+    __syncthreads();
+    if (kTma && full_tile && !p.plain_store) {
+        if (threadIdx.x == 0) {
+            if (stepping && !(p.dbg_skip & 16)) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
+            if (p.obs != nullptr && !(p.dbg_skip & 8)) {
+                unsigned char* gobs = p.obs + e0 * p.obs_row_bytes;
+                if (p.cache_hints & 2) bulk_s2g_hint(gobs, sobs, (uint32_t)p.obs_bytes, pol_first);
+                else bulk_s2g(gobs, sobs, (uint32_t)p.obs_bytes);
+            }
+            bulk_commit();
+        }
+    } else {
+        if (stepping) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
+            uint4* d4 = reinterpret_cast<uint4*>(ginv);
+            for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
+        }
+        if (p.obs != nullptr) {
+            const int n = (int)((p.env_end - e0 < 32 ? p.env_end - e0 : 32)) * (p.obs_row_bytes >> 2);
+            uint32_t* gobs = reinterpret_cast<uint32_t*>(p.obs + e0 * p.obs_row_bytes);
+            const uint32_t* so = reinterpret_cast<const uint32_t*>(sobs);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) gobs[i] = so[i];
         }
     }
 
-    for (int it = 0; it < n_iter; it++) {
-        const int stage = it % p.in_stages, ostage = it % p.obs_stages;
-        const long long e0 = p.env_begin + ((long long)blockIdx.x + (long long)it * gridDim.x) * 32;
-        const long long e = e0 + lane;
-        const bool valid = e < p.env_end;
-        const bool full_tile = e0 + 32 <= p.env_end;
-        int8_t* smap = reinterpret_cast<int8_t*>(smem + p.off_in + stage * in_bytes);
-        int32_t* sinv = reinterpret_cast<int32_t*>(smem + p.off_in + stage * in_bytes + p.map_bytes);
-        unsigned char* sobs = smem + p.off_obs + ostage * p.obs_bytes;
-        const int8_t* gmap = p.map + e0 * p.cells;
-        int32_t* ginv = p.inv + e0 * p.inv_stride;
-
-        if (it > 0 && (it >= p.obs_stages || it + 1 >= p.in_stages)) {
-            // ring reuse: the bulk stores of an earlier tile must have finished READING their buffers before this tile's
-            // observation buffer is zeroed again and before the load of tile it+1 lands in that tile's input stage.
-            // With 3 input / 2 observation stages that is tile it-2 (the stores of tile it-1 may still be draining).
-            if (kTma && threadIdx.x == 0) {
-                if (p.in_stages >= 3 && p.obs_stages >= 2) bulk_wait_read<1>();
-                else bulk_wait_read<0>();
-            }
-            __syncthreads();
-            if (p.obs != nullptr && it >= p.obs_stages) {
-                const uint4 z = make_uint4(0, 0, 0, 0);
-                uint4* o4 = reinterpret_cast<uint4*>(sobs);
-                for (int i = threadIdx.x; i < (p.obs_bytes >> 4); i += blockDim.x) o4[i] = z;
-            }
+    // ---- per-env outputs and episode statistics, behind the tile stores: each stepping warp writes the lanes it stepped
+    if (!kMulti && g < n_cls && stepping && !(p.dbg_skip & 4)) {
+        if (mine) {
+            p.pose[e] = ps;
+            p.reward[e] = (float)st_out.reward;
+            p.done[e] = (uint8_t)st_out.done;
+            p.cost[e] = st_out.cost;
+            p.result[e] = (uint8_t)st_out.result;
+            if (p.msg != nullptr) p.msg[e] = (uint16_t)st_out.msg;
         }
+        if (p.stats != nullptr)
+            tile_stats(p.stats, (int)blockIdx.x + g * 7, lane, mine, st_out.done, st_success, st_reset, st_invalid,
+                       st_out.reward, st_out.cost);
+    }
+
+    // Programmatic dependent launch: this tile's work is issued, let the next kernel of the stream start scheduling its
+    // CTAs; its prologue (up to griddepcontrol.wait) touches no global state, so it overlaps this kernel's store phase.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (kTma && threadIdx.x == 0) bulk_wait_read<0>();               // shared memory must outlive the bulk stores' reads
+}
+
+
+
+// ------------------------------------------------------------------ the ONE-STEP kernel (ngw_step / ngw_observe)
+// The hot kernel.  One CTA = tiles_per_cta TILE GROUPS that run concurrently and independently; a tile group = G warps
+// (1, 2 or 4) working on one tile of 32 consecutive envs, lane l of every warp owning env l.  Per group:
+//   prologue   mbarrier init, zeroed observation tile (no global state is touched before griddepcontrol.wait)
+//   load       two TMA bulk copies bring the tile's grid rows and inventory rows into shared memory
+//   step       split by ACTION CLASS over the first two warps: warp 0 executes the lanes whose action is a turn / craft /
+//              select, warp 1 the lanes that move or touch the block in front — each walks half of the divergent paths
+//   lidar      after one group barrier all G warps cast the LidarInFront lines of their lane's env (G = 2: axis / diagonals)
+//   store      two TMA bulk stores (inventory tile, observation tile), then warp 0 writes the per-env outputs of ALL lanes
+//              (handed over through shared memory, so the stores are full 128-byte lines) and folds the statistics
+// Several groups per CTA exist because an empty launch of one-tile CTAs already costs 3.4 us on C2 (2048 CTA launches of
+// 64 threads); with 7 groups per CTA the same tiles are 293 CTAs.  Groups synchronise with their own named barrier
+// (bar.sync 1 + group), never with the whole CTA after the prologue.
+struct TileOut {            // per-env hand-over from the warp that stepped the lane: 16 bytes
+    uchar4 ps;              // pose after the step
+    uint32_t bits;          // reward (int16) | done << 16 | result << 17 | success << 18 | reset << 19 | invalid << 20 | stepped << 21
+    float cost;
+    uint32_t msg;
+};
+#define NGW_GROUP_HDR 640   // mbarrier (8) | zero pad (8) | .. | TileOut[32] at +64 | pad to a multiple of 128
+#define NGW_CTA_HDR 128     // per-CTA statistics accumulators
+
+// kOne: the CTA is a single tile group, which synchronises on barrier 0 — a register-indexed bar.sync makes ptxas
+// reserve all 16 named barriers, and 64 / 16 = 4 such CTAs per SM is too few when every CTA is one tile.
+template <bool kOne>
+__device__ __forceinline__ void group_sync(int grp, int G) {
+    if (G == 1) __syncwarp();
+    else if (kOne) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(G * 32) : "memory");
+}
+
+template <bool kTma, int NC, bool kOne>
+__global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ StepArgs<NC> args) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const StepParams& p = args.p;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int G = 1 << p.g_shift;
+    const int grp = wid >> p.g_shift, g = wid & (G - 1);
+    const int gt = threadIdx.x & (32 * G - 1);                        // thread index inside the tile group
+    const int tile = (int)blockIdx.x * p.tiles_per_cta + grp;
+    const bool active = tile < p.n_tiles;
+    const long long e0 = p.env_begin + (long long)tile * 32;
+    const long long e = e0 + lane;
+    const bool valid = active && e < p.env_end;
+    const bool full_tile = e0 + 32 <= p.env_end;
+    const bool stepping = p.actions != nullptr;
+
+    int* scta = reinterpret_cast<int*>(smem);                         // [0] counts a, [1] counts b, [2] reward, [3] cost (float), [4] groups done
+    uint8_t* sfirstk = smem + p.off_luts;                             // lidar tables read with per-lane indices
+    int8_t* sslot = reinterpret_cast<int8_t*>(smem + p.off_luts + NGW_MAX_MAP_SIZE);
+    unsigned char* gbase = smem + p.off_groups + grp * p.group_bytes;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(gbase);               // "tile landed" barrier
+    int8_t* szero = reinterpret_cast<int8_t*>(gbase + 8);             // 8 bytes that always read 0 (landed lidar beams park here)
+    TileOut* sout = reinterpret_cast<TileOut*>(gbase + 64);
+    int8_t* smap = reinterpret_cast<int8_t*>(gbase + NGW_GROUP_HDR);
+    int32_t* sinv = reinterpret_cast<int32_t*>(gbase + NGW_GROUP_HDR + p.map_bytes);
+    unsigned char* sobs = gbase + NGW_GROUP_HDR + p.map_bytes + p.inv_bytes;
+
+    // ---- prologue without global state: barriers, zero pad, lidar tables
+    if (threadIdx.x < 8) scta[threadIdx.x] = 0;
+    if (gt == 0) {
+        if (kTma) mbar_init(bar, 1);
+        *reinterpret_cast<uint64_t*>(szero) = 0ull;
+    }
+    if (NC > 0) {                                                     // config tables are kernel arguments (constant bank)
+        if (threadIdx.x < NGW_MAX_MAP_SIZE / 4)
+            reinterpret_cast<uint32_t*>(sfirstk)[threadIdx.x] =
+                reinterpret_cast<const uint32_t*>(args.cfg[0].lidar.firstk)[threadIdx.x];
+#pragma unroll
+        for (int k = 0; k < NC; k++)
+            if (threadIdx.x < NGW_MAX_ITEMS / 4)
+                reinterpret_cast<uint32_t*>(sslot + k * NGW_MAX_ITEMS)[threadIdx.x] =
+                    reinterpret_cast<const uint32_t*>(args.cfg[k].c.lidar_slot)[threadIdx.x];
+    }
+    __syncthreads();                                                  // the only CTA-wide barrier
+
+    // ---- stage the tile: grid rows + inventory rows (state arrays are padded, a full tile is always readable).
+    // p.early_state: the launch that precedes this one in the stream does not belong to this handle, so this handle's
+    // state was last written at least two launches back and is complete and visible already (the predecessor passed its
+    // own griddepcontrol.wait before it let this launch start): the state loads go out BEFORE the wait and overlap the
+    // predecessor's tail.  Otherwise they follow the wait.
+    const int8_t* gmap = p.map + e0 * p.cells;
+    int32_t* ginv = p.inv + e0 * p.inv_stride;
+    uint64_t pol_first = 0;
+    auto issue_loads = [&]() {
         if (kTma) {
-            // one tile ahead: tile it+1 goes into the stage tile it-2 used (in_stages == 3) unless the prologue staged it
-            const int nx = it + 1;
-            if (threadIdx.x == 0 && nx < n_iter && nx >= p.in_stages) {
-                const int ns = nx % p.in_stages;
-                const long long t0 = p.env_begin + ((long long)blockIdx.x + (long long)nx * gridDim.x) * 32;
-                unsigned char* dst = smem + p.off_in + ns * in_bytes;
-                mbar_expect_tx(&bars[ns], (uint32_t)in_bytes);
+            if (gt == 0) {
+                mbar_expect_tx(bar, (uint32_t)(p.map_bytes + p.inv_bytes));
+                if (p.cache_hints) pol_first = policy_evict_first();
                 if (p.cache_hints & 1) {
-                    bulk_g2s_hint(dst, p.map + t0 * p.cells, (uint32_t)p.map_bytes, &bars[ns], pol_first);
-                    bulk_g2s_hint(dst + p.map_bytes, p.inv + t0 * p.inv_stride, (uint32_t)p.inv_bytes, &bars[ns], pol_first);
+                    bulk_g2s_hint(smap, gmap, (uint32_t)p.map_bytes, bar, pol_first);
+                    bulk_g2s_hint(sinv, ginv, (uint32_t)p.inv_bytes, bar, pol_first);
                 } else {
-                    bulk_g2s(dst, p.map + t0 * p.cells, (uint32_t)p.map_bytes, &bars[ns]);
-                    bulk_g2s(dst + p.map_bytes, p.inv + t0 * p.inv_stride, (uint32_t)p.inv_bytes, &bars[ns]);
+                    bulk_g2s(smap, gmap, (uint32_t)p.map_bytes, bar);
+                    bulk_g2s(sinv, ginv, (uint32_t)p.inv_bytes, bar);
                 }
             }
         } else {
             const uint4* s4 = reinterpret_cast<const uint4*>(gmap);
             uint4* d4 = reinterpret_cast<uint4*>(smap);
-            for (int i = threadIdx.x; i < (p.map_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
+            for (int i = gt; i < (p.map_bytes >> 4); i += 32 * G) d4[i] = s4[i];
             s4 = reinterpret_cast<const uint4*>(ginv);
             d4 = reinterpret_cast<uint4*>(sinv);
-            for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
+            for (int i = gt; i < (p.inv_bytes >> 4); i += 32 * G) d4[i] = s4[i];
         }
+    };
+    const int n_cls = G >= 2 ? 2 : 1;                                 // warps that take part in the step
+    uchar4 ps = make_uchar4(0, 0, 0, 0);
+    const bool early = p.early_state && active && !(p.dbg_skip & 64);
+    if (early) {
+        issue_loads();
+        if (g < n_cls) ps = p.pose[e];
+    }
+    if (p.obs != nullptr) {                                           // the group zeroes its observation tile while the loads fly
+        uint32_t a = smem_u32(sobs) + (uint32_t)gt * 16u;
+        const uint32_t end = smem_u32(sobs) + (uint32_t)p.obs_bytes, st = 512u * (uint32_t)G;
+        for (; a + 3u * st < end; a += 4u * st) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + st), "r"(0) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + 2u * st), "r"(0) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + 3u * st), "r"(0) : "memory");
+        }
+        for (; a < end; a += st) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");                // previous kernel of the stream done + visible
+    if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!active || (p.dbg_skip & 64)) { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); return; }
+    if (!early) issue_loads();
 
-        // ---- while the copies fly: per-lane scalars
-        const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[e];
-        const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
-        const ngw_config& cfg = dc.c;
-        const LidarDev& beam_tables = (NC > 1 && p.lidar_uniform) ? args.cfg[0].lidar : dc.lidar;
-        LidarLuts luts;
-        if (NC > 0) {
-            luts.slot = sslot + cfg_i * NGW_MAX_ITEMS;
-            luts.firstk = (NC == 1 || p.lidar_uniform) ? sfirstk : nullptr;
-            if (luts.firstk == nullptr) luts.slot = nullptr;          // heterogeneous beam tables: pointer-walking path
-        } else {
-            luts.slot = p.dcfgs[cfg_i].c.lidar_slot;
-            luts.firstk = p.dcfgs[cfg_i].lidar.firstk;
+    // ---- while the copies fly: per-lane scalars
+    const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[e];
+    const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
+    const ngw_config& cfg = dc.c;
+    int action = 0;
+    if (g < n_cls) {
+        if (!early) ps = p.pose[e];
+        if (stepping && valid) action = p.actions[e];
+    }
+
+    if (kTma) mbar_wait(bar, 0);
+    else group_sync<kOne>(grp, G);
+    if (p.dbg_skip & 128) { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); return; }
+
+    EnvRow env;
+    env.m = smap + lane * p.cells;
+    env.gm = p.map + e * p.cells;
+    env.inv = sinv + lane * p.inv_stride;
+    env.ms = p.ms;
+
+    if (g < n_cls) {
+        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+        bool mine = !stepping && g == 0;                              // this warp publishes this lane's hand-over record
+        uint32_t bits = 0;
+        StepOut o;
+        o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0; o.goal = 0;
+        if (stepping) {
+            ngw_action_entry a;
+            a.op = NGW_OP_INVALID;
+            if (valid && action >= 0 && action < cfg.n_actions) {
+                uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
+                memcpy(&a, &raw, sizeof(a));
+            }
+            // action class of the lane: which of the stepping warps executes it (lanes past the batch end: warp 0)
+            mine = n_cls == 1 || (int)((NGW_CLASS1_OPS >> a.op) & 1u) == g;
+            int did_reset = 0;
+            if (mine && valid) {
+                bits = 1u << 21;
+                if (a.op == NGW_OP_INVALID) {                         // wrappers.py:76 / pogostick_v1_env.py:236 would raise
+                    bits |= 1u << 20;
+                    p.err[e] |= NGW_ERR_INVALID_ACTION;
+                } else {
+                    if (!(p.dbg_skip & 1)) step_env(env, cfg, a, o);
+                    if (o.goal) bits |= 1u << 18;
+                    int finished = o.done;
+                    if (p.max_episode_steps > 0) {
+                        int len = p.ep_len[e] + 1;
+                        if (len >= p.max_episode_steps) { finished = 1; o.done = 1; }   // harness truncation knob
+                        p.ep_len[e] = finished && p.auto_reset ? 0 : len;
+                    }
+                    if (finished && p.auto_reset) { did_reset = 1; bits |= 1u << 19; }
+                }
+                ps = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
+                                 (unsigned char)env.sel);
+                bits |= ((uint32_t)o.reward & 0xFFFFu) | ((uint32_t)o.done << 16) | ((uint32_t)o.result << 17);
+            }
+            if (p.auto_reset) {
+                // queue the finished envs; reset_list_kernel (next in the stream, one warp per env at full occupancy)
+                // regenerates them and overwrites their observation rows
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, did_reset);
+                if (bal != 0) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(p.reset_count, __popc(bal));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (did_reset) p.reset_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)e;
+                }
+            }
         }
+        if (mine) {                                                   // one 16-byte record per lane, written by its stepping warp
+            TileOut t;
+            t.ps = ps; t.bits = bits; t.cost = o.cost; t.msg = (uint32_t)o.msg;
+            *reinterpret_cast<uint4*>(&sout[lane]) = *reinterpret_cast<uint4*>(&t);
+        }
+    }
+    group_sync<kOne>(grp, G);                                               // step results (grid, inventory, hand-over) visible to the group
+    ps = sout[lane].ps;
+    env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+
+    // ---- LidarInFront observation of the new state into the shared-memory tile
+    if (p.obs != nullptr && valid && cfg.n_beams > 0 && !(p.dbg_skip & 2)) {
         ObsRow orow;
         orow.p = sobs + lane * p.obs_row_bytes;
         orow.u8 = p.obs_u8;
-        uchar4 ps = make_uchar4(0, 0, 0, 0);
-        int action = 0;
-        if (g == 0) {
-            ps = p.pose[e];
-            const bool given_actions = !(kMulti && (p.random_policy || p.policy_w != nullptr));   // else `actions` is a marker
-            if (stepping && valid && given_actions) action = p.actions[e];
-        }
-
-        if (kTma) mbar_wait(&bars[stage], (uint32_t)((it / p.in_stages) & 1));
-        else __syncthreads();
-
-        StepOut st_out;                                              // one-step kernel: statistics are folded after the lidar,
-        st_out.reward = 0; st_out.done = 0; st_out.result = 0; st_out.cost = 0.0f; st_out.msg = 0;   // off the path to the barrier
-        int st_success = 0, st_reset = 0, st_invalid = 0;
-        EnvRow env;
-        env.m = smap + lane * p.cells;
-        env.gm = p.map + e * p.cells;
-        env.inv = sinv + lane * p.inv_stride;
-        env.ms = p.ms;
-
-        if (g == 0) {
-            env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
-            if (stepping) {
-                StepOut o;
-                o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0;
-                float reward_sum = 0.0f, cost_sum = 0.0f;
-                int done_count = 0;
-                const int n_steps = kMulti ? p.n_steps : 1;           // kMulti == false: the plain one-step kernel
-                const bool random_policy = kMulti && p.random_policy;
-                const bool closed_loop = kMulti && p.policy_w != nullptr;
-                for (int t = 0; t < n_steps; t++) {
-                    int next_action = 0;                              // prefetch the next step's action behind this step
-                    if (!random_policy && !closed_loop && t + 1 < n_steps && valid)
-                        next_action = p.actions[(t + 1) * p.act_stride + e];
-                    if (closed_loop) {                                // observe, then greedy linear policy (int32 rows only)
-                        int32_t* row = reinterpret_cast<int32_t*>(orow.p);
-                        for (int j = 0; j < p.obs_dim; j++) row[j] = 0;
-                        if (valid && cfg.n_beams > 0) lidar_observe<false>(env, dc, beam_tables, luts, orow, szero, 0, 1, true);
-                        if (valid) action = linear_policy_action(p, cfg, row);
-                    } else if (random_policy && valid) {              // uniform over the config's action ids
-                        Philox pr;
-                        pr.init(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, 0xFFF);
-                        action = (int)pr.below((uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
-                    }
-                    if (kMulti && p.actions_out != nullptr && valid) p.actions_out[t * p.act_stride + e] = action;
-                    o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0;
-                    int invalid = 0, did_reset = 0, success = 0;
-                    if (valid) {
-                        ngw_action_entry a;
-                        a.op = NGW_OP_INVALID;
-                        if (action >= 0 && action < cfg.n_actions) {
-                            uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
-                            memcpy(&a, &raw, sizeof(a));
-                        }
-                        if (a.op == NGW_OP_INVALID) {                 // wrappers.py:76 / pogostick_v1_env.py:236 would raise
-                            invalid = 1;
-                            p.err[e] |= NGW_ERR_INVALID_ACTION;
-                        } else {
-                            if (!(p.dbg_skip & 1)) step_env(env, cfg, a, o);
-                            success = o.done && env.inv[cfg.id_goal] >= 1;
-                            int finished = o.done;
-                            if (p.max_episode_steps > 0) {
-                                int len = p.ep_len[e] + 1;
-                                if (len >= p.max_episode_steps) { finished = 1; o.done = 1; } // harness truncation knob
-                                p.ep_len[e] = finished && p.auto_reset ? 0 : len;
-                            }
-                            if (finished && p.auto_reset) { did_reset = 1; }
-                        }
-                        ps = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
-                                         (unsigned char)env.sel);
-                        reward_sum += (float)o.reward; cost_sum += o.cost; done_count += o.done;
-                    }
-                    if (p.auto_reset) {
-                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, did_reset);
-                        if (bal != 0 && !kMulti) {
-                            // single step: queue the finished envs; reset_list_kernel (next in the stream, one warp per env at
-                            // full occupancy) regenerates them and overwrites their observation rows
-                            int base = 0;
-                            if (lane == 0) base = atomicAdd(p.reset_count, __popc(bal));
-                            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                            if (did_reset) p.reset_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)e;
-                        } else if (bal != 0) {
-                            // rollout: the next step needs the new episode now -> regenerate in place, warp-cooperatively
-                            auto_reset_warp(p, p.dcfgs, cfg_i, did_reset != 0, smap, sinv, sscratch, e0, ps);
-                            env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
-                        }
-                    }
-                    if (kMulti && p.stats != nullptr)
-                        tile_stats(p.stats, (int)blockIdx.x, lane, valid, o.done, success, did_reset, invalid, o.reward, o.cost);
-                    if (!kMulti) { st_success = success; st_reset = did_reset; st_invalid = invalid; }
-                    action = next_action;
-                }
-                if (closed_loop) {                                    // the last policy observation must not leak into the final one
-                    int32_t* row = reinterpret_cast<int32_t*>(orow.p);
-                    for (int j = 0; j < p.obs_dim; j++) row[j] = 0;
-                }
-                if (!kMulti) st_out = o;                              // one-step kernel: outputs are stored after the lidar
-                if (kMulti && valid) {
-                    p.pose[e] = ps;
-                    p.reward[e] = reward_sum;
-                    p.done[e] = (uint8_t)o.done;
-                    p.cost[e] = cost_sum;
-                    p.result[e] = (uint8_t)o.result;
-                    if (p.done_count != nullptr) p.done_count[e] = done_count;
-                    if (p.msg != nullptr) p.msg[e] = (uint16_t)o.msg;
-                }
-            }
-            if (G > 1) spose[lane] = ps;
-        }
-        if (G > 1) {
-            __syncthreads();                                         // step results (grid, inventory, pose) visible to all warps
-            ps = spose[lane];
-            env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
-        }
-
-        // ---- LidarInFront observation of the (possibly auto-reset) state into the shared-memory tile
-        if (p.obs != nullptr && valid && cfg.n_beams > 0 && !(p.dbg_skip & 2))
-            lidar_observe<false>(env, dc, beam_tables, luts, orow, szero, g, G, g == G - 1);
-
-        // ---- write back: inventory tile (only when stepping) and observation tile.  Every thread orders its generic-proxy
-        //      writes to the tiles before the async proxy reads them (fence before the barrier), then one thread issues.
-        if (kTma) fence_async_smem();
-        __syncthreads();
-        if (kTma && full_tile && !p.plain_store) {
-            if (threadIdx.x == 0) {
-                if (stepping && !(p.dbg_skip & 16)) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
-                if (p.obs != nullptr && !(p.dbg_skip & 8)) {
-                    unsigned char* gobs = p.obs + e0 * p.obs_row_bytes;
-                    if (p.cache_hints & 2) bulk_s2g_hint(gobs, sobs, (uint32_t)p.obs_bytes, pol_first);
-                    else bulk_s2g(gobs, sobs, (uint32_t)p.obs_bytes);
-                }
-                bulk_commit();
-            }
+        LidarLuts luts;
+        if (NC > 0) { luts.slot = sslot + cfg_i * NGW_MAX_ITEMS; luts.firstk = sfirstk; }
+        else { luts.slot = p.dcfgs[cfg_i].c.lidar_slot; luts.firstk = p.dcfgs[cfg_i].lidar.firstk; }
+        if (p.lidar_mode == 1) {                                      // every config: line gather, one shared geometry
+            const int sel = lidar_line_share(g, G);
+            if (sel) lidar_lines<false>(env, cfg, (NC > 0) ? args.cfg[0].lidar : dc.lidar, luts, orow, sel);
+            if (g == G - 1) obs_tail(env, cfg, orow);
         } else {
-            if (stepping) {
-                const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
-                uint4* d4 = reinterpret_cast<uint4*>(ginv);
-                for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
-            }
-            if (p.obs != nullptr) {
-                const int n = (int)((p.env_end - e0 < 32 ? p.env_end - e0 : 32)) * (p.obs_row_bytes >> 2);
-                uint32_t* gobs = reinterpret_cast<uint32_t*>(p.obs + e0 * p.obs_row_bytes);
-                const uint32_t* so = reinterpret_cast<const uint32_t*>(sobs);
-                for (int i = threadIdx.x; i < n; i += blockDim.x) gobs[i] = so[i];
-            }
-            if (it + 1 < n_iter) __syncthreads();                    // plain copies read the buffers: done before any reuse
+            if (NC > 1 && !p.lidar_uniform) luts.slot = nullptr;      // heterogeneous beam tables: pointer-walking path
+            lidar_observe<false>(env, dc, (NC > 1 && p.lidar_uniform) ? args.cfg[0].lidar : dc.lidar, luts, orow, szero,
+                                 g, G, g == G - 1);
         }
-        if (!kMulti && g == 0 && stepping && !(p.dbg_skip & 4)) {    // outputs and statistics, behind the tile stores
-            if (valid) {
-                p.pose[e] = ps;
-                p.reward[e] = (float)st_out.reward;
-                p.done[e] = (uint8_t)st_out.done;
-                p.cost[e] = st_out.cost;
-                p.result[e] = (uint8_t)st_out.result;
-                if (p.msg != nullptr) p.msg[e] = (uint16_t)st_out.msg;
-            }
-            if (p.stats != nullptr)
-                tile_stats(p.stats, (int)(e0 >> 5), lane, valid, st_out.done, st_success, st_reset, st_invalid, st_out.reward,
-                           st_out.cost);
-        }
-
-        // Programmatic dependent launch: this CTA's compute is done, let the next kernel of the stream start scheduling its
-        // CTAs; its prologue (up to griddepcontrol.wait) touches no global state, so it overlaps this kernel's store phase.
-        if (it == n_iter - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
-    if (n_iter == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (kTma && threadIdx.x == 0) bulk_wait_read<0>();               // shared memory must outlive the bulk stores' reads
-}
 
+    // ---- write back: inventory tile (only when stepping) and observation tile.  Every thread orders its generic-proxy
+    //      writes to the tiles before the async proxy reads them (fence before the barrier), then one thread issues.
+    if (kTma) fence_async_smem();
+    group_sync<kOne>(grp, G);
+    if (kTma && full_tile && !p.plain_store) {
+        if (gt == 0) {
+            if (stepping && !(p.dbg_skip & 16)) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
+            if (p.obs != nullptr && !(p.dbg_skip & 8)) {
+                unsigned char* gobs = p.obs + e0 * p.obs_row_bytes;
+                if (p.cache_hints & 2) bulk_s2g_hint(gobs, sobs, (uint32_t)p.obs_bytes, pol_first);
+                else bulk_s2g(gobs, sobs, (uint32_t)p.obs_bytes);
+            }
+            bulk_commit();
+        }
+    } else {
+        if (stepping) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
+            uint4* d4 = reinterpret_cast<uint4*>(ginv);
+            for (int i = gt; i < (p.inv_bytes >> 4); i += 32 * G) d4[i] = s4[i];
+        }
+        if (p.obs != nullptr) {
+            const int n = (int)((p.env_end - e0 < 32 ? p.env_end - e0 : 32)) * (p.obs_row_bytes >> 2);
+            uint32_t* gobs = reinterpret_cast<uint32_t*>(p.obs + e0 * p.obs_row_bytes);
+            const uint32_t* so = reinterpret_cast<const uint32_t*>(sobs);
+            for (int i = gt; i < n; i += 32 * G) gobs[i] = so[i];
+        }
+    }
+
+    // ---- per-env outputs (full lines, one warp) and episode statistics, behind the tile stores
+    if (g == 0 && stepping && !(p.dbg_skip & 4)) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(&sout[lane]);
+        const uint32_t bits = raw.y;
+        const int reward = (int)(short)(bits & 0xFFFFu);
+        const float cost = __uint_as_float(raw.z);
+        if (valid) {
+            p.pose[e] = *reinterpret_cast<const uchar4*>(&raw.x);
+            p.reward[e] = (float)reward;
+            p.done[e] = (uint8_t)((bits >> 16) & 1u);
+            p.cost[e] = cost;
+            p.result[e] = (uint8_t)((bits >> 17) & 1u);
+            if (p.msg != nullptr) p.msg[e] = (uint16_t)raw.w;
+        }
+        if (p.stats != nullptr) {
+            // warp reductions, then shared-memory accumulators of the CTA; the last group to arrive flushes them with one
+            // set of global atomics per CTA
+            const uint32_t stepped = valid ? (bits >> 21) & 1u : 0u;
+            const uint32_t a_cnt = stepped | ((valid ? (bits >> 16) & 1u : 0u) << 10) | (((bits >> 18) & 1u) << 20);     // steps | episodes | successes
+            const uint32_t b_cnt = ((bits >> 19) & 1u) | (((bits >> 20) & 1u) << 10);                                       // resets | invalid
+            const uint32_t a_sum = __reduce_add_sync(0xFFFFFFFFu, valid ? a_cnt : 0u);
+            const uint32_t b_sum = __reduce_add_sync(0xFFFFFFFFu, valid ? b_cnt : 0u);
+            const int r_sum = __reduce_add_sync(0xFFFFFFFFu, valid ? reward : 0);
+            const float c_sum = warp_sum(valid ? cost : 0.0f);
+            if (lane == 0) {
+                atomicAdd(&scta[0], (int)a_sum);
+                atomicAdd(&scta[1], (int)b_sum);
+                atomicAdd(&scta[2], r_sum);
+                atomicAdd(reinterpret_cast<float*>(&scta[3]), c_sum);
+                __threadfence_block();
+                const int n_groups = min(p.tiles_per_cta, p.n_tiles - (int)blockIdx.x * p.tiles_per_cta);
+                if (atomicAdd(&scta[4], 1) == n_groups - 1) {
+                    __threadfence_block();
+                    const int a_tot = *reinterpret_cast<volatile int*>(&scta[0]), b_tot = *reinterpret_cast<volatile int*>(&scta[1]);
+                    const int r_tot = *reinterpret_cast<volatile int*>(&scta[2]);
+                    const float c_tot = *reinterpret_cast<volatile float*>(&scta[3]);
+                    const int n_step = a_tot & 1023, n_done = (a_tot >> 10) & 1023, n_succ = (a_tot >> 20) & 1023;
+                    const int n_reset = b_tot & 1023, n_inv = (b_tot >> 10) & 1023;
+                    double* sg = p.stats + (size_t)(blockIdx.x % NGW_STAT_SLOTS) * NGW_STAT_COUNT;
+                    atomicAdd(&sg[NGW_STAT_STEPS], (double)(n_step - n_inv));
+                    atomicAdd(&sg[NGW_STAT_REWARD_SUM], (double)r_tot);
+                    atomicAdd(&sg[NGW_STAT_COST_SUM], (double)c_tot);
+                    if (n_done) atomicAdd(&sg[NGW_STAT_EPISODES], (double)n_done);
+                    if (n_succ) atomicAdd(&sg[NGW_STAT_SUCCESSES], (double)n_succ);
+                    if (n_reset) atomicAdd(&sg[NGW_STAT_RESETS], (double)n_reset);
+                    if (n_inv) atomicAdd(&sg[NGW_STAT_INVALID], (double)n_inv);
+                }
+            }
+        }
+    }
+
+    // Programmatic dependent launch: this group's work is issued; once every group of the CTA got here the next kernel of
+    // the stream may start scheduling its CTAs (its prologue touches no global state: it overlaps this kernel's stores).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (kTma && gt == 0) bulk_wait_read<0>();                         // shared memory must outlive the bulk stores' reads
+}
 
 }  // namespace ngw

@@ -207,36 +207,38 @@ class NovelGridworldBatchEnv(Env):
         return self._runtime_for(self._top).dict_observation()
 
     def render(self, mode='human', title=None, env_index=0):
-        """Host visualisation of ONE env of the batch from the exported state (pogostick_v1_env.py:556-620 draws the
-        same picture with matplotlib).  matplotlib is optional; without it (or with mode='ansi') the grid is printed /
-        returned as text: item ids, the agent as ^ v < >."""
+        """Host visualisation of ONE env of the batch from the exported state: the picture of pogostick_v1_env.py:556-620
+        (grid, facing arrow, info panel, win banner, inventory legend).  mode 'human' draws it with matplotlib when that is
+        installed and falls back to text; 'ansi' prints and returns the text form; 'spec' returns the drawing list."""
+        from . import render as R
         rt = self._runtime_for(self._top)
         if rt.handle is None:
             raise RuntimeError("render() before reset()")
-        grid = rt.handle.map[env_index].cpu().numpy()
-        r, c, facing, sel = [int(x) for x in rt.handle.pose[env_index].cpu().numpy()]
+        h, names = rt.handle, rt.compiled.item_names
+        grid = h.map[env_index].cpu().numpy()
+        r, c, facing, sel = [int(x) for x in h.pose[env_index].cpu().numpy()]
+        inv = h.inventory[env_index].cpu().numpy()
+        if self.num_envs == 1:
+            last = dict(step_count=self.step_count, last_action=self.last_action, last_reward=self.last_reward,
+                        last_step_cost=self.last_step_cost, last_done=self.last_done)
+        else:                                                   # batched: the latest outputs of that env
+            last = dict(step_count=int(h.ep_len[env_index].item()), last_action=self.last_action,
+                        last_reward=int(h.reward[env_index].item()), last_step_cost=float(h.step_cost[env_index].item()),
+                        last_done=bool(h.done[env_index].item()))
+        spec = R.render_spec(self.env_id, grid, (r, c), R.FACING[facing], dict(self.items_id),
+                             {n: int(inv[i]) for i, n in enumerate(names) if n in self.items}, self.goal_item_to_craft,
+                             selected_item=names[sel] if sel else '', title=title, **last)
+        if mode == 'spec':
+            return spec
         if mode != 'ansi':
             try:
-                import matplotlib.pyplot as plt
+                R.draw(spec)
+                return None
             except ImportError:
-                mode = 'ansi'
-        if mode == 'ansi':
-            rows = []
-            for i in range(grid.shape[0]):
-                rows.append(' '.join('^v<>'[facing] if (i, j) == (r, c) else ('.' if grid[i, j] == 0 else '%x' % grid[i, j])
-                                     for j in range(grid.shape[1])))
-            text = '\n'.join(rows)
-            print(text)
-            return text
-        plt.figure(title or self.env_id, figsize=(9, 5))
-        plt.imshow(grid, cmap="gist_ncar", vmin=0, vmax=len(self.items_id))
-        dx, dy = {0: (0, -0.01), 1: (0, 0.01), 2: (-0.01, 0), 3: (0.01, 0)}[facing]
-        plt.arrow(c, r, dx, dy, head_width=0.7, head_length=0.7, color='white')
-        plt.title('NORTH', fontsize=10)
-        plt.xlabel('SOUTH')
-        plt.ylabel('WEST')
-        plt.pause(0.01)
-        plt.clf()
+                pass
+        text = R.to_text(spec)
+        print(text)
+        return text
 
     def seed(self, seed=None):
         """The reference has no seed() (it draws from the global np.random); here it re-keys the Philox generator."""

@@ -372,13 +372,11 @@ class ChainRuntime(object):
     def dict_observation(self):
         h = self.handle
         names = self.compiled.item_names
-        if self.single:
-            inv = h.inventory[0].cpu().numpy()
-            pose = h.pose[0].cpu().numpy()
-            return {'map': h.map[0].cpu().numpy().astype(np.int64),
-                    'agent_location': (int(pose[0]), int(pose[1])),
-                    'agent_facing_id': int(pose[2]),
-                    'inventory_items_quantity': {n: int(inv[i]) for i, n in enumerate(names) if n in self.base.items}}
+        if self.single:                                 # the env's own live objects, as get_observation hands them out
+            b = self.base
+            self._sync_single()
+            return {'map': b.map, 'agent_location': b.agent_location, 'agent_facing_id': b.agent_facing_id,
+                    'inventory_items_quantity': b.inventory_items_quantity}
         return {'map': h.map, 'agent_location': h.pose[:, 0:2], 'agent_facing_id': h.pose[:, 2],
                 'inventory_items_quantity': {n: h.inventory[:, i] for i, n in enumerate(names) if n in self.base.items}}
 
@@ -399,11 +397,21 @@ class ChainRuntime(object):
         pose = h.pose[0].cpu().numpy()
         inv = h.inventory[0].cpu().numpy()
         names = self.compiled.item_names
-        b.map = h.map[0].cpu().numpy().astype(np.int64)
+        # like the reference, `map` and `inventory_items_quantity` are LIVE objects updated in place (Dict observations and
+        # SaveTrajectories states alias them, pogostick_v1_env.py:222-226, wrappers.py:29-45)
+        grid = h.map[0].cpu().numpy().astype(np.int64)
+        if isinstance(b.map, np.ndarray) and b.map.shape == grid.shape:
+            b.map[...] = grid
+        else:
+            b.map = grid
         b.agent_location = (int(pose[0]), int(pose[1]))
         b.agent_facing_id = int(pose[2])
         b.agent_facing_str = [k for k, v in b.direction_id.items() if v == b.agent_facing_id][0]
-        b.inventory_items_quantity = {n: int(inv[i]) for i, n in enumerate(names) if n in b.items}
+        quantities = {n: int(inv[i]) for i, n in enumerate(names) if n in b.items}
+        if isinstance(b.inventory_items_quantity, dict) and set(b.inventory_items_quantity) == set(quantities):
+            b.inventory_items_quantity.update(quantities)
+        else:
+            b.inventory_items_quantity = quantities
         b.selected_item = names[int(pose[3])] if pose[3] else ''
         dr, dc = {0: (-1, 0), 1: (1, 0), 2: (0, -1), 3: (0, 1)}[b.agent_facing_id]
         fr, fc = b.agent_location[0] + dr, b.agent_location[1] + dc
@@ -446,8 +454,14 @@ class ChainRuntime(object):
             torch.cuda.current_stream(h.device).synchronize()
             if int(h.error_flags[0].item()) & oc.ERR_PLACEMENT:
                 raise AssertionError("Cannot place items, increase map size!")      # pogostick_v1_env.py:167
+            b = self.base
+            b.map, b.inventory_items_quantity = None, None         # an episode gets fresh live objects
+            if b.env is None:                                       # pogostick_v1_env.py:119-127
+                b.last_action, b.last_done, b.last_reward, b.last_step_cost, b.step_count = 'Forward', False, 0, 0, 0
+            else:                                                   # restore: bookkeeping is copied, pogostick_v1_env.py:98-101
+                src = b.env.unwrapped
+                b.last_action, b.step_count, b.last_reward, b.last_done = src.last_action, src.step_count, src.last_reward, False
             self._sync_single()
-            self.base.step_count = 0
         else:
             b = self.base
             b.map, b.agent_location, b.agent_facing_id = h.map, h.pose[:, 0:2], h.pose[:, 2]
@@ -474,7 +488,16 @@ class ChainRuntime(object):
             b = self.base
             b.step_count += 1
             b.last_reward, b.last_done = int(reward[0].item()), bool(done[0].item())
-            b.last_step_cost = float(cost[0].item())
+            # the float32 the kernel wrote, as the shortest decimal that round-trips it: 27.906975, 3600.0, ... — the very
+            # doubles the reference reports
+            b.last_step_cost = float(str(np.float32(cost[0].item())))
+            # name of the action as the outermost wrapper sees it (pogostick_v1_env.py:236, wrappers.py:78)
+            top = b._top
+            ids = getattr(top, 'limited_actions_id', None) or top.actions_id
+            for name, aid in ids.items():
+                if aid == int(action):
+                    b.last_action = name
+                    break
             info = {'result': bool(result[0].item()), 'step_cost': b.last_step_cost,
                     'message': decode_message(h.msg[0].item(), cc)}
             o = (obs[0, :cc.obs_dim].cpu().numpy().astype(np.int64) if cc.obs_dim else self.dict_observation())

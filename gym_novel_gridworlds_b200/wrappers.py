@@ -8,41 +8,45 @@ from .core import Wrapper, _Invalid
 
 
 class SaveTrajectories(Wrapper):
-    """Host-side logger with the reference's pickle schema (wrappers.py:9-54): one state dict per step, `save()` writes
-    the list.  With num_envs == 1 the values are the reference's python objects; batched envs store CPU copies of the
-    state tensors (arrays indexed by env)."""
-
-    _STATIC_KEYS = (("map_size", "map_size"), ("items_id", "items_id"), ("items_quantity", "items_quantity"),
-                    ("action_str", "actions_id"), ("last_action", "last_action"))
+    """Host-side logger with the reference's pickle schema (wrappers.py:9-56): one state dict per step, `save()` pickles
+    the list into <save_path>/<timestamp>_<env_id>.bin.  With num_envs == 1 the values are the env's own python objects —
+    like the reference, `map` and `inventory_items_quantity` are the LIVE objects, so every entry of one episode aliases
+    the same array (the reference's pickle therefore holds the episode's final map in each entry; so does this one).
+    Batched envs store CPU copies of the state tensors (arrays indexed by env)."""
 
     def __init__(self, env, save_path):
         super().__init__(env)
-        os.makedirs(save_path, exist_ok=True)
-        self.save_path, self.state_trajectories, self.last_done = save_path, [], False
+        self.save_path = save_path
+        os.makedirs(self.save_path, exist_ok=True)
+        self.state_trajectories = []
 
     def step(self, action_id):
         out = self.unwrapped._runtime_for(self).step(action_id)
-        self.last_done = out[2]
         self.state_trajectories.append(self.get_state())
         return out
 
     def get_state(self):
-        base = self.unwrapped
+        env, base = self.env, self.unwrapped
         if base.num_envs == 1:
-            state = {key: getattr(base, key) for key in ("map", "agent_location", "agent_facing_str",
-                                                         "block_in_front_id", "inventory_items_quantity")}
+            state = {"map_size": env.map_size, "map": env.map, "agent_location": env.agent_location,
+                     "agent_facing_str": env.agent_facing_str, "block_in_front_id": env.block_in_front_id}
+        else:
+            grid, pose, _ = (t.cpu().numpy() for t in base._runtime.handle.export_state())
+            state = {"map_size": env.map_size, "map": grid, "agent_location": pose[:, :2], "agent_facing_id": pose[:, 2]}
+        if base.num_envs == 1:
+            inventory = env.inventory_items_quantity
         else:
             handle, names = base._runtime.handle, base._runtime.compiled.item_names
-            grid, pose, inv = (t.cpu().numpy() for t in handle.export_state())
-            state = {"map": grid, "agent_location": pose[:, :2], "agent_facing_id": pose[:, 2],
-                     "inventory_items_quantity": {n: inv[:, i] for i, n in enumerate(names) if n in base.items}}
-        state.update((key, getattr(base, attr)) for key, attr in self._STATIC_KEYS)
-        state["last_done"] = self.last_done
+            inv = handle.inventory.cpu().numpy()
+            inventory = {n: inv[:, i] for i, n in enumerate(names) if n in base.items}
+        state.update({"items_id": env.items_id, "items_quantity": env.items_quantity, "inventory_items_quantity": inventory,
+                      "action_str": env.actions_id, "last_action": env.last_action,
+                      "last_done": self.last_done if base.num_envs == 1 else base._runtime.handle.done.cpu().numpy().astype(bool)})
         return state
 
     def save(self):
-        stamp = datetime.now().strftime("%Y-%m-%d-%H-%M-%S")
-        path = os.path.join(self.save_path, "%s_%s.bin" % (stamp, self.env.env_id))
+        path = os.path.join(self.save_path,
+                            datetime.now().strftime("%Y-%m-%d-%H-%M-%S") + "_{env}.bin".format(env=self.env.env_id))
         with open(path, 'wb') as f:
             pickle.dump(self.state_trajectories, f)
         print("Trajectories saved at: ", path)

@@ -2,9 +2,13 @@
 """Golden-trace generator: runs the UNMODIFIED reference (/root/reference, via oracle/gymstub) and
 records reset states, actions and every step's outputs into tests/golden/traces.npz.
 
-Run in the build container only (the reference does not travel to the GPU box):
+Run where the reference is importable (/root/reference in the build container, or the baseline/_ref install):
 
     python oracle/gen_golden.py            # ~1-2 min, rewrites tests/golden/traces.npz
+
+The output is reproducible byte for byte: every iteration over a hash-ordered container is sorted, PYTHONHASHSEED is
+pinned to 0 (the script re-executes itself if needed), and tests/test_oracle_golden.py regenerates a few scenarios and
+compares them with the committed file.
 
 For each scenario of tests/scenarios.py and each episode:
   * np.random.seed(ep_seed); obs0 = env.reset()          -> reset observation + reset state (pins the
@@ -17,6 +21,10 @@ For each scenario of tests/scenarios.py and each episode:
 import json
 import os
 import sys
+
+if __name__ == '__main__' and os.environ.get('PYTHONHASHSEED') != '0':
+    os.environ['PYTHONHASHSEED'] = '0'
+    os.execv(sys.executable, [sys.executable] + sys.argv)
 
 import numpy as np
 
@@ -43,7 +51,8 @@ def snapshot(base):
 
 def perturb(base, rng):
     ids = base.items_id
-    names = [n for n in base.inventory_items_quantity if n not in ('air', 'wall')]
+    # sorted: inventory_items_quantity is built from a set (pogostick_v1_env.py:119-120), its order follows the string hash
+    names = sorted(n for n in base.inventory_items_quantity if n not in ('air', 'wall'))
     for name in names:
         if rng.rand() < 0.6:
             hi = 2 if name == base.goal_item_to_craft else 9
@@ -55,7 +64,7 @@ def perturb(base, rng):
         axes = [n for n in held if n.endswith('_axe')]
         base.selected_item = axes[0] if (axes and rng.rand() < 0.7) else held[rng.randint(len(held))]
     ms = base.map_size
-    placeable = [i for n, i in ids.items() if n not in ('air', 'wall')]
+    placeable = sorted(i for n, i in ids.items() if n not in ('air', 'wall'))
     for _ in range(rng.randint(0, 5)):
         r, c = rng.randint(1, ms - 1), rng.randint(1, ms - 1)
         if (r, c) != tuple(base.agent_location) and base.map[r][c] == 0:
@@ -134,17 +143,23 @@ def run_scenario(ns, desc, out):
         out[key + '/' + k] = arr
 
 
-def main():
+def generate(names=None, verbose=False):
+    """{npz key: array} for the named scenarios (all when None), straight from the unmodified reference."""
     ns = scenarios.reference_namespace()
     import io
     import contextlib
     out = {}
-    S = scenarios.all_scenarios()
+    S = [d for d in scenarios.all_scenarios() if names is None or d['name'] in names]
     for i, desc in enumerate(S):
         with contextlib.redirect_stdout(io.StringIO()):       # the reference prints remapped action tables
             run_scenario(ns, desc, out)
-        if i % 25 == 0:
+        if verbose and i % 25 == 0:
             print('%d/%d %s' % (i, len(S), desc['name']), flush=True)
+    return out, S
+
+
+def main():
+    out, S = generate(verbose=True)
     path = os.path.join(HERE, '..', 'tests', 'golden', 'traces.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, os.path.getsize(path) // 1024, 'KiB,', len(S), 'scenarios,',

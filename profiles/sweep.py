@@ -89,4 +89,7 @@ if __name__ == '__main__':
     if variants and variants[0] in ('i32', 'u8'):
         fmt, variants = variants[0], variants[1:] or ['']
     for knobs in variants:
-        print(json.dumps(measure(workload, knobs, fmt)), flush=True)
+        try:
+            print(json.dumps(measure(workload, knobs, fmt)), flush=True)
+        except Exception as e:                      # a knob combination the library refuses must not end the sweep
+            print(json.dumps({"workload": workload, "knobs": knobs, "obs_format": fmt, "error": str(e)[:200]}), flush=True)

@@ -40,13 +40,27 @@ def build_chain(ns, desc, **make_kwargs):
     return env
 
 
-def reference_namespace():
-    """The unmodified reference through oracle/gymstub (only possible where /root/reference exists)."""
+def reference_root():
+    """Where the unmodified reference package lives: /root/reference in the build container, else the copy that
+    __graft_entry__.build() installs under git-ignored baseline/_ref (it travels to the GPU box with the snapshot)."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    for root in ('/root/reference', os.path.join(here, '..', 'baseline', '_ref')):
+        if os.path.isdir(os.path.join(root, 'gym_novel_gridworlds')):
+            return os.path.abspath(root)
+    return None
+
+
+def reference_namespace(ref_root=None):
+    """The unmodified reference through oracle/gymstub (a ~150-line gym-0.18 / matplotlib stand-in)."""
     import os
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
-    stub = os.path.join(here, '..', 'oracle', 'gymstub')
-    for p in (stub, '/root/reference'):
+    stub = os.path.abspath(os.path.join(here, '..', 'oracle', 'gymstub'))
+    root = ref_root or reference_root()
+    if root is None:
+        raise RuntimeError("the reference package is neither at /root/reference nor under baseline/_ref")
+    for p in (stub, root):
         if p not in sys.path:
             sys.path.insert(0, p)
     import gym

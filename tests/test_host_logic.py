@@ -135,3 +135,62 @@ def test_fence_outside_wall_replacement_is_rejected_like_the_reference_crash():
     env = gym.inject_novelty(env, 'fencerestriction', 'hard', 'oak')
     with pytest.raises(NotImplementedError, match="IndexError"):
         compile_chain(env)
+
+
+def _aux():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'aux.json')) as f:
+        return json.load(f)
+
+
+def test_render_spec_matches_what_the_reference_draws():
+    """every render() of the unmodified reference recorded by oracle/gen_aux_golden.py (grid image, facing
+    arrow, axis labels, info panel, win / can't-win banner, inventory legend with colour fractions) is reproduced by the
+    pure host function the batched env's render() uses — Pogostick-v1 and Bow-v1 + axe, custom title included."""
+    from gym_novel_gridworlds_b200 import render as R
+    n = 0
+    for case in _aux()['render']:
+        ids = case['items_id']
+        names = sorted(ids, key=ids.get)
+        env_id = case['desc']['env']
+        for shot in case['shots']:
+            st, want = shot['state'], shot['spec']
+            inv = {nm: st['inv'][ids[nm]] for nm in names}
+            got = R.render_spec(env_id, st['map'], (st['pose'][0], st['pose'][1]), R.FACING[st['pose'][2]], ids, inv,
+                                case['goal'], selected_item=st['selected_item'], step_count=st['step_count'],
+                                last_action=st['last_action'], last_reward=st['last_reward'],
+                                last_step_cost=st['last_step_cost'], last_done=st['last_done'], title=shot['title_arg'])
+            assert got['title'] == want['title'] and got['grid'] == want['grid'] and got['vmax'] == want['vmax']
+            assert [float(x) for x in got['arrow']] == want['arrow'] and list(got['axis']) == want['axis']
+            assert [[float(x), float(y), s] for x, y, s in got['texts']] == [list(t) for t in want['texts']]
+            assert [[a, b] for a, b in got['legend']] == want['legend']
+            text = R.to_text(got)
+            assert 'Steps: %d' % st['step_count'] in text and 'agent' in text
+            n += 1
+    assert n == 11
+
+
+def test_ids_register_into_a_gym_module():
+    """SURVEY §7 step 8 / VERDICT r1 missing #6: the env ids of gym_novel_gridworlds/__init__.py:37-60 register into a
+    `gym` module (here the gym-0.18 stand-in of oracle/gymstub, the version the reference pins) and gym.make builds the
+    batched env with the batch keywords passed through."""
+    import importlib
+    import os
+    import sys
+    stub = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'oracle', 'gymstub'))
+    sys.path.insert(0, stub)
+    try:
+        gym = importlib.import_module('gym')
+        import gym_novel_gridworlds_b200 as b200
+        for k in list(gym.envs.registration.registry):
+            if k.startswith('B200-'):
+                del gym.envs.registration.registry[k]
+        ids = b200.register_into(gym, prefix='B200-')
+        assert sorted(ids) == sorted('B200-' + k for k in b200.ENV_IDS)
+        assert b200.register_into(gym, prefix='B200-') == []            # already known: left alone
+        env = gym.make('B200-NovelGridworld-Bow-v1', num_envs=7, seed=3)
+        assert type(env).__name__ == 'BowV1Env' and env.num_envs == 7 and env.rng_seed == 3
+        assert len(env.actions_id) == 15 and env.goal_item_to_craft == 'bow'
+    finally:
+        sys.path.remove(stub)

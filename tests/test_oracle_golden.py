@@ -92,3 +92,47 @@ def test_oracle_replay_matches_reference(name):
         if kind == 'agent_map':
             for i in range(E):
                 assert np.array_equal(agent_map_of(ob.map[i], ob.pose[i], cc.map_size), g['obs'][i, t]), where
+
+
+@pytest.mark.skipif(scenarios.reference_root() is None, reason="the reference package is not available here")
+def test_golden_fixtures_are_reproducible_from_the_unmodified_reference():
+    """tests/golden/traces.npz must be re-derivable.  Regenerates five scenarios (all three
+    episodes, so the perturbed ones too) from the unmodified reference — under whatever PYTHONHASHSEED pytest runs with —
+    and compares every array with the committed file byte for byte."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'oracle'))
+    import gen_golden
+    names = ['pogo_limit_lidar', 'bow_C3_axe_medium_fence_hard', 'pogo_A_crate_hard', 'pogo_remap_over_addjump_limit',
+             'pogo0_A_axe_easy']
+    fresh, S = gen_golden.generate(names)
+    assert len(S) == len(names)
+    committed = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'traces.npz'))
+    keys = [k for k in committed.files if k.rsplit('/', 1)[0] in names]
+    assert sorted(keys) == sorted(fresh.keys())
+    for k in keys:
+        assert committed[k].dtype == fresh[k].dtype and np.array_equal(committed[k], fresh[k]), k
+
+
+LONG = golden_util.long_names()
+
+
+@pytest.mark.parametrize('name', LONG)
+def test_oracle_replays_hashed_long_reference_traces(name):
+    """~10^6 steps of the unmodified reference (oracle/gen_long_traces.py), every step's complete outcome pinned by a
+    64-bit hash: the oracle's legacy-stream reset reproduces every reset state, and its replay every step."""
+    g = golden_util.long_get(name)
+    cc = compile_chain(scenarios.build_chain(scenarios.b200_namespace(), g['meta']))
+    E, T = g['actions'].shape
+    ob = OracleBatch([cc], E)
+    err = ob.reset_legacy(g['meta']['seed0'])
+    assert not err.any()
+    n_items = g['init_inv'].shape[1]
+    z = np.zeros(E)
+    assert np.array_equal(golden_util.trace_hash(np.zeros((E, 0)), z, z, z, z, ob.inv[:, :n_items], ob.pose, ob.map),
+                          g['reset_hash'])
+    ob.map[:] = g['init_map']; ob.pose[:] = g['init_pose']; ob.inv[:] = 0; ob.inv[:, :n_items] = g['init_inv']
+    for t in range(T):
+        obs, rew, done, cost, res = ob.step(g['actions'][:, t].astype(np.int32), n_threads=8)
+        h = golden_util.trace_hash(obs[:, :cc.obs_dim], rew, done, res, cost, ob.inv[:, :n_items], ob.pose, ob.map)
+        assert np.array_equal(h, g['hash'][:, t]), "%s step %d: %d envs differ" % (name, t, int((h != g['hash'][:, t]).sum()))

@@ -565,7 +565,9 @@ static cudaError_t launch_step1_nc(ngw_handle* h, StepParams p, cudaStream_t s) 
     p.lidar_mode = h->lidar_mode;
     // state loads before griddepcontrol.wait when the stream's previous state writer is another handle (observe-only
     // launches write no state, but they are ordered like steps: they read it)
-    p.early_state = claim_stream(h, s, h->early_state && h->use_pdl) ? 1 : 0;
+    // only for one-wave launches: with several waves the loads of later waves never wait anyway, and issuing them ahead
+    // of the tile's zero-fill measured 4 % slower (C4 122 vs 127 us)
+    p.early_state = claim_stream(h, s, h->early_state && h->use_pdl && C > 1) ? 1 : 0;
     p.pdl_early = h->pdl_early ? 1 : 0;
     const size_t smem = (size_t)p.off_groups + (size_t)C * p.group_bytes;
     args.p = p;

@@ -776,17 +776,25 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
             const int r_sum = __reduce_add_sync(0xFFFFFFFFu, valid ? reward : 0);
             const float c_sum = warp_sum(valid ? cost : 0.0f);
             if (lane == 0) {
-                atomicAdd(&scta[0], (int)a_sum);
-                atomicAdd(&scta[1], (int)b_sum);
-                atomicAdd(&scta[2], r_sum);
-                atomicAdd(reinterpret_cast<float*>(&scta[3]), c_sum);
-                __threadfence_block();
-                const int n_groups = min(p.tiles_per_cta, p.n_tiles - (int)blockIdx.x * p.tiles_per_cta);
-                if (atomicAdd(&scta[4], 1) == n_groups - 1) {
+                int a_tot = (int)a_sum, b_tot = (int)b_sum, r_tot = r_sum;
+                float c_tot = c_sum;
+                bool flush = true;
+                if (!kOne) {                                          // several groups: fold in shared memory, the last one flushes
+                    atomicAdd(&scta[0], a_tot);
+                    atomicAdd(&scta[1], b_tot);
+                    atomicAdd(&scta[2], r_tot);
+                    atomicAdd(reinterpret_cast<float*>(&scta[3]), c_tot);
                     __threadfence_block();
-                    const int a_tot = *reinterpret_cast<volatile int*>(&scta[0]), b_tot = *reinterpret_cast<volatile int*>(&scta[1]);
-                    const int r_tot = *reinterpret_cast<volatile int*>(&scta[2]);
-                    const float c_tot = *reinterpret_cast<volatile float*>(&scta[3]);
+                    const int n_groups = min(p.tiles_per_cta, p.n_tiles - (int)blockIdx.x * p.tiles_per_cta);
+                    flush = atomicAdd(&scta[4], 1) == n_groups - 1;
+                    if (flush) {
+                        __threadfence_block();
+                        a_tot = *reinterpret_cast<volatile int*>(&scta[0]); b_tot = *reinterpret_cast<volatile int*>(&scta[1]);
+                        r_tot = *reinterpret_cast<volatile int*>(&scta[2]);
+                        c_tot = *reinterpret_cast<volatile float*>(&scta[3]);
+                    }
+                }
+                if (flush) {
                     const int n_step = a_tot & 1023, n_done = (a_tot >> 10) & 1023, n_succ = (a_tot >> 20) & 1023;
                     const int n_reset = b_tot & 1023, n_inv = (b_tot >> 10) & 1023;
                     double* sg = p.stats + (size_t)(blockIdx.x % NGW_STAT_SLOTS) * NGW_STAT_COUNT;

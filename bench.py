@@ -112,8 +112,12 @@ def workload_bytes_per_env_step(compiled, obs_format='i32'):
     return float(np.mean([algorithmic_bytes_per_env_step(cc, obs_format) for cc in compiled])) + (1 if len(compiled) > 1 else 0)
 
 
-def batches_to_exceed_l2(envs, bytes_step):
-    return max(2, int(np.ceil(1.6 * L2_BYTES / (envs * bytes_step))))
+L2_FACTOR = 4.0                  # rotating working set >= 4 x L2: with 1.6 x (7 C2 batches) ncu still shows 28 % of the
+                                 # algorithmic bytes served by L2 (profiles/step_kernel_traffic.json), with 4 x about 10 %
+
+
+def batches_to_exceed_l2(envs, bytes_step, factor=L2_FACTOR):
+    return max(2, int(np.ceil(factor * L2_BYTES / (envs * bytes_step))))
 
 
 def c2_config(n_gpus):
@@ -122,8 +126,8 @@ def c2_config(n_gpus):
     return {"workload": "C2: NovelGridworld-Pogostick-v1 + LimitActions(10) + LidarInFront(8), 65536 envs/batch, "
                         "uniform random actions",
             "envs_per_batch": ENVS_PER_BATCH, "batches_rotated": n_b,
-            "l2": "inputs larger than L2: %d rotating batches, %.0f MB combined working set vs 126 MB L2"
-                  % (n_b, n_b * ENVS_PER_BATCH * 446.0 / 1e6),
+            "l2": "inputs larger than L2: %d rotating batches, %.0f MB combined working set = %.1f x the 126 MB L2"
+                  % (n_b, n_b * ENVS_PER_BATCH * 446.0 / 1e6, n_b * ENVS_PER_BATCH * 446.0 / L2_BYTES),
             "obs_dtype": "int32 rows for value/roofline (446 B/env-step); e2e moves NGW_OBS_U8 rows",
             "parallelism": "independent shards, one process per GPU x%d, no collective on the step path" % n_gpus}
 
@@ -533,12 +537,14 @@ def e2e_run(wl, n_steps, dev, world, host_acts):
         obs, rew, dn, cost, res = wl.batches[i % n_b].step_host_end()
         checksum += float(rew[0]) + float(obs[0, 0])                    # touch the results on the host
     t_pipe = time.perf_counter() - t0
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()                                            # the plain blocking call, one batch at a time
-    n_block = max(20, n_steps // 4)
-    for i in range(n_block):
+    for i in range(n_steps):
         obs, rew, dn, cost, res = wl.batches[i % n_b].step_host(host_acts[i % n_sets], **kw)
         checksum += float(rew[0]) + float(obs[0, 0])
-    t_block = (time.perf_counter() - t0) * n_steps / n_block           # scaled to n_steps
+    t_block = time.perf_counter() - t0
     return t_pipe, t_block, checksum
 
 
@@ -587,6 +593,18 @@ def run_ours(args, rank, world, local_rank):
     ov_regions = time_regions(wl, K, dev, world, n_streams=min(3, n_batches))[0]
     ms_overlap = float(np.median(ov_regions))
 
+    # ---- how much the rotation size matters (L2 keeps part of a small rotation): the same measurement with 7 and 32 batches
+    l2_sens = {}
+    if args.workload == 'C2' and not args.no_workloads:
+        for nb in (7, 32):
+            w2 = Workload('C2', rank, world, dev, n_batches=nb)
+            for i in range(nb):
+                w2.step(i)
+            torch.cuda.synchronize(dev)
+            reg2 = time_regions(w2, K, dev, world, floor_ms=20.0)[0]
+            l2_sens[nb] = float(np.median(reg2)) / K
+            w2.close()
+
     # ---- K-step rollout kernel: 64 steps per launch, uniform random policy drawn on the device
     roll_T = 64
     for h in wl.batches:
@@ -617,6 +635,29 @@ def run_ours(args, rank, world, local_rank):
         q1.record()
         torch.cuda.synchronize(dev)
         roll_policy_ms = q0.elapsed_time(q1)
+    # ---- general policy hook: one CUDA graph of 32 x [torch policy on the device observation -> ngw_step], one batch
+    torch_policy_ms, tp_T = 0.0, 32
+    if wl.batches[0].obs_dim > 0:
+        gw = torch.Generator(device=dev)
+        gw.manual_seed(11)
+        w_f = torch.randn((wl.batches[0].obs_dim, wl.max_actions), generator=gw, device=dev)
+        n_valid = torch.tensor([cc.c.n_actions for cc in wl.compiled], device=dev)[wl.batches[0].cfg_id.long()]
+        d0 = wl.batches[0].obs_dim
+
+        def torch_policy(obs):
+            return torch.remainder(torch.argmax(obs[:, :d0].float() @ w_f, dim=1), n_valid).to(torch.int32)
+
+        tp_graph, _ = wl.batches[0].capture_policy_rollout(torch_policy, tp_T, **wl.kw)
+        tp_graph.replay()
+        torch.cuda.synchronize(dev)
+        t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0_.record()
+        for _ in range(8):
+            tp_graph.replay()
+        t1_.record()
+        torch.cuda.synchronize(dev)
+        torch_policy_ms = t0_.elapsed_time(t1_) / 8
+        del tp_graph
     # ---- eager (one python call per launch) figure, for the launch-bound picture
     n_eager = min(max(K, 200), 2000)
     torch.cuda.synchronize(dev)
@@ -679,9 +720,10 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)                     # episode statistics over NCCL
     red = reduce_max([ms_region, ms_overlap, t_e2e, t_block, t_e2e_i32, t_block_i32, roll_ms, roll_policy_ms, eager_ms,
-                      probe["ms_per_step_bytes"]] + extra_times)
-    (ms_region, ms_overlap, t_e2e, t_block, t_e2e_i32, t_block_i32, roll_ms, roll_policy_ms, eager_ms, probe_ms) = red[:10]
-    extra_times = red[10:]
+                      probe["ms_per_step_bytes"], torch_policy_ms] + extra_times)
+    (ms_region, ms_overlap, t_e2e, t_block, t_e2e_i32, t_block_i32, roll_ms, roll_policy_ms, eager_ms, probe_ms,
+     torch_policy_ms) = red[:11]
+    extra_times = red[11:]
 
     if rank == 0:
         ms_per_step = ms_region / K
@@ -690,7 +732,11 @@ def run_ours(args, rank, world, local_rank):
         achieved = envs * bytes_step / (ms_per_step * 1e-3) / 1e9
         ov_achieved = envs * bytes_step / (ms_overlap / K * 1e-3) / 1e9
         traffic, traffic_src = measured_traffic(args.workload)
-        e2e_value = total_envs * n_e2e / t_e2e
+        # two ways to call the host-buffer API: pipelined over the batches (_begin/_end) or one blocking call per step.
+        # On one GPU the pipeline wins (the link never idles); with 8 ranks sharing the host's PCIe / memory system the
+        # blocking call does (fewer copies in flight).  A caller picks the faster one; both are in the line.
+        e2e_pipe, e2e_block = total_envs * n_e2e / t_e2e, total_envs * n_e2e / t_block
+        e2e_value = max(e2e_pipe, e2e_block)
         pcie_gbs = d2h_u8 / (probe_ms * 1e-3) / 1e9
         pcie_limit = world * envs / (probe_ms * 1e-3)
         for name, ms in zip(names, extra_times):
@@ -709,12 +755,15 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_u8,
                     "steps": n_e2e, "obs_format": "NGW_OBS_U8 (uint8 lidar ranges + int32 inventory tail, %d B/env)" % row8,
-                    "api": "ngw_step_host_begin/_end, pinned host buffers: H2D actions, one launch, D2H obs/reward/"
-                           "step_cost/done/result per step; batch i+1 enqueued before waiting for batch i",
-                    "blocking_value": total_envs * n_e2e / t_block,
-                    "pcie": {"d2h_gbs_per_gpu": pcie_gbs, "limit_env_steps_per_s": pcie_limit,
-                             "frac": e2e_value / pcie_limit,
-                             "note": "plain cudaMemcpyAsync of the same bytes per step, both directions, all ranks at once"},
+                    "api": "ngw_step_host (blocking) / ngw_step_host_begin+_end (batch i+1 enqueued before waiting for batch "
+                           "i), pinned host buffers: H2D actions, one launch, D2H obs/reward/step_cost/done/result per step",
+                    "mode": "pipelined" if e2e_pipe >= e2e_block else "blocking",
+                    "pipelined_value": e2e_pipe, "blocking_value": e2e_block,
+                    "achieved_d2h_gbs_total": e2e_value * (row8 + 10) / 1e9,
+                    "pcie": {"d2h_gbs_per_gpu": pcie_gbs, "d2h_gbs_total": pcie_gbs * world,
+                             "limit_env_steps_per_s": pcie_limit, "frac": e2e_value / pcie_limit,
+                             "note": "probe = plain cudaMemcpyAsync of one step's bytes, both directions at once, on every "
+                                     "rank at the same time; the host side of this box delivers that much in aggregate"},
                     "int32_rows": {"value": total_envs * n_e2e_i32 / t_e2e_i32, "d2h_bytes_per_step": d2h_i32,
                                    "blocking_value": total_envs * n_e2e_i32 / t_block_i32, "steps": n_e2e_i32},
                     "numa": numa},
@@ -722,7 +771,10 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": "ngw::step_kernel",
                          "peak_source": peak_src, "algorithmic_bytes_per_env_step": bytes_step,
-                         "algorithmic_bytes_per_launch": envs * bytes_step, "avg_launch_us": ms_per_step * 1e3},
+                         "algorithmic_bytes_per_launch": envs * bytes_step, "avg_launch_us": ms_per_step * 1e3,
+                         "l2_sensitivity": {"%d_batches_%.0f_MB" % (nb, nb * envs * bytes_step / 1e6):
+                                            {"us_per_step": ms * 1e3, "frac": envs * bytes_step / (ms * 1e-3) / 1e9 / peak}
+                                            for nb, ms in sorted(l2_sens.items())}},
             "timing": {"regions": len(regions),
                        "region_ms_min_med_max": [min(regions), float(np.median(regions)), max(regions)],
                        "timed_ms_total": float(sum(regions)), "graph_steps": g_steps,
@@ -739,6 +791,12 @@ def run_ours(args, rank, world, local_rank):
                 "note": "ngw_rollout_policy: %d steps per launch, action = argmax(b + obs @ W) on the device from each "
                         "step's lidar observation" % roll_T,
                 "value": total_envs * roll_T * n_roll / (roll_policy_ms * 1e-3), "unit": "env-steps/s"},
+            "torch_policy_graph": None if not torch_policy_ms else {
+                "note": "BatchHandle.capture_policy_rollout: ONE CUDA graph of %d x [torch policy (float matmul + argmax on the "
+                        "device observation) -> ngw_step] on one batch: the closed loop with a general policy, host out of "
+                        "the loop" % tp_T,
+                "value": total_envs * tp_T / (torch_policy_ms * 1e-3), "unit": "env-steps/s",
+                "us_per_step": torch_policy_ms / tp_T * 1e3},
             "eager": {"value": total_envs / (eager_ms * 1e-3), "unit": "env-steps/s", "us_per_step": eager_ms * 1e3},
             "workloads": extra,
             "episode_stats": dict(zip(('steps', 'episodes', 'successes', 'reward_sum', 'cost_sum', 'resets',

@@ -33,6 +33,7 @@ struct ngw_handle {
     int map_bytes = 0, inv_bytes = 0, obs_bytes = 0, warps = 2, tiles_per_cta = 0, lidar_mode = 0;
     int obs_u8 = 0, obs_row_bytes = 0;             // observation row layout (ngw_set_obs_format)
     int cache_hints = 3, dbg_skip = 0;
+    uint32_t key_mask = 0xFFFFFFFFu;
     bool use_tma = true, collect_stats = true, force_global_cfg = false, plain_store = false, use_pdl = true;
     bool pdl_in_graph = true, early_state = true, pdl_early = true;
     bool lidar_uniform = false;
@@ -247,6 +248,7 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     // measured on C2 9.15 -> 8.82 us/step, C3 29.3 -> 28.0, C5 278 -> 274 (hinting the inventory store as well: 9.0)
     h->cache_hints = getenv("NGW_HINTS") ? atoi(getenv("NGW_HINTS")) : 3;
     h->dbg_skip = getenv("NGW_SKIP") ? atoi(getenv("NGW_SKIP")) : 0;   // attribution runs only: results are wrong
+    if (const char* km = getenv("NGW_DEBUG_KEY_MASK")) h->key_mask = (uint32_t)strtoul(km, nullptr, 0);   // test knob: key ties
     for (int i = 0; i < n_cfgs; i++) {
         const ngw_config& c = cfgs[i];
         if (c.n_items < 1 || c.n_items > NGW_MAX_ITEMS || c.n_actions < 0 || c.n_actions > NGW_MAX_ACTIONS ||
@@ -319,6 +321,7 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     // grids, 4 when shared memory limits the tiles per SM to a few
     int tiles_per_sm = (227 * 1024) / (one_tile + 1024);
     int warps = tiles_per_sm >= 6 ? 2 : 4;
+    if (n_cfgs > 1 && warps == 2) warps = 1;      // mixed batches: a second warp repeats the per-lane config reads (C4 129 vs 139 us)
     if (const char* w = getenv("NGW_WARPS")) {                      // tuning knob: warps per tile
         int v = atoi(w);
         if (v == 1 || v == 2 || v == 4) warps = v;
@@ -421,6 +424,7 @@ static ResetParams reset_params(ngw_handle* h, const uint8_t* mask, int phase) {
     p.ms = h->ms; p.cells = h->cells; p.inv_stride = h->inv_stride; p.phase = phase; p.zero_byte = h->zero_byte;
     p.reset_list = h->reset_list; p.reset_count = h->reset_ctl; p.done_ctas = h->reset_ctl + 1; p.obs = nullptr;
     p.obs_dim = h->obs_dim; p.obs_row_bytes = h->obs_row_bytes; p.obs_u8 = h->obs_u8;
+    p.key_mask = h->key_mask;
     return p;
 }
 
@@ -534,7 +538,9 @@ static cudaError_t launch_step1_nc(ngw_handle* h, StepParams p, cudaStream_t s) 
     const int luts = (NGW_MAX_MAP_SIZE + NGW_MAX_ITEMS * (NC > 0 ? NC : 0) + 127) & ~127;
     p.off_luts = NGW_CTA_HDR;
     p.off_groups = p.off_luts + luts;
-    p.group_bytes = (NGW_GROUP_HDR + p.map_bytes + p.inv_bytes + p.obs_bytes + 127) & ~127;
+    // shared-memory row stride of the observation tile: rows of a multiple of 8 words get 16 bytes of padding
+    p.obs_srow = p.obs_row_bytes + (((p.obs_row_bytes >> 2) % 8 == 0 && p.obs_row_bytes > 0 && !getenv("NGW_NO_ROW_PAD")) ? 16 : 0);
+    p.group_bytes = (NGW_GROUP_HDR + p.map_bytes + p.inv_bytes + 32 * p.obs_srow + 127) & ~127;
     const int G = h->warps;
     p.g_shift = G == 4 ? 2 : (G == 2 ? 1 : 0);
     const long long tiles = (p.env_end - p.env_begin + 31) / 32;

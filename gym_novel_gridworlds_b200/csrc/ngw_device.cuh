@@ -647,7 +647,7 @@ __device__ __forceinline__ bool reset_candidate(int kind, int id, int wall, int 
 __device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m, int32_t* inv, int ms, int inv_stride,
                                                 uint64_t seed, uint64_t gid, uint32_t episode, bool do_base,
                                                 int op_begin, int op_end, uint32_t* hist, int& pr, int& pc, int& pf,
-                                                int& psel) {
+                                                int& psel, uint32_t key_mask = 0xFFFFFFFFu) {
     const uint32_t FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const int cells = ms * ms;
@@ -770,6 +770,8 @@ __device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m
                 uint32_t key[4];
                 philox_keys4(seed, gid, episode, stream, (uint32_t)q, key);
 #pragma unroll
+                for (int j = 0; j < 4; j++) key[j] &= key_mask;
+#pragma unroll
                 for (int j = 0; j < 4; j++)
                     if (cand[j] && (bits == 0 || (key[j] >> (32 - bits)) == prefix))
                         atomicAdd(&hist[(key[j] >> (24 - bits)) & 0xFF], 1u);
@@ -808,6 +810,7 @@ __device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m
         }
         // ---- apply: one pass; winners are written at once, boundary-bin cells (<= 32, unless all of them win) are listed
         const bool all_in_bin_win = remaining >= bin_count;
+        const bool exact_keys = bits >= 32 && bin_count > 32;
         int n_list = 0;
         uint32_t my_key = 0; int my_idx = -1;
         const int value = op.kind == NGW_RESET_ADDITEM ? op.a : op.b;
@@ -826,24 +829,28 @@ __device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int i = 4 * q + j;
+                key[j] &= key_mask;
                 uint32_t top = bits == 0 ? 0 : (key[j] >> (32 - bits));
                 bool wins = cand[j] && (bits == 0 ? all_in_bin_win : (top < prefix || (top == prefix && all_in_bin_win)));
                 bool boundary = cand[j] && !all_in_bin_win && top == prefix;
+                uint32_t bal = __ballot_sync(FULL, boundary);
+                if (boundary) {
+                    int slot = n_list + __popc(bal & ((1u << lane) - 1u));
+                    // all 32 key bits consumed and still more than 32 contenders: their keys are IDENTICAL (probability
+                    // ~ n^2 / 2^33 per reset), so the tie goes by visiting order and no list is needed
+                    if (exact_keys) wins = slot < remaining;
+                    else if (slot < 32) { hist[slot] = key[j]; hist[32 + slot] = (uint32_t)i; }
+                }
+                n_list += __popc(bal);
                 if (wins) {
                     if (op.kind == NGW_RESET_FENCE) m[i] = (int8_t)(id[j] | 0x80);    // mark; fences go in afterwards
                     else if (i != agent) m[i] = (int8_t)value;                        // novelty_wrappers.py:1027,1141
                 }
-                uint32_t bal = __ballot_sync(FULL, boundary);
-                if (boundary) {
-                    int slot = n_list + __popc(bal & ((1u << lane) - 1u));
-                    if (slot < 32) { hist[slot] = key[j]; hist[32 + slot] = (uint32_t)i; }
-                }
-                n_list += __popc(bal);
             }
         }
         __syncwarp();
-        if (n_list > 0) {
-            if (n_list > 32) n_list = 32;                             // > 32 equal 32-bit prefixes: cannot happen in practice
+        if (n_list > 0 && !exact_keys) {
+            if (n_list > 32) n_list = 32;                             // unreachable: the loop above ends with <= 32 contenders or exact keys
             if (lane < n_list) { my_key = hist[lane]; my_idx = (int)hist[32 + lane]; }
             int rank = 0;
             for (int j = 0; j < n_list; j++) {

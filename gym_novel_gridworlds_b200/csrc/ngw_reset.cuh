@@ -26,6 +26,7 @@ struct ResetParams {
     int32_t* done_ctas;
     unsigned char* obs;         // observation rows of obs_row_bytes bytes (layout as in the step kernel)
     int obs_dim, obs_row_bytes, obs_u8;
+    uint32_t key_mask;          // 0xFFFFFFFF; test knob NGW_DEBUG_KEY_MASK forces ties between the subset-sampling keys
 };
 
 #define NGW_RESET_WARPS 4
@@ -68,13 +69,13 @@ __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_kernel(const Reset
         uint32_t ep = p.episode[e] + 1;
         __syncwarp();
         uint32_t err = reset_env_warp(cfg, sc.row, sc.inv, p.ms, p.inv_stride, p.seed, gid, ep, true, 0,
-                                      p.phase == 0 ? k : NGW_MAX_RESET_OPS, sc.hist, r, c, f, sel);
+                                      p.phase == 0 ? k : NGW_MAX_RESET_OPS, sc.hist, r, c, f, sel, p.key_mask);
         if (lane == 0) { p.episode[e] = ep; p.ep_len[e] = 0; p.err[e] = err; }
     } else {
         uint32_t ep = p.episode[e];
         rows_to_smem(sc, m, inv, p.cells, p.inv_stride, lane);
         reset_env_warp(cfg, sc.row, sc.inv, p.ms, p.inv_stride, p.seed, gid, ep, false, k, NGW_MAX_RESET_OPS, sc.hist, r, c,
-                       f, sel);
+                       f, sel, p.key_mask);
     }
     rows_from_smem(sc, m, inv, p.cells, p.inv_stride, lane);
     if (lane == 0) p.pose[e] = make_uchar4((unsigned char)r, (unsigned char)c, (unsigned char)f, (unsigned char)sel);
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_list_kernel(const 
         int k_obs = dc.c.reset_obs_after_ops;
         if (p.obs == nullptr || k_obs >= dc.c.n_reset_ops) k_obs = NGW_MAX_RESET_OPS;
         uint32_t err = reset_env_warp(&dc.c, sc.row, sc.inv, p.ms, p.inv_stride, p.seed, gid, ep, true, 0, k_obs, sc.hist,
-                                      r, c, f, sel);
+                                      r, c, f, sel, p.key_mask);
         if (p.obs != nullptr) {                                       // observation of the new episode replaces the row
             ObsRow orow;
             orow.p = p.obs + e * p.obs_row_bytes;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_list_kernel(const 
         }
         if (k_obs < dc.c.n_reset_ops)
             err |= reset_env_warp(&dc.c, sc.row, sc.inv, p.ms, p.inv_stride, p.seed, gid, ep, false, k_obs,
-                                  NGW_MAX_RESET_OPS, sc.hist, r, c, f, sel);
+                                  NGW_MAX_RESET_OPS, sc.hist, r, c, f, sel, p.key_mask);
         rows_from_smem(sc, m, inv, p.cells, p.inv_stride, lane);
         if (lane == 0) {
             p.episode[e] = ep;

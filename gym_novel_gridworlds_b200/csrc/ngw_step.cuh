@@ -102,6 +102,9 @@ struct StepParams {
     int ms, cells, inv_stride, obs_dim;
     int map_bytes, inv_bytes, obs_bytes;                 // bytes of one 32-env tile of each array
     int obs_row_bytes, obs_u8;                           // observation row layout (NGW_OBS_I32 / NGW_OBS_U8)
+    int obs_srow;               // one-step kernel: row stride of the observation tile in SHARED memory: obs_row_bytes, or
+                                // 16 bytes more when the row is a multiple of 8 words (64-word rows would put every
+                                // lane's row on the same bank: C4 / C5 measured 64-71 % of their shared wavefronts as conflicts)
     // shared-memory carve-up (bytes from the start of dynamic shared memory), all multiples of 128
     int off_luts, off_scratch, off_in, off_obs;          // rollout kernel (one tile per CTA)
     int off_groups, group_bytes;                         // one-step kernel: tile group k lives at off_groups + k * group_bytes
@@ -612,7 +615,7 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
     }
     if (p.obs != nullptr) {                                           // the group zeroes its observation tile while the loads fly
         uint32_t a = smem_u32(sobs) + (uint32_t)gt * 16u;
-        const uint32_t end = smem_u32(sobs) + (uint32_t)p.obs_bytes, st = 512u * (uint32_t)G;
+        const uint32_t end = smem_u32(sobs) + 32u * (uint32_t)p.obs_srow, st = 512u * (uint32_t)G;
         for (; a + 3u * st < end; a += 4u * st) {
             asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a + st), "r"(0) : "memory");
@@ -707,7 +710,7 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
     // ---- LidarInFront observation of the new state into the shared-memory tile
     if (p.obs != nullptr && valid && cfg.n_beams > 0 && !(p.dbg_skip & 2)) {
         ObsRow orow;
-        orow.p = sobs + lane * p.obs_row_bytes;
+        orow.p = sobs + lane * p.obs_srow;
         orow.u8 = p.obs_u8;
         LidarLuts luts;
         if (NC > 0) { luts.slot = sslot + cfg_i * NGW_MAX_ITEMS; luts.firstk = sfirstk; }
@@ -727,16 +730,23 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
     //      writes to the tiles before the async proxy reads them (fence before the barrier), then one thread issues.
     if (kTma) fence_async_smem();
     group_sync<kOne>(grp, G);
+    const bool padded_rows = p.obs_srow != p.obs_row_bytes;
     if (kTma && full_tile && !p.plain_store) {
-        if (gt == 0) {
-            if (stepping && !(p.dbg_skip & 16)) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
-            if (p.obs != nullptr && !(p.dbg_skip & 8)) {
-                unsigned char* gobs = p.obs + e0 * p.obs_row_bytes;
-                if (p.cache_hints & 2) bulk_s2g_hint(gobs, sobs, (uint32_t)p.obs_bytes, pol_first);
-                else bulk_s2g(gobs, sobs, (uint32_t)p.obs_bytes);
+        if (gt == 0 && stepping && !(p.dbg_skip & 16)) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
+        if (p.obs != nullptr && !(p.dbg_skip & 8)) {
+            unsigned char* gobs = p.obs + e0 * p.obs_row_bytes;
+            if (!padded_rows) {                                       // the tile is one contiguous span on both sides
+                if (gt == 0) {
+                    if (p.cache_hints & 2) bulk_s2g_hint(gobs, sobs, (uint32_t)p.obs_bytes, pol_first);
+                    else bulk_s2g(gobs, sobs, (uint32_t)p.obs_bytes);
+                }
+            } else if (g == 0) {                                      // padded rows in shared memory: lane l stores row l
+                if (p.cache_hints & 2) bulk_s2g_hint(gobs + lane * p.obs_row_bytes, sobs + lane * p.obs_srow,
+                                                     (uint32_t)p.obs_row_bytes, lane == 0 ? pol_first : policy_evict_first());
+                else bulk_s2g(gobs + lane * p.obs_row_bytes, sobs + lane * p.obs_srow, (uint32_t)p.obs_row_bytes);
             }
-            bulk_commit();
         }
+        if (g == 0) bulk_commit();
     } else {
         if (stepping) {
             const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
@@ -744,10 +754,12 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
             for (int i = gt; i < (p.inv_bytes >> 4); i += 32 * G) d4[i] = s4[i];
         }
         if (p.obs != nullptr) {
-            const int n = (int)((p.env_end - e0 < 32 ? p.env_end - e0 : 32)) * (p.obs_row_bytes >> 2);
-            uint32_t* gobs = reinterpret_cast<uint32_t*>(p.obs + e0 * p.obs_row_bytes);
-            const uint32_t* so = reinterpret_cast<const uint32_t*>(sobs);
-            for (int i = gt; i < n; i += 32 * G) gobs[i] = so[i];
+            const int rows = (int)(p.env_end - e0 < 32 ? p.env_end - e0 : 32), words = p.obs_row_bytes >> 2;
+            for (int r = 0; r < rows; r++) {
+                uint32_t* grow = reinterpret_cast<uint32_t*>(p.obs + (e0 + r) * p.obs_row_bytes);
+                const uint32_t* srow = reinterpret_cast<const uint32_t*>(sobs + r * p.obs_srow);
+                for (int i = gt; i < words; i += 32 * G) grow[i] = srow[i];
+            }
         }
     }
 
@@ -813,7 +825,7 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
     // Programmatic dependent launch: this group's work is issued; once every group of the CTA got here the next kernel of
     // the stream may start scheduling its CTAs (its prologue touches no global state: it overlaps this kernel's stores).
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (kTma && gt == 0) bulk_wait_read<0>();                         // shared memory must outlive the bulk stores' reads
+    if (kTma && g == 0) bulk_wait_read<0>();                          // shared memory must outlive the bulk stores' reads
 }
 
 }  // namespace ngw

@@ -31,7 +31,7 @@ class NovelGridworldBatchEnv(Env):
     _PLACES_TREE_TAP = False           # pogostick_v0_env.py:155-178
 
     def __init__(self, env=None, num_envs=1, device=None, seed=0, first_env_gid=0, auto_reset=False,
-                 max_episode_steps=0, messages=False):
+                 max_episode_steps=0, messages=False, strict_actions=False, obs_format='i32'):
         self.env = env                                  # env to restore in reset (pogostick_v1_env.py:29,89-109)
         self.num_envs = int(num_envs)
         self.device = device
@@ -42,6 +42,11 @@ class NovelGridworldBatchEnv(Env):
         self.auto_reset = bool(auto_reset)
         self.max_episode_steps = int(max_episode_steps)
         self.messages = bool(messages)
+        # strict_actions: a batched step raises like the reference (wrappers.py:76, pogostick_v1_env.py:236) when any env
+        # was given an id its chain rejects — one device-to-host read per step; off, the step is a no-op for that env,
+        # info['invalid'] marks it and the sticky error flag / NGW_STAT_INVALID count it.  obs_format: 'i32' | 'u8' rows.
+        self.strict_actions = bool(strict_actions)
+        self.obs_format = obs_format
 
         self.map_size = 10
         self.direction_id = {'NORTH': 0, 'SOUTH': 1, 'WEST': 2, 'EAST': 3}

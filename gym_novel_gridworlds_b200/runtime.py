@@ -204,6 +204,36 @@ class BatchHandle(object):
         out = (self.obs, self.reward, self.step_cost, self._done_count, self.done, self.result)
         return out + (taken,) if record_actions else out
 
+    def capture_policy_rollout(self, policy, n_steps, auto_reset=False, max_episode_steps=0):
+        """SURVEY §8f N1, general policy hook: ONE CUDA graph of n_steps x [actions = policy(obs); ngw_step(actions)].
+        `policy` is any callable made of torch ops on the current stream mapping the handle's observation tensor
+        (int32 [n, obs_dim], or uint8 rows with obs_format='u8') to an int32 action tensor [n]; observations and actions
+        never leave the device and the host is out of the loop (tests/train.py:122-135 is the use case).  Returns
+        (graph, record): `graph.replay()` advances every env by n_steps; `record` holds the tensors the graph fills
+        (actions [n_steps, n], reward_sum, cost_sum, done_count, and the handle's obs/reward/done/... of the last step)."""
+        dev = self.device
+        rec = {'actions': torch.zeros((n_steps, self.n), dtype=torch.int32, device=dev),
+               'reward_sum': torch.zeros(self.n, dtype=torch.float32, device=dev),
+               'cost_sum': torch.zeros(self.n, dtype=torch.float32, device=dev),
+               'done_count': torch.zeros(self.n, dtype=torch.int32, device=dev)}
+        stream = torch.cuda.Stream(dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream):
+            for _ in range(2):                                  # warm-up outside the capture (lazy torch initialisation)
+                a = policy(self.obs).to(torch.int32)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                rec['reward_sum'].zero_(); rec['cost_sum'].zero_(); rec['done_count'].zero_()
+                for t in range(n_steps):
+                    rec['actions'][t].copy_(policy(self.obs))
+                    self.step(rec['actions'][t], auto_reset, max_episode_steps)
+                    rec['reward_sum'] += self.reward
+                    rec['cost_sum'] += self.step_cost
+                    rec['done_count'] += self.done
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        rec.update(obs=self.obs, reward=self.reward, done=self.done, step_cost=self.step_cost, result=self.result)
+        return graph, rec
+
     def enable_messages(self, on=True):
         """Make every following step also write info['message'] codes (uint16 per env) into self.msg."""
         if on and getattr(self, 'msg', None) is None:
@@ -312,15 +342,17 @@ def decode_message(code, compiled):
 class LazyInfo(object):
     """info of a batched step: tensors; the reference's strings are formatted only when 'message' is asked for."""
 
-    def __init__(self, result, step_cost, msg=None, compiled=None, cfg_ids=None):
+    def __init__(self, result, step_cost, msg=None, compiled=None, cfg_ids=None, flags=None):
         self.result, self.step_cost = result, step_cost
-        self._msg, self._compiled, self._cfg_ids = msg, compiled, cfg_ids
+        self._msg, self._compiled, self._cfg_ids, self._flags = msg, compiled, cfg_ids, flags
 
     def __getitem__(self, key):
         if key == 'result':
             return self.result
         if key == 'step_cost':
             return self.step_cost
+        if key == 'invalid':         # envs whose action id the chain rejects (the reference raises, wrappers.py:76)
+            return None if self._flags is None else (self._flags & oc.ERR_INVALID_ACTION) != 0
         if key == 'message':
             if self._msg is None:
                 return None      # message codes are off unless the env was made with messages=True
@@ -331,7 +363,7 @@ class LazyInfo(object):
         raise KeyError(key)
 
     def keys(self):
-        return ['result', 'step_cost', 'message']
+        return ['result', 'step_cost', 'message', 'invalid']
 
 
 class ChainRuntime(object):
@@ -355,7 +387,8 @@ class ChainRuntime(object):
                 self.handle.close()
             self.compiled, self._fingerprint = cc, fp
             self.handle = BatchHandle([cc], self.base.num_envs, self.base.device, self.base.rng_seed,
-                                      self.base.first_env_gid)
+                                      self.base.first_env_gid,
+                                      obs_format='i32' if self.base.num_envs == 1 else self.base.obs_format)
             if self.single or self.messages:
                 self.handle.enable_messages()
         return self.handle
@@ -388,7 +421,9 @@ class ChainRuntime(object):
         return out[0].cpu().numpy().astype(np.int64) if self.single else out
 
     def lidar_observation(self):
-        obs = self.handle.observe()[:, :self.compiled.obs_dim]
+        obs = self.handle.observe()
+        if self.handle.obs_format != 'u8':
+            obs = obs[:, :self.compiled.obs_dim]
         return obs[0].cpu().numpy().astype(np.int64) if self.single else obs
 
     def _sync_single(self):
@@ -467,7 +502,7 @@ class ChainRuntime(object):
             b.map, b.agent_location, b.agent_facing_id = h.map, h.pose[:, 0:2], h.pose[:, 2]
             b.inventory_items_quantity = {n: h.inventory[:, i] for i, n in enumerate(cc.item_names) if n in b.items}
         if cc.reset_returns == 'lidar':
-            o = obs[:, :cc.obs_dim]
+            o = obs if h.obs_format == 'u8' else obs[:, :cc.obs_dim]
             return o[0].cpu().numpy().astype(np.int64) if self.single else o
         return self.dict_observation()
 
@@ -502,13 +537,31 @@ class ChainRuntime(object):
                     'message': decode_message(h.msg[0].item(), cc)}
             o = (obs[0, :cc.obs_dim].cpu().numpy().astype(np.int64) if cc.obs_dim else self.dict_observation())
             return o, b.last_reward, b.last_done, info
+        lidar_cols = slice(None) if h.obs_format == 'u8' else slice(0, cc.obs_dim)     # u8 rows: see BatchHandle.split_obs
         if isinstance(action, torch.Tensor) and action.is_cuda:
             obs, reward, done, cost, result = h.step(action, self.auto_reset, self.max_episode_steps)
-            o = obs[:, :cc.obs_dim] if cc.obs_dim else self.dict_observation()
-            return o, reward, done.view(torch.bool), LazyInfo(result.view(torch.bool), cost, getattr(h, 'msg', None), [cc])
+            self._check_actions(action)
+            o = obs[:, lidar_cols] if cc.obs_dim else self.dict_observation()
+            return o, reward, done.view(torch.bool), LazyInfo(result.view(torch.bool), cost, getattr(h, 'msg', None), [cc],
+                                                              flags=h.error_flags)
         obs, reward, done, cost, result = h.step_host(action, self.auto_reset, self.max_episode_steps)
-        o = obs[:, :cc.obs_dim] if cc.obs_dim else self.dict_observation()
-        return o, reward, done.view(np.bool_), LazyInfo(result.view(np.bool_), cost)
+        self._check_actions(action)
+        o = obs[:, lidar_cols] if cc.obs_dim else self.dict_observation()
+        return o, reward, done.view(np.bool_), LazyInfo(result.view(np.bool_), cost, flags=h.error_flags)
+
+    def _check_actions(self, action):
+        """strict_actions: raise what the reference raises as soon as one env of the batch got a rejected id."""
+        if not self.base.strict_actions:
+            return
+        h, cc = self.handle, self.compiled
+        bad = torch.nonzero((h.error_flags & oc.ERR_INVALID_ACTION) != 0)
+        if bad.numel() == 0:
+            return
+        i = int(bad[0].item())
+        h.error_flags.bitwise_and_(~oc.ERR_INVALID_ACTION)
+        a = int(action[i].item()) if hasattr(action[i], 'item') else int(action[i])
+        why = cc.invalid_reasons.get(a, "Action ID " + str(a) + " is not valid")
+        raise (ValueError if why.startswith('ValueError') else AssertionError)("env %d of %d: %s" % (i, int(bad.numel()), why))
 
 
 class MixedBatch(object):

@@ -1,6 +1,6 @@
 """Minimal driver for ncu: one BASELINE workload, rotating batches, eager launches.
     ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 14 -c 2 -o gpurun_out/prof \
-        python profiles/prof_step.py [C2|C3|C4|C4-blocked|C5] [steps]"""
+        python profiles/prof_step.py [C2|C3|C4|C4-blocked|C5] [steps] [rotating batches]"""
 import os
 import sys
 
@@ -14,7 +14,7 @@ from gym_novel_gridworlds_b200.runtime import BatchHandle  # noqa: E402
 workload = sys.argv[1] if len(sys.argv) > 1 else 'C2'
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 28
 desc, compiled, envs, rule, kw = bench.build_workload(workload)
-n_b = 7 if workload == 'C2' else 2
+n_b = int(sys.argv[3]) if len(sys.argv) > 3 else (7 if workload == 'C2' else 2)
 batches = []
 for b in range(n_b):
     cfg_id = None

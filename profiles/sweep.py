@@ -20,7 +20,9 @@ def measure(workload, knobs, obs_format='i32'):
         saved[k] = os.environ.get(k)
         os.environ[k] = v
     try:
-        desc, compiled, envs, rule, kw = bench.build_workload(workload)
+        desc, compiled, envs, rule, kw = bench.build_workload(workload.replace('-noreset', ''))
+        if workload.endswith('-noreset'):
+            kw = {}
         bytes_step = float(np.mean([bench.algorithmic_bytes_per_env_step(cc, obs_format) for cc in compiled])) + (1 if len(compiled) > 1 else 0)
         n_b = max(2, int(np.ceil(1.6 * 126e6 / (envs * bytes_step))))
         batches = []

@@ -741,3 +741,63 @@ def test_env_restore_chain_matches_the_reference():
     assert np.asarray(b2.map).tolist() == g['final_state']['map'] and b2.step_count == g['final_state']['step_count']
     assert b2.block_in_front_id == g['block_in_front_id']
     assert np.asarray(first.unwrapped.map).tolist() == g['first_state']['map']        # the source env is untouched
+
+
+def test_batched_invalid_actions_surface():
+    """ADVICE r1 (low): a batched step must not swallow rejected action ids.  info['invalid'] marks the envs;
+    strict_actions=True raises what the reference raises (wrappers.py:76) and names the first offender; the u8 observation
+    format is reachable through gym.make."""
+    import gym_novel_gridworlds_b200 as gym
+    n = 500
+    env = gym.LidarInFront(gym.LimitActions(gym.make('NovelGridworld-Pogostick-v1', num_envs=n, obs_format='u8'),
+                                            set(scenarios.C2_SET)))
+    obs = env.reset()
+    assert obs.dtype == torch.uint8 and obs.shape == (n, 84)
+    a = torch.zeros(n, dtype=torch.int32, device='cuda')
+    a[17] = 10
+    a[400] = -1
+    obs, r, d, info = env.step(a)
+    bad = info['invalid'].cpu().numpy()
+    assert bad.sum() == 2 and bad[17] and bad[400] and obs.shape == (n, 84)
+    strict = gym.LidarInFront(gym.LimitActions(gym.make('NovelGridworld-Pogostick-v1', num_envs=n, strict_actions=True),
+                                               set(scenarios.C2_SET)))
+    strict.reset()
+    strict.step(torch.zeros(n, dtype=torch.int32, device='cuda'))
+    with pytest.raises(AssertionError, match="env 17 of 2"):
+        strict.step(a)
+    strict.step(torch.zeros(n, dtype=torch.int32, device='cuda'))       # the flags were cleared by the raise
+    with pytest.raises(AssertionError, match="env 400 of 1"):
+        strict.step(np.where(np.arange(n) == 400, 11, 0).astype(np.int32))      # host-buffer path too
+
+
+def test_torch_policy_rollout_graph_matches_host_replay():
+    """N1 with a general policy: a CUDA graph of K x [torch policy on the device observation -> ngw_step]; replayed twice;
+    the recorded actions are replayed through the oracle and every output must agree."""
+    cc = _compiled(C2_DESC)
+    n, K, A = 3000 + 17, 12, cc.c.n_actions
+    ob = OracleBatch([cc], n)
+    ob.reset_legacy(606)
+    h = BatchHandle([cc], n)
+    h.load_state(ob.map, ob.pose, ob.inv)
+    h.observe()
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    W = torch.randn((cc.obs_dim, A), generator=gen, device='cuda')
+    policy = lambda obs: torch.argmax(obs[:, :cc.obs_dim].float() @ W, dim=1).to(torch.int32)     # noqa: E731
+    graph, rec = h.capture_policy_rollout(policy, K)
+    h.load_state(ob.map, ob.pose, ob.inv)                      # the capture's warm-up did not step, but be explicit
+    h.observe()
+    for rep in range(2):
+        graph.replay()
+        torch.cuda.synchronize()
+        acts = rec['actions'].cpu().numpy()
+        rew = np.zeros(n)
+        for t in range(K):
+            obs_before = ob.observe()
+            want = torch.argmax(torch.from_numpy(obs_before).cuda().float() @ W, dim=1).cpu().numpy()
+            assert np.array_equal(acts[t], want), "replay %d step %d" % (rep, t)
+            o_obs, o_rew, o_done, o_cost, o_res = ob.step(acts[t])
+            rew += o_rew
+        assert np.array_equal(rec['obs'].cpu().numpy()[:, :cc.obs_dim], o_obs)
+        assert np.array_equal(rec['reward_sum'].cpu().numpy(), rew)
+        assert np.array_equal(h.map.cpu().numpy().reshape(n, -1), ob.map) and np.array_equal(h.inventory.cpu().numpy(), ob.inv)
+    assert len(np.unique(acts)) >= 3

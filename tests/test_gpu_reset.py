@@ -187,3 +187,75 @@ def test_agent_map_wrapper_single_and_batched():
         a = 0 if n == 1 else torch.zeros(n, dtype=torch.int32, device='cuda')
         obs, reward, done, info = env.step(a)
         assert 'agent_map' in obs and 'agent_facing_id' in obs and 'inventory_items_quantity' in obs
+
+
+def _chi2_two_sample(a, b, min_expected=5.0):
+    """two-sample chi-square statistic and its degrees of freedom for two count vectors of equal totals' order"""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    keep = (a + b) >= 2 * min_expected
+    ka, kb = np.sqrt(b.sum() / a.sum()), np.sqrt(a.sum() / b.sum())
+    stat = (((ka * a - kb * b) ** 2) / (a + b))[keep].sum()
+    return stat, int(keep.sum()) - 1
+
+
+@pytest.mark.parametrize('name,item_name', [('pogo_A_additem_hard', 'spring'), ('pogo_A_additem_easy', 'spring'),
+                                            ('pogo_A_fence_hard', 'oak_fence'), ('pogo_A_replaceitem_medium_log', 'birch_log'),
+                                            ('pogo_ms40_additem_hard', 'spring')])
+def test_subset_sampling_is_uniform_like_the_reference_shuffle(name, item_name):
+    """Fence / AddItem / ReplaceItem take "the first ceil(n pct / 100) of the shuffled candidates"
+    (novelty_wrappers.py:872-883,1017-1028,1130-1142).  The GPU draws pct and picks the m smallest of independent keys with
+    a warp radix-select; against the reference generator (legacy stream, via the oracle) it must reproduce
+      * the histogram of the number of chosen cells per env (= the randint(lo, hi) percentage law), and
+      * the per-cell marginals of the chosen item over the grid (a positional bias of the selection would show here),
+    both by two-sample chi-square tests at p > 1e-4."""
+    from scipy.stats import chi2
+    cc = _compiled(golden_util.get(name)['meta'])
+    item = cc.item_names.index(item_name)
+    n = 4096 if cc.map_size > 20 else 16384
+    h = BatchHandle([cc], n, seed=77)
+    h.reset()
+    m = h.export_state()[0].cpu().numpy().reshape(n, -1)
+    ok_g = h.error_flags.cpu().numpy() == 0
+    ref = OracleBatch([cc], n)
+    ok_r = ref.reset_legacy(4242) == 0
+    g, r = (m[ok_g] == item), (ref.map[ok_r] == item)
+    # (1) chosen cells per env
+    top = int(max(g.sum(1).max(), r.sum(1).max())) + 1
+    stat, df = _chi2_two_sample(np.bincount(g.sum(1), minlength=top), np.bincount(r.sum(1), minlength=top))
+    assert df >= 3 and stat < chi2.ppf(1 - 1e-4, df), ('count histogram', stat, df)
+    # (2) per-cell marginals
+    stat, df = _chi2_two_sample(g.sum(0), r.sum(0))
+    assert df >= 30 and stat < chi2.ppf(1 - 1e-4, df), ('per-cell marginals', stat, df)
+
+
+def test_subset_sampling_survives_tied_keys():
+    """The radix-select's boundary bin may hold more than 32 candidates only when their 32-bit keys are identical
+    (probability ~ n^2 / 2^33 per reset).  NGW_DEBUG_KEY_MASK keeps two key bits, which makes that the normal case: every
+    env must still receive exactly the number of cells its percentage draw asks for (the draw does not depend on the
+    keys, so the counts of a masked and an unmasked run with the same seed coincide), on candidate cells only."""
+    import os
+    for name, item_name in (('pogo_ms40_additem_hard', 'spring'), ('pogo_A_additem_hard', 'spring'), ('pogo_A_fence_hard', 'oak_fence')):
+        cc = _compiled(golden_util.get(name)['meta'])
+        item = cc.item_names.index(item_name)
+        n = 1024
+        plain = BatchHandle([cc], n, seed=5)
+        plain.reset()
+        os.environ['NGW_DEBUG_KEY_MASK'] = '0x3'
+        try:
+            tied = BatchHandle([cc], n, seed=5)
+        finally:
+            del os.environ['NGW_DEBUG_KEY_MASK']
+        tied.reset()
+        mp = plain.export_state()[0].cpu().numpy().reshape(n, -1)
+        mt = tied.export_state()[0].cpu().numpy().reshape(n, -1)
+        assert torch.equal(plain.pose, tied.pose)
+        if item_name == 'spring':                                     # AddItem: exactly m air cells become the item
+            # m cells are chosen; the agent's own cell, if among them, is skipped (novelty_wrappers.py:1027): m or m - 1
+            diff = (mp == item).sum(1) - (mt == item).sum(1)
+            assert np.abs(diff).max() <= 1 and (diff == 0).mean() > 0.5
+            assert not np.array_equal(mp, mt)                         # ... but different ones: the keys did change
+            assert ((mt == item) <= ((mp == 0) | (mp == item))).all()    # only cells that were air before the op
+        else:                                                         # Fence: the same number of items gets fenced in
+            base_items = lambda g: ((g != 0) & (g != item) & (g != cc.c.id_wall)).sum(1)
+            assert np.array_equal(base_items(mp), base_items(mt))
+            assert ((mt == item).sum(1) > 0).all()

@@ -205,7 +205,7 @@ static int build_lidar_tables(const ngw_config& c, int map_size, LidarDev& ld, s
     if (getenv("NGW_NO_FAST_LIDAR")) { fast = false; lines = false; }
     if (!lines) { memset(ld.firstk, 0, sizeof(ld.firstk)); memset(ld.rot, 0, sizeof(ld.rot)); }
     ld.fast = fast ? 1 : 0;
-    ld.lines = lines ? 1 : 0;
+    ld.lines = lines ? (getenv("NGW_LINE_LIDAR_BIG") ? 2 : 1) : 0;   // 2: A/B knob, line gather also on grids above 32x32
     if (!fast && lin) {
         int n = 4 * B * K;
         lin->resize(n);
@@ -280,7 +280,7 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     h->lidar_uniform = n_cfgs > 1;
     for (int i = 1; i < n_cfgs; i++) {
         const LidarDev &a = h->h_cfgs[0].lidar, &b = h->h_cfgs[i].lidar;
-        if (!a.fast || !b.fast || a.lines != b.lines || h->h_cfgs[0].c.max_range != h->h_cfgs[i].c.max_range ||
+        if (!a.fast || !b.fast || (a.lines != 0) != (b.lines != 0) || h->h_cfgs[0].c.max_range != h->h_cfgs[i].c.max_range ||
             memcmp(a.unit, b.unit, sizeof(a.unit)) != 0 || memcmp(a.disp, b.disp, sizeof(a.disp)) != 0)
             h->lidar_uniform = false;
     }
@@ -315,7 +315,7 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     h->obs_u8 = 0;
     h->obs_row_bytes = obs_row_bytes_of(h, 0);
     h->obs_bytes = 32 * h->obs_row_bytes;
-    const int one_tile = NGW_SMEM_HDR + 512 + 1024 + h->map_bytes + h->inv_bytes + 128 * h->obs_dim;
+    const int one_tile = NGW_SMEM_HDR + 512 + 1280 + h->map_bytes + h->inv_bytes + 128 * h->obs_dim;
     if (one_tile > 227 * 1024) return fail("ngw_create: map too large for shared memory");
     // G warps share one tile (the first two split the step by action class, all G cast the lidar lines): 2 for small
     // grids, 4 when shared memory limits the tiles per SM to a few
@@ -339,12 +339,15 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
         if (dc.c.n_beams <= 0 || !dc.lidar.lines) h->lidar_mode = 0;
     }
     if (n_cfgs > 1 && !h->lidar_uniform) h->lidar_mode = 0;
+    if (map_size > 32) h->lidar_mode = 0;           // large grids: pointer-walking beams (lidar_observe decides per lane)
 #define NGW_SMEM_ATTR(K) CK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
 #define NGW_SMEM_ATTR4(K, T, O) NGW_SMEM_ATTR((K<T, 0, O>)); NGW_SMEM_ATTR((K<T, 1, O>)); NGW_SMEM_ATTR((K<T, 4, O>)); NGW_SMEM_ATTR((K<T, 16, O>))
     NGW_SMEM_ATTR4(step1_kernel, true, true); NGW_SMEM_ATTR4(step1_kernel, true, false);
     NGW_SMEM_ATTR4(step1_kernel, false, true);
-    NGW_SMEM_ATTR4(step_kernel, true, true); NGW_SMEM_ATTR4(step_kernel, false, true);
 #undef NGW_SMEM_ATTR4
+    NGW_SMEM_ATTR((rollout_kernel<true, 0>)); NGW_SMEM_ATTR((rollout_kernel<true, 1>)); NGW_SMEM_ATTR((rollout_kernel<true, 4>));
+    NGW_SMEM_ATTR((rollout_kernel<true, 16>)); NGW_SMEM_ATTR((rollout_kernel<false, 0>)); NGW_SMEM_ATTR((rollout_kernel<false, 1>));
+    NGW_SMEM_ATTR((rollout_kernel<false, 4>)); NGW_SMEM_ATTR((rollout_kernel<false, 16>));
 #undef NGW_SMEM_ATTR
     return 0;
 }
@@ -511,7 +514,8 @@ static cudaError_t launch_rollout_nc(ngw_handle* h, StepParams p, cudaStream_t s
     const int luts = (NGW_MAX_MAP_SIZE + NGW_MAX_ITEMS * (NC > 0 ? NC : 0) + 127) & ~127;
     p.off_luts = NGW_SMEM_HDR;
     p.off_scratch = p.off_luts + luts;
-    p.off_in = p.off_scratch + 1024;
+    p.off_policy = p.off_scratch + ((NGW_RESET_SCRATCH_WORDS * 4 + 127) & ~127);
+    p.off_in = p.off_policy + (p.policy_w ? ((16 + p.obs_dim * p.policy_actions) * 4 + 127) & ~127 : 0);
     const long long tiles = (p.env_end - p.env_begin + 31) / 32;
     p.off_obs = p.off_in + in_bytes;
     const size_t smem = (size_t)p.off_obs + p.obs_bytes;
@@ -526,8 +530,8 @@ static cudaError_t launch_rollout_nc(ngw_handle* h, StepParams p, cudaStream_t s
     lc.stream = s;
     cudaLaunchAttribute attr[1];
     pdl_attr(h, s, lc, attr);
-    if (h->use_tma) return cudaLaunchKernelEx(&lc, step_kernel<true, NC, true>, args);
-    return cudaLaunchKernelEx(&lc, step_kernel<false, NC, true>, args);
+    if (h->use_tma) return cudaLaunchKernelEx(&lc, rollout_kernel<true, NC>, args);
+    return cudaLaunchKernelEx(&lc, rollout_kernel<false, NC>, args);
 }
 
 // one-step launches (ngw_step / ngw_step_host / ngw_observe): several tile groups per CTA

@@ -366,6 +366,33 @@ struct ObsRow {
     __device__ __forceinline__ int32_t* tail(int n_lidar) const {
         return reinterpret_cast<int32_t*>(p + (u8 ? ((n_lidar + 3) & ~3) : 4 * n_lidar));
     }
+    __device__ __forceinline__ void put_tail(int n_lidar, int i, int v) const { tail(n_lidar)[i] = v; }
+};
+
+// Observation "sink" of the closed-loop rollout: instead of materialising the (sparse) observation row and scanning it,
+// the integer linear policy  score[a] = bias[a] + sum_j obs[j] * W[j][a]  is accumulated entry by entry as the lidar
+// produces them (<= 8 ranges + the inventory tail).  W: [obs_dim][A] int32, staged in shared memory by the kernel.
+struct PolicySink {
+    const int32_t* w;
+    int A;
+    int acc[16];
+    __device__ __forceinline__ void init(const int32_t* weights, const int32_t* bias, int n_actions) {
+        w = weights; A = n_actions;
+#pragma unroll
+        for (int a = 0; a < 16; a++) acc[a] = a < A ? bias[a] : 0;
+    }
+    __device__ __forceinline__ void put(int idx, int v) {
+        const int32_t* row = w + idx * A;
+#pragma unroll
+        for (int a = 0; a < 16; a++) if (a < A) acc[a] += v * row[a];
+    }
+    __device__ __forceinline__ void put_tail(int n_lidar, int i, int v) { if (v != 0) put(n_lidar + i, v); }
+    __device__ __forceinline__ int argmax(int n_valid) const {       // first maximum over the env's valid action ids
+        int best = 0, best_v = acc[0];
+#pragma unroll
+        for (int a = 1; a < 16; a++) if (a < n_valid && acc[a] > best_v) { best_v = acc[a]; best = a; }
+        return best;
+    }
 };
 
 // Small per-config lookup tables the lidar reads with per-lane indices (shared memory in the step kernel, global
@@ -441,9 +468,9 @@ __device__ __forceinline__ void gather_lines(const int8_t* m, int ms_rt, int r, 
 
 // the two beams of one line: `p` = the agent's bit index on the line, `stride` = linear offset of one cell towards
 // higher bit indices, a_pos / a_neg = compass directions of the two beams
-template <typename MaskT>
+template <typename MaskT, typename Sink>
 __device__ __forceinline__ void line_beams(MaskT occ, int p, int stride, const int8_t* here, bool diagonal, int a_pos,
-                                           int a_neg, int K, int L, int rot, const LidarLuts& luts, const ObsRow& obs) {
+                                           int a_neg, int K, int L, int rot, const LidarLuts& luts, Sink& obs) {
     const MaskT hi = (occ >> p) >> 1;                                 // bit 0 = the cell next to the agent
     const MaskT lo = occ & (((MaskT)1 << p) - 1);
     const int n_pos = mask_ffs<MaskT>(hi);                            // cells to the first non-air cell, 0 = none
@@ -460,9 +487,9 @@ __device__ __forceinline__ void line_beams(MaskT occ, int p, int stride, const i
     }
 }
 
-template <typename MaskT, int MS, int SEL, bool kSafe>
+template <typename MaskT, int MS, int SEL, bool kSafe, typename Sink>
 __device__ __forceinline__ void lidar_lines_t(const EnvRow& e, const ngw_config& cfg, const LidarDev& t,
-                                              const LidarLuts& luts, const ObsRow& obs, int sel_rt) {
+                                              const LidarLuts& luts, Sink& obs, int sel_rt) {
     MaskT row, col, dg, an;
     gather_lines<MaskT, MS, SEL, kSafe>(e.m, e.ms, e.r, e.c, sel_rt, row, col, dg, an);
     const int ms = MS > 0 ? MS : e.ms;
@@ -471,22 +498,24 @@ __device__ __forceinline__ void lidar_lines_t(const EnvRow& e, const ngw_config&
     const int rot = (int)((*reinterpret_cast<const uint32_t*>(t.rot) >> (8 * e.facing)) & 7u);   // one uniform table read
     const int8_t* here = e.m + e.r * ms + e.c;
     // compass directions (d_row, d_col): 0 (+1,0)  1 (+1,+1)  2 (0,+1)  3 (-1,+1)  4 (-1,0)  5 (-1,-1)  6 (0,-1)  7 (+1,-1)
-    if (sel & 1) line_beams<MaskT>(row, e.c, 1, here, false, 2, 6, K, L, rot, luts, obs);
-    if (sel & 2) line_beams<MaskT>(col, e.r, ms, here, false, 0, 4, K, L, rot, luts, obs);
-    if (sel & 4) line_beams<MaskT>(dg, e.r, ms + 1, here, true, 1, 5, K, L, rot, luts, obs);
-    if (sel & 8) line_beams<MaskT>(an, e.r, ms - 1, here, true, 7, 3, K, L, rot, luts, obs);
+    if (sel & 1) line_beams<MaskT, Sink>(row, e.c, 1, here, false, 2, 6, K, L, rot, luts, obs);
+    if (sel & 2) line_beams<MaskT, Sink>(col, e.r, ms, here, false, 0, 4, K, L, rot, luts, obs);
+    if (sel & 4) line_beams<MaskT, Sink>(dg, e.r, ms + 1, here, true, 1, 5, K, L, rot, luts, obs);
+    if (sel & 8) line_beams<MaskT, Sink>(an, e.r, ms - 1, here, true, 7, 3, K, L, rot, luts, obs);
 }
 
 // `sel` is warp-uniform.  The hot shapes (the reference's 10x10 grid; all four lines, or the axis / diagonal halves of
-// a two-warp tile) get fully unrolled, unpredicated code; everything else shares two generic loops.
-template <bool kSafe>
+// a two-warp tile) get fully unrolled, unpredicated code; other sizes share two generic loops.  (Grids above 32x32 keep
+// the pointer-walking beams, see lidar_observe: on C5's dense 40x40 grids beams land after a few cells, and reading whole
+// 40-cell lines — or 16-cell windows outwards, also tried — measured 2-8 % slower than walking.)
+template <bool kSafe, typename Sink>
 __device__ __forceinline__ void lidar_lines(const EnvRow& e, const ngw_config& cfg, const LidarDev& t,
-                                            const LidarLuts& luts, const ObsRow& obs, int sel) {
-    if (!kSafe && e.ms == 10 && sel == 0xF) lidar_lines_t<uint32_t, 10, 0xF, false>(e, cfg, t, luts, obs, sel);
-    else if (!kSafe && e.ms == 10 && sel == 0x3) lidar_lines_t<uint32_t, 10, 0x3, false>(e, cfg, t, luts, obs, sel);
-    else if (!kSafe && e.ms == 10 && sel == 0xC) lidar_lines_t<uint32_t, 10, 0xC, false>(e, cfg, t, luts, obs, sel);
-    else if (e.ms <= 32) lidar_lines_t<uint32_t, 0, -1, kSafe>(e, cfg, t, luts, obs, sel);
-    else lidar_lines_t<uint64_t, 0, -1, kSafe>(e, cfg, t, luts, obs, sel);
+                                            const LidarLuts& luts, Sink& obs, int sel) {
+    if (!kSafe && e.ms == 10 && sel == 0xF) lidar_lines_t<uint32_t, 10, 0xF, false, Sink>(e, cfg, t, luts, obs, sel);
+    else if (!kSafe && e.ms == 10 && sel == 0x3) lidar_lines_t<uint32_t, 10, 0x3, false, Sink>(e, cfg, t, luts, obs, sel);
+    else if (!kSafe && e.ms == 10 && sel == 0xC) lidar_lines_t<uint32_t, 10, 0xC, false, Sink>(e, cfg, t, luts, obs, sel);
+    else if (e.ms <= 32) lidar_lines_t<uint32_t, 0, -1, kSafe, Sink>(e, cfg, t, luts, obs, sel);
+    else lidar_lines_t<uint64_t, 0, -1, kSafe, Sink>(e, cfg, t, luts, obs, sel);
 }
 
 // which of the four lines warp g of G handles (bit 0 row, 1 column, 2 diagonal, 3 anti-diagonal)
@@ -545,9 +574,9 @@ __device__ __forceinline__ void lidar_fast(const EnvRow& e, const ngw_config& cf
 }
 
 // inventory tail of the observation (observation_wrappers.py:77-78): quantities in sorted-name order minus unbreakables (Q7)
-__device__ __forceinline__ void obs_tail(const EnvRow& e, const ngw_config& cfg, const ObsRow& obs) {
-    const int n_tail = cfg.n_inv_obs;
-    int32_t* tail = obs.tail(cfg.n_lidar_items * cfg.n_beams);
+template <typename Sink>
+__device__ __forceinline__ void obs_tail(const EnvRow& e, const ngw_config& cfg, Sink& obs) {
+    const int n_tail = cfg.n_inv_obs, n_lidar = cfg.n_lidar_items * cfg.n_beams;
     const uint32_t w0 = *reinterpret_cast<const uint32_t*>(&cfg.inv_obs_item[0]);     // four item ids per table read
     const uint32_t w1 = *reinterpret_cast<const uint32_t*>(&cfg.inv_obs_item[4]);
     const int first = (int)(w0 & 0xFF);
@@ -559,16 +588,10 @@ __device__ __forceinline__ void obs_tail(const EnvRow& e, const ngw_config& cfg,
     if (contiguous && n_tail >= 4) {
         const int32_t* src = e.inv + first;
 #pragma unroll
-        for (int i = 0; i < 8; i++) if (i < n_tail) tail[i] = src[i];
+        for (int i = 0; i < 8; i++) if (i < n_tail) obs.put_tail(n_lidar, i, src[i]);
         return;
     }
-    int i = 0;
-    for (; i + 4 <= n_tail; i += 4) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(&cfg.inv_obs_item[i]);
-        const int v0 = e.inv[w & 0xFF], v1 = e.inv[(w >> 8) & 0xFF], v2 = e.inv[(w >> 16) & 0xFF], v3 = e.inv[w >> 24];
-        tail[i] = v0; tail[i + 1] = v1; tail[i + 2] = v2; tail[i + 3] = v3;
-    }
-    for (; i < n_tail; i++) tail[i] = e.inv[cfg.inv_obs_item[i]];
+    for (int i = 0; i < n_tail; i++) obs.put_tail(n_lidar, i, e.inv[cfg.inv_obs_item[i]]);
 }
 
 // `tables`: the beam tables to walk with — the env's own config, or (mixed batches whose configs all share one lidar
@@ -581,9 +604,10 @@ __device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& 
                                               bool with_tail) {
     const ngw_config& cfg = dc.c;
     const int B = cfg.n_beams, K = cfg.max_range, L = cfg.n_lidar_items;
-    if (dc.lidar.lines && luts.slot != nullptr) {
+    if (dc.lidar.lines && luts.slot != nullptr && (e.ms <= 32 || !dc.lidar.fast || dc.lidar.lines == 2)) {
         const int sel = lidar_line_share(g, G);
-        if (sel) lidar_lines<kSafe>(e, cfg, tables, luts, obs, sel);
+        ObsRow sink = obs;
+        if (sel) lidar_lines<kSafe, ObsRow>(e, cfg, tables, luts, sink, sel);
     } else if (dc.lidar.fast) {
         if (G == 1) lidar_fast<8>(e, cfg, tables, obs, zero, 0);
         else if (G == 2) lidar_fast<4>(e, cfg, tables, obs, zero, g * 4);
@@ -607,7 +631,7 @@ __device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& 
             }
         }
     }
-    if (with_tail) obs_tail(e, cfg, obs);
+    if (with_tail) { ObsRow sink = obs; obs_tail<ObsRow>(e, cfg, sink); }
 }
 
 // ------------------------------------------------------------------ reset (pogostick_v1_env.py:86-181 + novelty resets)
@@ -643,24 +667,46 @@ __device__ __forceinline__ bool reset_candidate(int kind, int id, int wall, int 
          : (id == a);                                                  // novelty_wrappers.py:1130
 }
 
-// hist: 256 uint32 of shared memory owned by the calling warp.  Returns error flags; pose in/out (uniform over lanes).
-__device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m, int32_t* inv, int ms, int inv_stride,
+// A TEAM regenerates one environment: TW == 1, the 32 lanes of one warp (ngw_reset: one env per warp, throughput-bound);
+// TW == 4, a whole CTA of 128 threads (the auto-reset queue consumer: few envs per step, latency-bound — one env per warp
+// took 10 k dependent instructions, 50-65 us, whatever the queue length).  All threads of the team call with the same
+// arguments.  `hist`: NGW_RESET_SCRATCH_WORDS uint32 of shared memory owned by the team.
+#define NGW_RESET_SCRATCH_WORDS (256 + 32)
+template <int TW> __device__ __forceinline__ void team_sync() { if (TW == 1) __syncwarp(); else __syncthreads(); }
+template <int TW> __device__ __forceinline__ int team_sum(int v, uint32_t* word) {
+    v = __reduce_add_sync(0xFFFFFFFFu, v);
+    if (TW == 1) return v;
+    if (threadIdx.x == 0) *word = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) atomicAdd(word, (uint32_t)v);
+    __syncthreads();
+    v = (int)*word;
+    __syncthreads();
+    return v;
+}
+
+template <int TW>
+__device__ __noinline__ uint32_t reset_env_team(const ngw_config* cfg, int8_t* m, int32_t* inv, int ms, int inv_stride,
                                                 uint64_t seed, uint64_t gid, uint32_t episode, bool do_base,
                                                 int op_begin, int op_end, uint32_t* hist, int& pr, int& pc, int& pf,
                                                 int& psel, uint32_t key_mask = 0xFFFFFFFFu) {
     const uint32_t FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
+    const int tid = TW == 1 ? lane : (int)threadIdx.x, NT = 32 * TW;
+    const bool lead = TW == 1 || threadIdx.x < 32;                    // the warp that does the serial parts
+    uint32_t* xw = hist + 256;                                        // [0] reduction word, [1] boundary-list length, [2..4] scan result
     const int cells = ms * ms;
     const int wall = cfg->id_wall;
     uint32_t err = 0;
     if (do_base) {
-        for (int i = lane; i < inv_stride; i += 32) inv[i] = 0;        // pogostick_v1_env.py:119-120
+        for (int i = tid; i < inv_stride; i += NT) inv[i] = 0;         // pogostick_v1_env.py:119-120
         psel = 0;
-        for (int i = lane; i < cells; i += 32) {                      // pogostick_v1_env.py:129-130
-            int r = i / ms, c = i - r * ms;
+        for (int r = tid / ms, c = tid - (tid / ms) * ms, i = tid; i < cells; i += NT) {   // pogostick_v1_env.py:129-130
             m[i] = (r == 0 || c == 0 || r == ms - 1 || c == ms - 1) ? (int8_t)wall : (int8_t)0;
+            c += NT;
+            while (c >= ms) { c -= ms; r++; }
         }
-        __syncwarp();
+        team_sync<TW>();
         Philox rng;
         rng.init(seed, gid, episode, 0);
         const int side = ms - 4;                                      // rows/cols 2 .. ms-3 (pogostick_v1_env.py:136-138)
@@ -691,8 +737,9 @@ __device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m
                                 pick--;
                             }
                 }
-                if (lane == 0) m[where] = (int8_t)item;
-                __syncwarp();
+                team_sync<TW>();                                      // every thread has read the grid it decided on
+                if (tid == 0) m[where] = (int8_t)item;
+                team_sync<TW>();
             }
         }
     }
@@ -701,49 +748,55 @@ __device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m
     for (int k = op_begin; k < op_end; k++) {
         const ngw_reset_op op = cfg->reset_ops[k];
         if (op.kind == NGW_RESET_INVSET) {                            // novelty_wrappers.py:33,460,668-671
-            if (lane == 0) inv[op.a] = op.lo;
-            __syncwarp();
+            if (tid == 0) inv[op.a] = op.lo;
+            team_sync<TW>();
             continue;
         }
         const uint32_t stream = 1 + k;
         if (op.kind == NGW_RESET_TREETAP) {                           // pogostick_v0_env.py:155-178
             // uniform over (tree_log, direction) pairs until the target cell is free == the reference's retry loop;
-            // the few draws are computed redundantly by all lanes
-            int n_logs = 0;
-            for (int i = lane; i < cells; i += 32) n_logs += (m[i] == (int8_t)op.b);
-            n_logs = __reduce_add_sync(FULL, n_logs);
-            if (n_logs <= 1) { err |= NGW_ERR_PLACEMENT; continue; }
-            Philox rt;
-            rt.init(seed, gid, episode, stream);
-            int target = -1;
-            for (int attempt = 0; attempt < 4096 && target < 0; attempt++) {
-                int direction = (int)rt.below(4);
-                int which = (int)rt.below((uint32_t)n_logs);
-                int log = -1;
-                for (int base = 0; base < cells && log < 0; base += 32) {     // which-th tree_log in row-major order
-                    int i = base + lane;
-                    uint32_t bal = __ballot_sync(FULL, i < cells && m[i] == (int8_t)op.b);
-                    int c = __popc(bal);
-                    if (which < c) {
-                        int bit = __fns(bal, 0, which + 1);
-                        log = base + bit;
-                    } else which -= c;
+            // done by the lead warp (a rare op on 10x10 grids), the draws redundantly by its lanes
+            int target = -1, n_logs = 0;
+            if (lead) {
+                for (int i = lane; i < cells; i += 32) n_logs += (m[i] == (int8_t)op.b);
+                n_logs = __reduce_add_sync(FULL, n_logs);
+                if (n_logs > 1) {
+                    Philox rt;
+                    rt.init(seed, gid, episode, stream);
+                    for (int attempt = 0; attempt < 4096 && target < 0; attempt++) {
+                        int direction = (int)rt.below(4);
+                        int which = (int)rt.below((uint32_t)n_logs);
+                        int log = -1;
+                        for (int base = 0; base < cells && log < 0; base += 32) {     // which-th tree_log in row-major order
+                            int i = base + lane;
+                            uint32_t bal = __ballot_sync(FULL, i < cells && m[i] == (int8_t)op.b);
+                            int c = __popc(bal);
+                            if (which < c) {
+                                int bit = __fns(bal, 0, which + 1);
+                                log = base + bit;
+                            } else which -= c;
+                        }
+                        int r = log / ms, c = log - r * ms;
+                        int tr = r + (direction == NGW_SOUTH) - (direction == NGW_NORTH);
+                        int tc = c + (direction == NGW_EAST) - (direction == NGW_WEST);
+                        if (tr >= 0 && tr < ms && tc >= 0 && tc < ms && m[tr * ms + tc] == 0 && tr * ms + tc != agent)
+                            target = tr * ms + tc;
+                    }
                 }
-                int r = log / ms, c = log - r * ms;
-                int tr = r + (direction == NGW_SOUTH) - (direction == NGW_NORTH);
-                int tc = c + (direction == NGW_EAST) - (direction == NGW_WEST);
-                if (tr >= 0 && tr < ms && tc >= 0 && tc < ms && m[tr * ms + tc] == 0 && tr * ms + tc != agent)
-                    target = tr * ms + tc;
+                if (lane == 0) { xw[2] = (uint32_t)n_logs; xw[3] = (uint32_t)target; }
             }
-            if (target < 0) { err |= NGW_ERR_PLACEMENT; continue; }
-            if (lane == 0) m[target] = (int8_t)op.a;
-            __syncwarp();
+            team_sync<TW>();
+            n_logs = (int)xw[2]; target = (int)xw[3];
+            team_sync<TW>();
+            if (n_logs <= 1 || target < 0) { err |= NGW_ERR_PLACEMENT; continue; }
+            if (tid == 0) m[target] = (int8_t)op.a;
+            team_sync<TW>();
             continue;
         }
         // ---- n candidates, percentage, m
         int n = 0;
-        for (int i = lane; i < cells; i += 32) n += reset_candidate(op.kind, m[i], wall, op.a);
-        n = __reduce_add_sync(FULL, n);
+        for (int i = tid; i < cells; i += NT) n += reset_candidate(op.kind, m[i], wall, op.a);
+        n = team_sum<TW>(n, &xw[0]);
         Philox rng;
         rng.init(seed, gid, episode, stream);
         const int pct = op.lo + (int)rng.below((uint32_t)(op.hi - op.lo));            // randint(low, high), high exclusive
@@ -754,11 +807,11 @@ __device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m
         //      keys whose top bits == prefix compete for the `remaining` last places
         uint32_t prefix = 0;
         int bits = 0, remaining = take, bin_count = n;
-        const int quads = (cells + 3) >> 2;                           // a lane handles 4 consecutive cells per Philox block
+        const int quads = (cells + 3) >> 2;                           // a thread handles 4 consecutive cells per Philox block
         while (remaining < bin_count && bin_count > 32 && bits < 32) {
-            for (int i = lane; i < 256; i += 32) hist[i] = 0;
-            __syncwarp();
-            for (int q = lane; q < quads; q += 32) {
+            for (int i = tid; i < 256; i += NT) hist[i] = 0;
+            team_sync<TW>();
+            for (int q = tid; q < quads; q += NT) {
                 bool cand[4], any = false;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -776,46 +829,44 @@ __device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m
                     if (cand[j] && (bits == 0 || (key[j] >> (32 - bits)) == prefix))
                         atomicAdd(&hist[(key[j] >> (24 - bits)) & 0xFF], 1u);
             }
-            __syncwarp();
-            uint32_t mine[8], sum = 0;
+            team_sync<TW>();
+            if (lead) {                                               // the lead warp scans the 256 bins, 8 per lane
+                uint32_t mine[8], sum = 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) { mine[j] = hist[lane * 8 + j]; sum += mine[j]; }
-            uint32_t incl = sum;
+                for (int j = 0; j < 8; j++) { mine[j] = hist[lane * 8 + j]; sum += mine[j]; }
+                uint32_t incl = sum;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += t;
-            }
-            uint32_t excl = incl - sum;
-            bool owner = (uint32_t)remaining > excl && (uint32_t)remaining <= incl;   // the bin holding the remaining-th key
-            int bin = 0; uint32_t below = excl, cnt = 0;
-            if (owner) {
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t t = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                uint32_t excl = incl - sum;
+                bool owner = (uint32_t)remaining > excl && (uint32_t)remaining <= incl;   // the bin holding the remaining-th key
+                if (owner) {
+                    uint32_t below = excl;
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if (cnt == 0) {
-                        if ((uint32_t)remaining <= below + mine[j]) { bin = lane * 8 + j; cnt = mine[j]; }
-                        else below += mine[j];
+                    for (int j = 0; j < 8; j++) {
+                        if ((uint32_t)remaining <= below + mine[j]) { xw[2] = (uint32_t)(lane * 8 + j); xw[3] = below; xw[4] = mine[j]; break; }
+                        below += mine[j];
                     }
                 }
             }
-            int src = __ffs(__ballot_sync(FULL, owner)) - 1;
-            bin = __shfl_sync(FULL, bin, src);
-            below = __shfl_sync(FULL, below, src);
-            cnt = __shfl_sync(FULL, cnt, src);
-            prefix = (prefix << 8) | (uint32_t)bin;
+            team_sync<TW>();
+            const uint32_t bin = xw[2], below = xw[3], cnt = xw[4];
+            team_sync<TW>();
+            prefix = (prefix << 8) | bin;
             bits += 8;
             remaining -= (int)below;
             bin_count = (int)cnt;
-            __syncwarp();
         }
         // ---- apply: one pass; winners are written at once, boundary-bin cells (<= 32, unless all of them win) are listed
         const bool all_in_bin_win = remaining >= bin_count;
         const bool exact_keys = bits >= 32 && bin_count > 32;
-        int n_list = 0;
-        uint32_t my_key = 0; int my_idx = -1;
         const int value = op.kind == NGW_RESET_ADDITEM ? op.a : op.b;
-        for (int qb = 0; qb < quads; qb += 32) {
-            const int q = qb + lane;
+        if (tid == 0) xw[1] = 0;
+        team_sync<TW>();
+        for (int qb = 0; qb < quads; qb += NT) {
+            const int q = qb + tid;
             uint32_t key[4] = {0, 0, 0, 0};
             int id[4]; bool cand[4], any = false;
 #pragma unroll
@@ -834,23 +885,31 @@ __device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m
                 bool wins = cand[j] && (bits == 0 ? all_in_bin_win : (top < prefix || (top == prefix && all_in_bin_win)));
                 bool boundary = cand[j] && !all_in_bin_win && top == prefix;
                 uint32_t bal = __ballot_sync(FULL, boundary);
-                if (boundary) {
-                    int slot = n_list + __popc(bal & ((1u << lane) - 1u));
-                    // all 32 key bits consumed and still more than 32 contenders: their keys are IDENTICAL (probability
-                    // ~ n^2 / 2^33 per reset), so the tie goes by visiting order and no list is needed
-                    if (exact_keys) wins = slot < remaining;
-                    else if (slot < 32) { hist[slot] = key[j]; hist[32 + slot] = (uint32_t)i; }
+                if (bal != 0) {
+                    // a slot per boundary cell: warp-aggregated counter in shared memory (visiting order across the team's
+                    // warps is arbitrary, which is fine: the list is ranked by (key, cell) afterwards)
+                    int base = 0;
+                    if (lane == __ffs((int)bal) - 1) base = (int)atomicAdd(&xw[1], (uint32_t)__popc(bal));
+                    base = __shfl_sync(FULL, base, __ffs((int)bal) - 1);
+                    if (boundary) {
+                        int slot = base + __popc(bal & ((1u << lane) - 1u));
+                        // all 32 key bits consumed and still more than 32 contenders: their keys are IDENTICAL (probability
+                        // ~ n^2 / 2^33 per reset), so the tie goes by arrival order and no list is needed
+                        if (exact_keys) wins = slot < remaining;
+                        else if (slot < 32) { hist[slot] = key[j]; hist[32 + slot] = (uint32_t)i; }
+                    }
                 }
-                n_list += __popc(bal);
                 if (wins) {
                     if (op.kind == NGW_RESET_FENCE) m[i] = (int8_t)(id[j] | 0x80);    // mark; fences go in afterwards
                     else if (i != agent) m[i] = (int8_t)value;                        // novelty_wrappers.py:1027,1141
                 }
             }
         }
-        __syncwarp();
-        if (n_list > 0 && !exact_keys) {
+        team_sync<TW>();
+        int n_list = (int)xw[1];
+        if (n_list > 0 && !exact_keys && lead) {
             if (n_list > 32) n_list = 32;                             // unreachable: the loop above ends with <= 32 contenders or exact keys
+            uint32_t my_key = 0; int my_idx = -1;
             if (lane < n_list) { my_key = hist[lane]; my_idx = (int)hist[32 + lane]; }
             int rank = 0;
             for (int j = 0; j < n_list; j++) {
@@ -863,22 +922,36 @@ __device__ __noinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m
                 else if (my_idx != agent) m[my_idx] = (int8_t)value;
             }
         }
-        __syncwarp();
+        team_sync<TW>();
         if (op.kind == NGW_RESET_FENCE) {                             // add_fence_around, pogostick_v1_env.py:524-536
-            for (int i = lane; i < cells; i += 32) {
+            // two phases so that the team's warps do not race: read every mark first, then write the fences
+            for (int i = tid; i < cells; i += NT) {
                 int v = m[i];
                 if (!(v & 0x80)) continue;
-                m[i] = (int8_t)(v & 0x7F);
                 int r = i / ms, c = i - r * ms;
                 for (int rr = r - 1; rr <= r + 1; rr++)
                     for (int cc = c - 1; cc <= c + 1; cc++)
                         if (rr >= 0 && rr < ms && cc >= 0 && cc < ms && m[rr * ms + cc] == 0 && rr * ms + cc != agent)
                             m[rr * ms + cc] = (int8_t)op.a;
             }
-            __syncwarp();
+            team_sync<TW>();
+            for (int i = tid; i < cells; i += NT) {
+                int v = m[i];
+                if (v & 0x80) m[i] = (int8_t)(v & 0x7F);
+            }
+            team_sync<TW>();
         }
     }
     return err;
+}
+
+// the one-env-per-warp form (ngw_reset, the in-place regeneration of the rollout kernel)
+__device__ __forceinline__ uint32_t reset_env_warp(const ngw_config* cfg, int8_t* m, int32_t* inv, int ms, int inv_stride,
+                                                   uint64_t seed, uint64_t gid, uint32_t episode, bool do_base,
+                                                   int op_begin, int op_end, uint32_t* hist, int& pr, int& pc, int& pf,
+                                                   int& psel, uint32_t key_mask = 0xFFFFFFFFu) {
+    return reset_env_team<1>(cfg, m, inv, ms, inv_stride, seed, gid, episode, do_base, op_begin, op_end, hist, pr, pc, pf,
+                             psel, key_mask);
 }
 
 }  // namespace ngw

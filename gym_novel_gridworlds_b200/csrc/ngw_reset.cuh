@@ -33,7 +33,7 @@ struct ResetParams {
 // The cold kernels regenerate an env on a shared-memory copy of its rows (every pass of reset_env_warp would otherwise
 // pay HBM latency) and write the rows back with coalesced stores.
 struct ResetScratch {
-    uint32_t hist[256];
+    uint32_t hist[NGW_RESET_SCRATCH_WORDS];
     int32_t inv[NGW_MAX_ITEMS];
     int8_t row[NGW_MAX_MAP_SIZE * NGW_MAX_MAP_SIZE];
 };
@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_kernel(const Reset
 // observation row and writes the rows back.  Like ngw_reset, the observation of the new episode is taken after
 // reset_obs_after_ops ops (quirk Q3: a novelty wrapped outside LidarInFront patches the state after the observation
 // was computed).  The last CTA to finish empties the queue for the next step.
+// (Measured and rejected: a whole CTA of 4 warps per env, reset_env_team<4> — at 96 registers only 5 such CTAs fit an SM, the
+// ~2000 queued envs of a C5 step then take three rounds instead of one: 356 vs 315 us per step.)
 __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_list_kernel(const ResetParams p) {
     __shared__ ResetScratch scratch[NGW_RESET_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -106,7 +106,7 @@ struct StepParams {
                                 // 16 bytes more when the row is a multiple of 8 words (64-word rows would put every
                                 // lane's row on the same bank: C4 / C5 measured 64-71 % of their shared wavefronts as conflicts)
     // shared-memory carve-up (bytes from the start of dynamic shared memory), all multiples of 128
-    int off_luts, off_scratch, off_in, off_obs;          // rollout kernel (one tile per CTA)
+    int off_luts, off_scratch, off_policy, off_in, off_obs;   // rollout kernel (one tile per CTA)
     int off_groups, group_bytes;                         // one-step kernel: tile group k lives at off_groups + k * group_bytes
     int tiles_per_cta, g_shift, n_tiles;                 // one-step kernel: tile groups per CTA, log2(warps per tile), tiles
     int lidar_mode;             // 1: every config takes the line-gather path with one shared geometry (the common case)
@@ -204,39 +204,20 @@ __device__ __forceinline__ void tile_stats(double* stats, int slot, int lane, in
     }
 }
 
-// closed-loop policy of ngw_rollout_policy: argmax_a (b[a] + sum_j obs[j] W[j][a]) over the env's valid ids, first maximum
-__device__ __forceinline__ int linear_policy_action(const StepParams& p, const ngw_config& cfg, const int32_t* row) {
-    int acc[16];
-    const int A = p.policy_actions;
-#pragma unroll
-    for (int a = 0; a < 16; a++) acc[a] = a < A ? p.policy_b[a] : 0;
-    const int D = cfg.n_lidar_items * cfg.n_beams + cfg.n_inv_obs;
-    for (int j = 0; j < D; j++) {
-        const int v = row[j];
-        if (v == 0) continue;                                         // the observation is sparse (<= 8 hits + inventory)
-        const int32_t* w = p.policy_w + (size_t)j * A;
-#pragma unroll
-        for (int a = 0; a < 16; a++) if (a < A) acc[a] += v * w[a];
-    }
-    int best = 0, best_v = acc[0];
-    const int n_valid_actions = cfg.n_actions < A ? cfg.n_actions : A;
-#pragma unroll
-    for (int a = 1; a < 16; a++) if (a < n_valid_actions && acc[a] > best_v) { best_v = acc[a]; best = a; }
-    return best;
-}
-
-// ------------------------------------------------------------------ the fused step + LidarInFront kernel
-// One CTA = one tile of 32 consecutive envs; lane l of every warp owns env l of the tile; G = blockDim.x / 32 warps
-// share the tile.  With G >= 2 the step itself is split by ACTION CLASS: warp 0 executes the lanes whose action is a
-// turn / craft / select, warp 1 the lanes that move or touch the block in front — each warp then walks only half of
-// the divergent per-action paths, on disjoint envs.  After one barrier all G warps cast the LidarInFront lines of their
-// lane's env (G = 2: axis lines / diagonal lines).  (Measured and rejected, see profiles/README.md: several tiles per
-// CTA through a ring of staged buffers — the kernel is bound by per-tile latency, not by bandwidth.)
+// ------------------------------------------------------------------ the K-STEP ROLLOUT kernel (ngw_rollout, ngw_rollout_policy)
+// SURVEY §8f N1.  One CTA = one tile of 32 consecutive envs that stays in shared memory for n_steps steps; lane l owns env
+// l.  Warp 0 runs the steps; actions come from a [K][N] tensor (next step's action prefetched behind the current step),
+// from an on-device uniform random policy (Philox keyed by global env id and step), or — the closed loop — from an integer
+// linear policy evaluated on each step's LidarInFront observation.  The closed loop never materialises that observation:
+// the lidar feeds a PolicySink that accumulates  score[a] = bias[a] + sum_j obs[j] W[j][a]  hit by hit, with W staged in
+// shared memory.  Finished lanes are regenerated in place by the step warp (auto_reset_warp).  After the last step all G
+// warps cast the final observation, which leaves with the inventory tile through two TMA bulk stores; the other outputs are
+// per-env sums (reward, step_cost, episodes finished) and the last step's done / result.
 #define NGW_CLASS1_OPS ((1u << NGW_OP_FORWARD) | (1u << NGW_OP_BREAK) | (1u << NGW_OP_PLACE_TREE_TAP) | \
                         (1u << NGW_OP_EXTRACT_RUBBER) | (1u << NGW_OP_EXTRACT_STRING) | (1u << NGW_OP_CHOP) | (1u << NGW_OP_JUMP))
 
-template <bool kTma, int NC, bool kMulti>
-__global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepArgs<NC> args) {
+template <bool kTma, int NC>
+__global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ StepArgs<NC> args) {
     extern __shared__ __align__(128) unsigned char smem[];
     const StepParams& p = args.p;
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, G = blockDim.x >> 5;
@@ -244,17 +225,18 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
     const long long e = e0 + lane;
     const bool valid = e < p.env_end;
     const bool full_tile = e0 + 32 <= p.env_end;
-    const bool stepping = p.actions != nullptr;
 
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);               // "tile landed" barrier
     int8_t* szero = reinterpret_cast<int8_t*>(smem + 32);            // 8 bytes that always read 0 (landed lidar beams park here)
-    uchar4* spose = reinterpret_cast<uchar4*>(smem + 64);            // pose after the step, for the other warps
+    uchar4* spose = reinterpret_cast<uchar4*>(smem + 64);            // pose after the last step, for the other warps
     uint8_t* sfirstk = smem + p.off_luts;                            // lidar tables read with per-lane indices
     int8_t* sslot = reinterpret_cast<int8_t*>(smem + p.off_luts + NGW_MAX_MAP_SIZE);
-    uint32_t* sscratch = reinterpret_cast<uint32_t*>(smem + p.off_scratch);   // radix-select histogram (rollout only)
+    uint32_t* sscratch = reinterpret_cast<uint32_t*>(smem + p.off_scratch);   // radix-select scratch of the in-place auto-reset
+    int32_t* spol = reinterpret_cast<int32_t*>(smem + p.off_policy); // closed loop: bias [16] | W [obs_dim][A]
     int8_t* smap = reinterpret_cast<int8_t*>(smem + p.off_in);
     int32_t* sinv = reinterpret_cast<int32_t*>(smem + p.off_in + p.map_bytes);
     unsigned char* sobs = smem + p.off_obs;
+    const bool closed_loop = p.policy_w != nullptr;
 
     // ---- prologue without global state: barrier, zero pad, lidar tables, zeroed observation tile
     const int8_t* gmap = p.map + e0 * p.cells;
@@ -276,23 +258,19 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
     if (p.obs != nullptr) {
         const uint4 z = make_uint4(0, 0, 0, 0);
         uint4* o4 = reinterpret_cast<uint4*>(sobs);
-        const int n16 = p.obs_bytes >> 4;
-#pragma unroll 4
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) o4[i] = z;
+        for (int i = threadIdx.x; i < (p.obs_bytes >> 4); i += blockDim.x) o4[i] = z;
     }
     __syncthreads();                                                 // barrier init visible before anyone waits on it
     asm volatile("griddepcontrol.wait;" ::: "memory");               // previous kernel of the stream done + visible
-    if (p.dbg_skip & 64) { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); return; }
 
     // ---- stage the tile: grid rows + inventory rows (state arrays are padded, a full tile is always readable)
-    uint64_t pol_first = 0;
     if (kTma) {
         if (threadIdx.x == 0) {
             mbar_expect_tx(bar, (uint32_t)(p.map_bytes + p.inv_bytes));
-            if (p.cache_hints) pol_first = policy_evict_first();
             if (p.cache_hints & 1) {
-                bulk_g2s_hint(smap, gmap, (uint32_t)p.map_bytes, bar, pol_first);
-                bulk_g2s_hint(sinv, ginv, (uint32_t)p.inv_bytes, bar, pol_first);
+                uint64_t pol = policy_evict_first();
+                bulk_g2s_hint(smap, gmap, (uint32_t)p.map_bytes, bar, pol);
+                bulk_g2s_hint(sinv, ginv, (uint32_t)p.inv_bytes, bar, pol);
             } else {
                 bulk_g2s(smap, gmap, (uint32_t)p.map_bytes, bar);
                 bulk_g2s(sinv, ginv, (uint32_t)p.inv_bytes, bar);
@@ -306,9 +284,13 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
         d4 = reinterpret_cast<uint4*>(sinv);
         for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
     }
+    if (closed_loop) {                                               // the policy's weights, once per CTA
+        const int n_w = p.obs_dim * p.policy_actions;
+        for (int i = threadIdx.x; i < 16; i += blockDim.x) spol[i] = i < p.policy_actions ? p.policy_b[i] : 0;
+        for (int i = threadIdx.x; i < n_w; i += blockDim.x) spol[16 + i] = p.policy_w[i];
+    }
 
     // ---- while the copies fly: per-lane scalars
-    const int n_cls = (!kMulti && G >= 2) ? 2 : 1;                   // warps that take part in the step
     const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[e];
     const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
     const ngw_config& cfg = dc.c;
@@ -327,117 +309,113 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
     orow.u8 = p.obs_u8;
     uchar4 ps = make_uchar4(0, 0, 0, 0);
     int action = 0;
-    if (g < n_cls) {
+    const bool given_actions = !(p.random_policy || closed_loop);     // else `actions` is only a non-null marker
+    if (g == 0) {
         ps = p.pose[e];
-        const bool given_actions = !(kMulti && (p.random_policy || p.policy_w != nullptr));   // else `actions` is a marker
-        if (stepping && valid && given_actions) action = p.actions[e];
+        if (valid && given_actions) action = p.actions[e];
     }
 
     if (kTma) mbar_wait(bar, 0);
-    else __syncthreads();
-    if (p.dbg_skip & 128) { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); return; }
+    __syncthreads();                                                 // plain copies / policy weights visible to the step warp
 
-    StepOut st_out;                                                  // one-step kernel: outputs and statistics are written
-    st_out.reward = 0; st_out.done = 0; st_out.result = 0; st_out.cost = 0.0f; st_out.msg = 0; st_out.goal = 0;   // after the tile stores
-    int st_success = 0, st_reset = 0, st_invalid = 0;
-    bool mine = false;                                               // this warp stepped this lane's env
     EnvRow env;
     env.m = smap + lane * p.cells;
     env.gm = p.map + e * p.cells;
     env.inv = sinv + lane * p.inv_stride;
     env.ms = p.ms;
 
-    if (g < n_cls) {
+    if (g == 0) {
         env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
-        if (stepping) {
-            StepOut o;
-            o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0; o.goal = 0;
-            float reward_sum = 0.0f, cost_sum = 0.0f;
-            int done_count = 0;
-            const int n_steps = kMulti ? p.n_steps : 1;               // kMulti == false: the plain one-step kernel
-            const bool random_policy = kMulti && p.random_policy;
-            const bool closed_loop = kMulti && p.policy_w != nullptr;
-            for (int t = 0; t < n_steps; t++) {
-                int next_action = 0;                                  // prefetch the next step's action behind this step
-                if (!random_policy && !closed_loop && t + 1 < n_steps && valid)
-                    next_action = p.actions[(t + 1) * p.act_stride + e];
-                if (closed_loop) {                                    // observe, then greedy linear policy (int32 rows only)
+        StepOut o;
+        o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0; o.goal = 0;
+        float reward_sum = 0.0f, cost_sum = 0.0f;
+        int done_count = 0;
+        // the sink needs the line-gather lidar (lidar_observe would take the same branch); otherwise the observation row
+        // is materialised and scanned
+        const bool use_sink = closed_loop && dc.lidar.lines && luts.slot != nullptr && (p.ms <= 32 || !dc.lidar.fast);
+        for (int t = 0; t < p.n_steps; t++) {
+            int next_action = 0;                                      // prefetch the next step's action behind this step
+            if (given_actions && t + 1 < p.n_steps && valid) next_action = p.actions[(t + 1) * p.act_stride + e];
+            if (closed_loop) {                                        // observe, then greedy linear policy (int32 arithmetic)
+                const int n_valid = cfg.n_actions < p.policy_actions ? cfg.n_actions : p.policy_actions;
+                if (use_sink) {
+                    PolicySink sink;
+                    sink.init(spol + 16, spol, p.policy_actions);
+                    if (valid && cfg.n_beams > 0) {
+                        lidar_lines<false, PolicySink>(env, cfg, beam_tables, luts, sink, 0xF);
+                        obs_tail<PolicySink>(env, cfg, sink);
+                    }
+                    action = sink.argmax(n_valid);
+                } else {
                     int32_t* row = reinterpret_cast<int32_t*>(orow.p);
                     for (int j = 0; j < p.obs_dim; j++) row[j] = 0;
                     if (valid && cfg.n_beams > 0) lidar_observe<false>(env, dc, beam_tables, luts, orow, szero, 0, 1, true);
-                    if (valid) action = linear_policy_action(p, cfg, row);
-                } else if (random_policy && valid) {                  // uniform over the config's action ids
-                    Philox pr;
-                    pr.init(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, 0xFFF);
-                    action = (int)pr.below((uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
+                    PolicySink sink;
+                    sink.init(spol + 16, spol, p.policy_actions);
+                    const int D = cfg.n_lidar_items * cfg.n_beams + cfg.n_inv_obs;
+                    for (int j = 0; j < D; j++) {
+                        const int v = row[j];
+                        if (v != 0) sink.put(j, v);                    // the observation is sparse (<= 8 hits + inventory)
+                    }
+                    action = sink.argmax(n_valid);
                 }
-                if (kMulti && p.actions_out != nullptr && valid) p.actions_out[t * p.act_stride + e] = action;
-                o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0; o.goal = 0;
-                int invalid = 0, did_reset = 0, success = 0;
+            } else if (p.random_policy && valid) {                    // uniform over the config's action ids
+                Philox pr;
+                pr.init(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, 0xFFF);
+                action = (int)pr.below((uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
+            }
+            if (p.actions_out != nullptr && valid) p.actions_out[t * p.act_stride + e] = action;
+            o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0; o.goal = 0;
+            int invalid = 0, did_reset = 0, success = 0;
+            if (valid) {
                 ngw_action_entry a;
                 a.op = NGW_OP_INVALID;
-                if (valid && action >= 0 && action < cfg.n_actions) {
+                if (action >= 0 && action < cfg.n_actions) {
                     uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
                     memcpy(&a, &raw, sizeof(a));
                 }
-                // action class of the lane: which of the stepping warps executes it
-                mine = valid && (n_cls == 1 || (int)((NGW_CLASS1_OPS >> a.op) & 1u) == g);
-                if (mine) {
-                    if (a.op == NGW_OP_INVALID) {                     // wrappers.py:76 / pogostick_v1_env.py:236 would raise
-                        invalid = 1;
-                        p.err[e] |= NGW_ERR_INVALID_ACTION;
-                    } else {
-                        if (!(p.dbg_skip & 1)) step_env(env, cfg, a, o);
-                        success = o.done && env.inv[cfg.id_goal] >= 1;
-                        int finished = o.done;
-                        if (p.max_episode_steps > 0) {
-                            int len = p.ep_len[e] + 1;
-                            if (len >= p.max_episode_steps) { finished = 1; o.done = 1; } // harness truncation knob
-                            p.ep_len[e] = finished && p.auto_reset ? 0 : len;
-                        }
-                        if (finished && p.auto_reset) { did_reset = 1; }
+                if (a.op == NGW_OP_INVALID) {                         // wrappers.py:76 / pogostick_v1_env.py:236 would raise
+                    invalid = 1;
+                    p.err[e] |= NGW_ERR_INVALID_ACTION;
+                } else {
+                    step_env(env, cfg, a, o);
+                    success = o.goal;
+                    int finished = o.done;
+                    if (p.max_episode_steps > 0) {
+                        int len = p.ep_len[e] + 1;
+                        if (len >= p.max_episode_steps) { finished = 1; o.done = 1; }   // harness truncation knob
+                        p.ep_len[e] = finished && p.auto_reset ? 0 : len;
                     }
-                    ps = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing,
-                                     (unsigned char)env.sel);
-                    reward_sum += (float)o.reward; cost_sum += o.cost; done_count += o.done;
+                    if (finished && p.auto_reset) did_reset = 1;
                 }
-                if (p.auto_reset) {
-                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, did_reset);
-                    if (bal != 0 && !kMulti) {
-                        // single step: queue the finished envs; reset_list_kernel (next in the stream, one warp per env at
-                        // full occupancy) regenerates them and overwrites their observation rows
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(p.reset_count, __popc(bal));
-                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                        if (did_reset) p.reset_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)e;
-                    } else if (bal != 0) {
-                        // rollout: the next step needs the new episode now -> regenerate in place, warp-cooperatively
-                        auto_reset_warp(p, p.dcfgs, cfg_i, did_reset != 0, smap, sinv, sscratch, e0, ps);
-                        env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
-                    }
+                ps = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing, (unsigned char)env.sel);
+                reward_sum += (float)o.reward; cost_sum += o.cost; done_count += o.done;
+            }
+            if (p.auto_reset) {
+                // the next step needs the new episode now -> regenerate in place, warp-cooperatively
+                if (__ballot_sync(0xFFFFFFFFu, did_reset) != 0) {
+                    auto_reset_warp(p, p.dcfgs, cfg_i, did_reset != 0, smap, sinv, sscratch, e0, ps);
+                    env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
                 }
-                if (kMulti && p.stats != nullptr)
-                    tile_stats(p.stats, (int)blockIdx.x, lane, valid, o.done, success, did_reset, invalid, o.reward, o.cost);
-                if (!kMulti) { st_success = success; st_reset = did_reset; st_invalid = invalid; }
-                action = next_action;
             }
-            if (closed_loop) {                                        // the last policy observation must not leak into the final one
-                int32_t* row = reinterpret_cast<int32_t*>(orow.p);
-                for (int j = 0; j < p.obs_dim; j++) row[j] = 0;
-            }
-            if (!kMulti) st_out = o;                                  // one-step kernel: outputs are stored after the tile stores
-            if (kMulti && valid) {
-                p.pose[e] = ps;
-                p.reward[e] = reward_sum;
-                p.done[e] = (uint8_t)o.done;
-                p.cost[e] = cost_sum;
-                p.result[e] = (uint8_t)o.result;
-                if (p.done_count != nullptr) p.done_count[e] = done_count;
-                if (p.msg != nullptr) p.msg[e] = (uint16_t)o.msg;
-            }
+            if (p.stats != nullptr)
+                tile_stats(p.stats, (int)blockIdx.x, lane, valid, o.done, success, did_reset, invalid, o.reward, o.cost);
+            action = next_action;
         }
-        // hand the pose over: the warp that stepped the lane (or, when nothing was stepped, warp 0) publishes it
-        if (G > 1 && (stepping ? (mine || (g == 0 && !valid)) : g == 0)) spose[lane] = ps;
+        if (closed_loop && !use_sink) {                               // the last policy observation must not leak into the final one
+            int32_t* row = reinterpret_cast<int32_t*>(orow.p);
+            for (int j = 0; j < p.obs_dim; j++) row[j] = 0;
+        }
+        if (valid) {
+            p.pose[e] = ps;
+            p.reward[e] = reward_sum;
+            p.done[e] = (uint8_t)o.done;
+            p.cost[e] = cost_sum;
+            p.result[e] = (uint8_t)o.result;
+            if (p.done_count != nullptr) p.done_count[e] = done_count;
+            if (p.msg != nullptr) p.msg[e] = (uint16_t)o.msg;
+        }
+        if (G > 1) spose[lane] = ps;
     }
     if (G > 1) {
         __syncthreads();                                             // step results (grid, inventory, pose) visible to all warps
@@ -445,30 +423,30 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
         env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
     }
 
-    // ---- LidarInFront observation of the (possibly auto-reset) state into the shared-memory tile
-    if (p.obs != nullptr && valid && cfg.n_beams > 0 && !(p.dbg_skip & 2))
+    // ---- LidarInFront observation of the final state into the shared-memory tile
+    if (p.obs != nullptr && valid && cfg.n_beams > 0)
         lidar_observe<false>(env, dc, beam_tables, luts, orow, szero, g, G, g == G - 1);
 
-    // ---- write back: inventory tile (only when stepping) and observation tile.  Every thread orders its generic-proxy
-    //      writes to the tiles before the async proxy reads them (fence before the barrier), then one thread issues.
+    // ---- write back: inventory tile and observation tile.  Every thread orders its generic-proxy writes to the tiles
+    //      before the async proxy reads them (fence before the barrier), then one thread issues.
     if (kTma) fence_async_smem();
     __syncthreads();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (kTma && full_tile && !p.plain_store) {
         if (threadIdx.x == 0) {
-            if (stepping && !(p.dbg_skip & 16)) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
-            if (p.obs != nullptr && !(p.dbg_skip & 8)) {
+            bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
+            if (p.obs != nullptr) {
                 unsigned char* gobs = p.obs + e0 * p.obs_row_bytes;
-                if (p.cache_hints & 2) bulk_s2g_hint(gobs, sobs, (uint32_t)p.obs_bytes, pol_first);
+                if (p.cache_hints & 2) bulk_s2g_hint(gobs, sobs, (uint32_t)p.obs_bytes, policy_evict_first());
                 else bulk_s2g(gobs, sobs, (uint32_t)p.obs_bytes);
             }
             bulk_commit();
+            bulk_wait_read<0>();                                     // shared memory must outlive the bulk stores' reads
         }
     } else {
-        if (stepping) {
-            const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
-            uint4* d4 = reinterpret_cast<uint4*>(ginv);
-            for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
-        }
+        const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
+        uint4* d4 = reinterpret_cast<uint4*>(ginv);
+        for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += blockDim.x) d4[i] = s4[i];
         if (p.obs != nullptr) {
             const int n = (int)((p.env_end - e0 < 32 ? p.env_end - e0 : 32)) * (p.obs_row_bytes >> 2);
             uint32_t* gobs = reinterpret_cast<uint32_t*>(p.obs + e0 * p.obs_row_bytes);
@@ -476,29 +454,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
             for (int i = threadIdx.x; i < n; i += blockDim.x) gobs[i] = so[i];
         }
     }
-
-    // ---- per-env outputs and episode statistics, behind the tile stores: each stepping warp writes the lanes it stepped
-    if (!kMulti && g < n_cls && stepping && !(p.dbg_skip & 4)) {
-        if (mine) {
-            p.pose[e] = ps;
-            p.reward[e] = (float)st_out.reward;
-            p.done[e] = (uint8_t)st_out.done;
-            p.cost[e] = st_out.cost;
-            p.result[e] = (uint8_t)st_out.result;
-            if (p.msg != nullptr) p.msg[e] = (uint16_t)st_out.msg;
-        }
-        if (p.stats != nullptr)
-            tile_stats(p.stats, (int)blockIdx.x + g * 7, lane, mine, st_out.done, st_success, st_reset, st_invalid,
-                       st_out.reward, st_out.cost);
-    }
-
-    // Programmatic dependent launch: this tile's work is issued, let the next kernel of the stream start scheduling its
-    // CTAs; its prologue (up to griddepcontrol.wait) touches no global state, so it overlaps this kernel's store phase.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (kTma && threadIdx.x == 0) bulk_wait_read<0>();               // shared memory must outlive the bulk stores' reads
 }
-
-
 
 // ------------------------------------------------------------------ the ONE-STEP kernel (ngw_step / ngw_observe)
 // The hot kernel.  One CTA = tiles_per_cta TILE GROUPS that run concurrently and independently; a tile group = G warps
@@ -717,8 +673,8 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
         else { luts.slot = p.dcfgs[cfg_i].c.lidar_slot; luts.firstk = p.dcfgs[cfg_i].lidar.firstk; }
         if (p.lidar_mode == 1) {                                      // every config: line gather, one shared geometry
             const int sel = lidar_line_share(g, G);
-            if (sel) lidar_lines<false>(env, cfg, (NC > 0) ? args.cfg[0].lidar : dc.lidar, luts, orow, sel);
-            if (g == G - 1) obs_tail(env, cfg, orow);
+            if (sel) lidar_lines<false, ObsRow>(env, cfg, (NC > 0) ? args.cfg[0].lidar : dc.lidar, luts, orow, sel);
+            if (g == G - 1) obs_tail<ObsRow>(env, cfg, orow);
         } else {
             if (NC > 1 && !p.lidar_uniform) luts.slot = nullptr;      // heterogeneous beam tables: pointer-walking path
             lidar_observe<false>(env, dc, (NC > 1 && p.lidar_uniform) ? args.cfg[0].lidar : dc.lidar, luts, orow, szero,

@@ -37,6 +37,7 @@ struct ngw_handle {
     bool use_tma = true, collect_stats = true, force_global_cfg = false, plain_store = false, use_pdl = true;
     bool pdl_in_graph = true, early_state = true, pdl_early = true;
     bool lidar_uniform = false;
+    int wshape = 1;                                // 1: one-wave launches take the warp-per-tile kernel, 0: never, 2: always
     DevConfig* d_cfgs = nullptr;
     std::vector<int16_t*> d_luts;
     std::vector<DevConfig> h_cfgs;
@@ -243,6 +244,7 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     h->use_pdl = getenv("NGW_NO_PDL") == nullptr;
     h->pdl_in_graph = getenv("NGW_NO_PDL_GRAPH") == nullptr;
     h->early_state = getenv("NGW_NO_EARLY_STATE") == nullptr;
+    h->wshape = getenv("NGW_WSHAPE") ? atoi(getenv("NGW_WSHAPE")) : 1;
     h->pdl_early = getenv("NGW_NO_PDL_EARLY") == nullptr;   // trigger right after the wait: C2 7.70 -> 7.60 us/step
     // streaming data (each tile is read once and its observations written once per step) should not linger in L2:
     // measured on C2 9.15 -> 8.82 us/step, C3 29.3 -> 28.0, C5 278 -> 274 (hinting the inventory store as well: 9.0)
@@ -276,6 +278,10 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
         }
         dc.lidar.lut = d_lut;
         dc.c.beam_lut = nullptr;
+        // the observation's inventory tail as an id range (the usual case: ids follow the sorted names)
+        dc.lidar.tail_first = dc.c.n_inv_obs > 0 ? (int)dc.c.inv_obs_item[0] : -1;
+        for (int j = 0; j < dc.c.n_inv_obs; j++)
+            if ((int)dc.c.inv_obs_item[j] != dc.lidar.tail_first + j) dc.lidar.tail_first = -1;
     }
     h->lidar_uniform = n_cfgs > 1;
     for (int i = 1; i < n_cfgs; i++) {
@@ -345,6 +351,8 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     NGW_SMEM_ATTR4(step1_kernel, true, true); NGW_SMEM_ATTR4(step1_kernel, true, false);
     NGW_SMEM_ATTR4(step1_kernel, false, true);
 #undef NGW_SMEM_ATTR4
+    NGW_SMEM_ATTR((step1w_kernel<0, 8>)); NGW_SMEM_ATTR((step1w_kernel<1, 8>)); NGW_SMEM_ATTR((step1w_kernel<4, 8>)); NGW_SMEM_ATTR((step1w_kernel<16, 8>));
+    NGW_SMEM_ATTR((step1w_kernel<0, 16>)); NGW_SMEM_ATTR((step1w_kernel<1, 16>)); NGW_SMEM_ATTR((step1w_kernel<4, 16>)); NGW_SMEM_ATTR((step1w_kernel<16, 16>));
     NGW_SMEM_ATTR((rollout_kernel<true, 0>)); NGW_SMEM_ATTR((rollout_kernel<true, 1>)); NGW_SMEM_ATTR((rollout_kernel<true, 4>));
     NGW_SMEM_ATTR((rollout_kernel<true, 16>)); NGW_SMEM_ATTR((rollout_kernel<false, 0>)); NGW_SMEM_ATTR((rollout_kernel<false, 1>));
     NGW_SMEM_ATTR((rollout_kernel<false, 4>)); NGW_SMEM_ATTR((rollout_kernel<false, 16>));
@@ -595,6 +603,54 @@ static cudaError_t launch_step1_nc(ngw_handle* h, StepParams p, cudaStream_t s) 
     return cudaLaunchKernelEx(&lc, step1_kernel<true, NC, false>, args);
 }
 
+// one-step launches in the warp-per-tile shape (step1w_kernel): returns cudaErrorNotSupported when the launch does not
+// qualify and the caller should take the tile-group kernel
+template <int NC>
+static cudaError_t launch_step1w_nc(ngw_handle* h, StepParams p, cudaStream_t s) {
+    static thread_local StepArgs<NC> args;
+    if (h->wshape == 0 || !h->use_tma) return cudaErrorNotSupported;
+    if (h->obs_dim > 0 && h->lidar_mode != 1) return cudaErrorNotSupported;     // needs the line-gather lidar (register sink)
+    int max_tail = 0;
+    for (const DevConfig& dc : h->h_cfgs) max_tail = dc.c.n_inv_obs > max_tail ? dc.c.n_inv_obs : max_tail;
+    if (max_tail > NGW_REGSINK_TAIL) return cudaErrorNotSupported;
+    const int luts = (NGW_MAX_MAP_SIZE + NGW_MAX_ITEMS * (NC > 0 ? NC : 0) + 127) & ~127;
+    p.off_luts = NGW_WCTA_HDR;
+    p.off_groups = p.off_luts + luts;
+    p.obs_srow = p.obs_row_bytes + (((p.obs_row_bytes >> 2) % 8 == 0 && p.obs_row_bytes > 0 && !getenv("NGW_NO_ROW_PAD")) ? 16 : 0);
+    const int in_bytes = p.map_bytes + p.inv_bytes, obs_tile = p.obs ? 32 * p.obs_srow : 0;
+    p.group_bytes = (NGW_WTILE_HDR + (in_bytes > obs_tile ? in_bytes : obs_tile) + 127) & ~127;
+    const long long tiles = (p.env_end - p.env_begin + 31) / 32;
+    // half an SM per launch: two CTAs (of this launch and the next) share an SM's 228 KB, 1 KB of each is the system's
+    int c_cap = (int)((115712 - p.off_groups) / p.group_bytes);
+    if (c_cap > 16) c_cap = 16;
+    if (c_cap < 1) return cudaErrorNotSupported;
+    int C = h->tiles_per_cta;
+    if (C <= 0) {
+        // one wave: one CTA per SM and launch.  Several waves: CTAs of four tiles (small CTAs retire independently, which
+        // staggers the phases of neighbouring tiles; C4 123 / 116 / 116 / 113 us with 1 / 2 / 3 / 4 tiles, C3 flat)
+        if (tiles > (long long)c_cap * h->sm_count) C = h->wshape == 3 ? c_cap : 4;
+        else C = (int)((tiles + h->sm_count - 1) / h->sm_count);
+    }
+    if (C > c_cap) C = c_cap;
+    if (C > tiles) C = (int)tiles;
+    p.tiles_per_cta = C;
+    p.n_tiles = (int)tiles;
+    p.lidar_mode = h->lidar_mode;
+    p.early_state = claim_stream(h, s, h->early_state && h->use_pdl) ? 1 : 0;
+    p.pdl_early = h->pdl_early ? 1 : 0;
+    const size_t smem = (size_t)p.off_groups + (size_t)C * p.group_bytes;
+    args.p = p;
+    for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)((tiles + C - 1) / C)); lc.blockDim = dim3(32 * C); lc.dynamicSmemBytes = smem;
+    lc.stream = s;
+    cudaLaunchAttribute attr[1];
+    pdl_attr(h, s, lc, attr);
+    if (max_tail <= 8) return cudaLaunchKernelEx(&lc, step1w_kernel<NC, 8>, args);
+    return cudaLaunchKernelEx(&lc, step1w_kernel<NC, 16>, args);
+}
+
 static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
     if (p.env_end <= p.env_begin) return 0;
     int nc = h->force_global_cfg ? 0 : h->n_cfgs;
@@ -605,10 +661,16 @@ static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
         else if (nc <= 4) e = launch_rollout_nc<4>(h, p, s);
         else e = launch_rollout_nc<16>(h, p, s);
     } else {
-        if (nc == 0 || nc > 16) e = launch_step1_nc<0>(h, p, s);
-        else if (nc == 1) e = launch_step1_nc<1>(h, p, s);
-        else if (nc <= 4) e = launch_step1_nc<4>(h, p, s);
-        else e = launch_step1_nc<16>(h, p, s);
+        if (nc == 0 || nc > 16) e = launch_step1w_nc<0>(h, p, s);
+        else if (nc == 1) e = launch_step1w_nc<1>(h, p, s);
+        else if (nc <= 4) e = launch_step1w_nc<4>(h, p, s);
+        else e = launch_step1w_nc<16>(h, p, s);
+        if (e == cudaErrorNotSupported) {
+            if (nc == 0 || nc > 16) e = launch_step1_nc<0>(h, p, s);
+            else if (nc == 1) e = launch_step1_nc<1>(h, p, s);
+            else if (nc <= 4) e = launch_step1_nc<4>(h, p, s);
+            else e = launch_step1_nc<16>(h, p, s);
+        }
     }
     if (e != cudaSuccess) return fail(std::string("step kernel launch: ") + cudaGetErrorString(e));
     h->launches++;

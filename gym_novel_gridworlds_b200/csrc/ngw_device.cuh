@@ -346,6 +346,7 @@ struct LidarDev {
     uint8_t disp[2][NGW_MAX_RANGE];     // cells travelled at sample k (0-based) by even / odd beams
     uint8_t firstk[NGW_MAX_MAP_SIZE];   // firstk[d-1]: 1-based sample at which a diagonal beam first reaches its d-th cell, 0 = never
     alignas(4) uint8_t rot[4];          // beam b of an agent facing f looks along compass direction (b + rot[f]) & 7
+    int32_t tail_first;                 // >= 0: the observation's inventory tail is the id range tail_first .. + n_inv_obs - 1, -1: table
     const int16_t* lut;                 // generic path: device int16 [4][B][K]
 };
 
@@ -363,6 +364,7 @@ struct ObsRow {
         if (u8) p[idx] = (unsigned char)v;
         else reinterpret_cast<int32_t*>(p)[idx] = v;
     }
+    __device__ __forceinline__ void put_beam(int, bool hit, int idx, int v) const { if (hit) put(idx, v); }
     __device__ __forceinline__ int32_t* tail(int n_lidar) const {
         return reinterpret_cast<int32_t*>(p + (u8 ? ((n_lidar + 3) & ~3) : 4 * n_lidar));
     }
@@ -386,12 +388,51 @@ struct PolicySink {
 #pragma unroll
         for (int a = 0; a < 16; a++) if (a < A) acc[a] += v * row[a];
     }
+    __device__ __forceinline__ void put_beam(int, bool hit, int idx, int v) { if (hit) put(idx, v); }
     __device__ __forceinline__ void put_tail(int n_lidar, int i, int v) { if (v != 0) put(n_lidar + i, v); }
     __device__ __forceinline__ int argmax(int n_valid) const {       // first maximum over the env's valid action ids
         int best = 0, best_v = acc[0];
 #pragma unroll
         for (int a = 1; a < 16; a++) if (a < n_valid && acc[a] > best_v) { best_v = acc[a]; best = a; }
         return best;
+    }
+};
+
+// Observation sink of the warp-per-tile step kernel (step1w_kernel): the <= 8 lidar hits and the inventory tail stay in
+// REGISTERS (every call site has a compile-time beam / tail position) while the observation tile's shared memory is
+// still occupied by the grid and inventory rows it aliases; flush() writes them into the zeroed row afterwards.
+#define NGW_REGSINK_TAIL 16
+template <int NT>
+struct RegSink {
+    uint32_t hit[8];                    // per compass direction: (byte offset in the row << 8) | range, 0 = nothing seen
+    int32_t tail[NT];
+    int sh;                             // log2 of the bytes per lidar entry (2: int32 rows, 0: NGW_OBS_U8 rows)
+    __device__ __forceinline__ void init(int u8) {
+        sh = u8 ? 0 : 2;
+#pragma unroll
+        for (int a = 0; a < 8; a++) hit[a] = 0u;
+    }
+    __device__ __forceinline__ void put_beam(int a, bool on, int idx, int v) {   // every position is written exactly once
+        const uint32_t packed = on ? (((uint32_t)idx << sh) << 8) | (uint32_t)v : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (j == a) hit[j] = packed;
+    }
+    __device__ __forceinline__ void put_tail(int, int i, int v) {
+#pragma unroll
+        for (int j = 0; j < NT; j++) if (j == i) tail[j] = v;
+    }
+    // row: the lane's (zeroed) observation row in shared memory
+    __device__ __forceinline__ void flush(unsigned char* row, int tail_off, int n_tail) const {
+        if (sh) {
+#pragma unroll
+            for (int a = 0; a < 8; a++) if (hit[a]) *reinterpret_cast<uint32_t*>(row + (hit[a] >> 8)) = hit[a] & 0xFFu;
+        } else {
+#pragma unroll
+            for (int a = 0; a < 8; a++) if (hit[a]) row[hit[a] >> 8] = (unsigned char)hit[a];
+        }
+        int32_t* t = reinterpret_cast<int32_t*>(row + tail_off);
+#pragma unroll
+        for (int i = 0; i < NT; i++) if (i < n_tail) t[i] = tail[i];
     }
 };
 
@@ -483,7 +524,7 @@ __device__ __forceinline__ void line_beams(MaskT occ, int p, int stride, const i
         const int k = diagonal ? (int)luts.firstk[n - 1] : (n <= K ? n : 0);   // obsw:52-58: sample index of that cell, 0 = beyond max_beam_range
         const int id = here[side ? -n * stride : n * stride];
         const int slot = luts.slot[id];                               // -1: occludes but is not a lidar item (Q2)
-        if (slot >= 0 && n != 0 && k != 0) obs.put(((a - rot) & 7) * L + slot, k);
+        obs.put_beam(a, slot >= 0 && n != 0 && k != 0, ((a - rot) & 7) * L + slot, k);
     }
 }
 
@@ -574,21 +615,15 @@ __device__ __forceinline__ void lidar_fast(const EnvRow& e, const ngw_config& cf
 }
 
 // inventory tail of the observation (observation_wrappers.py:77-78): quantities in sorted-name order minus unbreakables (Q7)
-template <typename Sink>
-__device__ __forceinline__ void obs_tail(const EnvRow& e, const ngw_config& cfg, Sink& obs) {
+// tail_first: LidarDev::tail_first of the env's config.  Item ids follow the sorted names (pogostick_v1_env.py:200-212),
+// so without late-injected items the tail is an id range and the copy needs no table; NT bounds the unrolled copy.
+template <typename Sink, int NT = 16>
+__device__ __forceinline__ void obs_tail(const EnvRow& e, const ngw_config& cfg, Sink& obs, int tail_first) {
     const int n_tail = cfg.n_inv_obs, n_lidar = cfg.n_lidar_items * cfg.n_beams;
-    const uint32_t w0 = *reinterpret_cast<const uint32_t*>(&cfg.inv_obs_item[0]);     // four item ids per table read
-    const uint32_t w1 = *reinterpret_cast<const uint32_t*>(&cfg.inv_obs_item[4]);
-    const int first = (int)(w0 & 0xFF);
-    // item ids follow the sorted names (pogostick_v1_env.py:200-212), so without late-injected items the tail is the
-    // id range first .. first + n - 1: then the copy needs no table
-    const bool contiguous = n_tail <= 8 && ((w0 - 0x01010101u * (uint32_t)first) == 0x03020100u) &&
-                            (n_tail <= 4 || ((w1 - 0x01010101u * (uint32_t)first) & (0xFFFFFFFFu >> (8 * (8 - n_tail)))) ==
-                                                (0x07060504u & (0xFFFFFFFFu >> (8 * (8 - n_tail)))));
-    if (contiguous && n_tail >= 4) {
-        const int32_t* src = e.inv + first;
+    if (tail_first >= 0 && n_tail <= NT) {
+        const int32_t* src = e.inv + tail_first;
 #pragma unroll
-        for (int i = 0; i < 8; i++) if (i < n_tail) obs.put_tail(n_lidar, i, src[i]);
+        for (int i = 0; i < NT; i++) if (i < n_tail) obs.put_tail(n_lidar, i, src[i]);
         return;
     }
     for (int i = 0; i < n_tail; i++) obs.put_tail(n_lidar, i, e.inv[cfg.inv_obs_item[i]]);
@@ -631,7 +666,7 @@ __device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& 
             }
         }
     }
-    if (with_tail) { ObsRow sink = obs; obs_tail<ObsRow>(e, cfg, sink); }
+    if (with_tail) { ObsRow sink = obs; obs_tail<ObsRow>(e, cfg, sink, dc.lidar.tail_first); }
 }
 
 // ------------------------------------------------------------------ reset (pogostick_v1_env.py:86-181 + novelty resets)

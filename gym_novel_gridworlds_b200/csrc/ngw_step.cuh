@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ St
                     sink.init(spol + 16, spol, p.policy_actions);
                     if (valid && cfg.n_beams > 0) {
                         lidar_lines<false, PolicySink>(env, cfg, beam_tables, luts, sink, 0xF);
-                        obs_tail<PolicySink>(env, cfg, sink);
+                        obs_tail<PolicySink>(env, cfg, sink, dc.lidar.tail_first);
                     }
                     action = sink.argmax(n_valid);
                 } else {
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
         if (p.lidar_mode == 1) {                                      // every config: line gather, one shared geometry
             const int sel = lidar_line_share(g, G);
             if (sel) lidar_lines<false, ObsRow>(env, cfg, (NC > 0) ? args.cfg[0].lidar : dc.lidar, luts, orow, sel);
-            if (g == G - 1) obs_tail<ObsRow>(env, cfg, orow);
+            if (g == G - 1) obs_tail<ObsRow>(env, cfg, orow, dc.lidar.tail_first);
         } else {
             if (NC > 1 && !p.lidar_uniform) luts.slot = nullptr;      // heterogeneous beam tables: pointer-walking path
             lidar_observe<false>(env, dc, (NC > 1 && p.lidar_uniform) ? args.cfg[0].lidar : dc.lidar, luts, orow, szero,
@@ -782,6 +782,278 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
     // the stream may start scheduling its CTAs (its prologue touches no global state: it overlaps this kernel's stores).
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (kTma && g == 0) bulk_wait_read<0>();                          // shared memory must outlive the bulk stores' reads
+}
+
+// ------------------------------------------------------------------ the ONE-STEP kernel, WARP-PER-TILE shape (one-wave launches)
+// One warp owns one tile of 32 envs from load to store; a CTA is tiles_per_cta such warps that never synchronise with
+// each other after the prologue.  The point of the shape is its shared-memory plan: the observation tile (the largest
+// buffer, written only at the end) ALIASES the grid and inventory rows (read only until the lidar is done),
+//     tile = header 128 B | region max(grid + inventory rows, observation tile)
+// which is 8 KB on C2 instead of 13 KB.  All tiles of a one-wave launch then fit in HALF an SM (C2: 14 warps, 112 KB, one
+// CTA per SM), so the NEXT launch of the stream — started early through programmatic dependent launch — is co-resident:
+// its prologue, its zero-fill and (other handle: early_state) its TMA loads run underneath this launch's compute and
+// store phases instead of after them.  Per warp:
+//   load    two TMA bulk copies (grid rows, inventory rows) on the tile's mbarrier
+//   step    all 32 lanes, no hand-over
+//   store 1 inventory tile -> HBM (TMA bulk store, issued right after the step)
+//   lidar   line gather into a RegSink: hits and inventory tail stay in registers
+//   store 2 once the inventory store has read its rows: zero the region, write the <= 8 hits + tail per row, TMA bulk store
+//   outputs pose / reward / step_cost / done / result straight from registers (lane = env: full lines), statistics
+#define NGW_WTILE_HDR 128
+#define NGW_WCTA_HDR 384            // [0] tiles done | per-warp statistics partials at +64: int4[16]
+
+__device__ __forceinline__ void zero_span(uint32_t a, uint32_t end) {      // 16 bytes per lane, 512 per warp and pass
+#pragma unroll 4
+    for (; a < end; a += 512u) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
+}
+
+// NT: compile-time bound of the inventory tail kept in registers (8 when every config has n_inv_obs <= 8, else 16)
+template <int NC, int NT>
+__global__ void __launch_bounds__(512, 2) step1w_kernel(const __grid_constant__ StepArgs<NC> args) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const StepParams& p = args.p;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tile = (int)blockIdx.x * p.tiles_per_cta + wid;
+    const bool active = tile < p.n_tiles;
+    const long long e0 = p.env_begin + (long long)tile * 32;
+    const long long e = e0 + lane;
+    const bool valid = active && e < p.env_end;
+    const bool full_tile = e0 + 32 <= p.env_end;
+    const bool stepping = p.actions != nullptr;
+
+    int* scta = reinterpret_cast<int*>(smem);
+    uint8_t* sfirstk = smem + p.off_luts;
+    int8_t* sslot = reinterpret_cast<int8_t*>(smem + p.off_luts + NGW_MAX_MAP_SIZE);
+    unsigned char* gbase = smem + p.off_groups + wid * p.group_bytes;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(gbase);               // "tile landed" barrier
+    unsigned char* region = gbase + NGW_WTILE_HDR;
+    int8_t* smap = reinterpret_cast<int8_t*>(region);
+    int32_t* sinv = reinterpret_cast<int32_t*>(region + p.map_bytes);
+    unsigned char* sobs = region;                                     // aliases the rows above
+    const uint32_t region_a = smem_u32(region);
+    const uint32_t in_bytes = (uint32_t)(p.map_bytes + p.inv_bytes);
+    const uint32_t obs_tile = p.obs != nullptr ? 32u * (uint32_t)p.obs_srow : 0u;
+
+    // ---- prologue without global state
+    if (threadIdx.x == 0) scta[0] = 0;
+    if (lane == 0) mbar_init(bar, 1);
+    if (NC > 0) {
+        if (threadIdx.x < NGW_MAX_MAP_SIZE / 4)
+            reinterpret_cast<uint32_t*>(sfirstk)[threadIdx.x] =
+                reinterpret_cast<const uint32_t*>(args.cfg[0].lidar.firstk)[threadIdx.x];
+#pragma unroll
+        for (int k = 0; k < NC; k++)
+            if (threadIdx.x < NGW_MAX_ITEMS / 4)
+                reinterpret_cast<uint32_t*>(sslot + k * NGW_MAX_ITEMS)[threadIdx.x] =
+                    reinterpret_cast<const uint32_t*>(args.cfg[k].c.lidar_slot)[threadIdx.x];
+    }
+    __syncthreads();                                                  // the only CTA-wide barrier
+
+    const int8_t* gmap = p.map + e0 * p.cells;
+    int32_t* ginv = p.inv + e0 * p.inv_stride;
+    uint64_t pol_first = 0;
+    if (p.cache_hints) pol_first = policy_evict_first();
+    auto issue_loads = [&]() {
+        if (lane == 0) {
+            mbar_expect_tx(bar, in_bytes);
+            if (p.cache_hints & 1) {
+                bulk_g2s_hint(smap, gmap, (uint32_t)p.map_bytes, bar, pol_first);
+                bulk_g2s_hint(sinv, ginv, (uint32_t)p.inv_bytes, bar, pol_first);
+            } else {
+                bulk_g2s(smap, gmap, (uint32_t)p.map_bytes, bar);
+                bulk_g2s(sinv, ginv, (uint32_t)p.inv_bytes, bar);
+            }
+        }
+    };
+    uchar4 ps = make_uchar4(0, 0, 0, 0);
+    const bool early = p.early_state && active && !(p.dbg_skip & 64);
+    if (early) {                                                      // see step1_kernel: this handle's state is complete already
+        issue_loads();
+        ps = p.pose[e];
+    }
+    // the part of the observation tile that lies beyond the rows it aliases is zeroed while the loads fly
+    zero_span(region_a + in_bytes + (uint32_t)lane * 16u, region_a + obs_tile);
+    asm volatile("griddepcontrol.wait;" ::: "memory");                // previous kernel of the stream done + visible
+    // the dependent launch may start now: it is co-resident (half an SM per launch) and blocks in its own wait until
+    // this grid has completed
+    if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!active || (p.dbg_skip & 64)) { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); return; }
+    if (!early) {
+        issue_loads();
+        ps = p.pose[e];
+    }
+
+    const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[e];
+    const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
+    const ngw_config& cfg = dc.c;
+    int action = 0;
+    if (stepping && valid) action = p.actions[e];
+
+    mbar_wait(bar, 0);
+    if (p.dbg_skip & 128) { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); return; }
+
+    EnvRow env;
+    env.m = smap + lane * p.cells;
+    env.gm = p.map + e * p.cells;
+    env.inv = sinv + lane * p.inv_stride;
+    env.ms = p.ms;
+    env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+
+    // ---- step
+    uint32_t counts = 0;                                              // steps | episodes << 6 | successes << 12 | resets << 18 | invalid << 24
+    StepOut o;
+    o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0; o.goal = 0;
+    if (stepping) {
+        int did_reset = 0;
+        if (valid) {
+            ngw_action_entry a;
+            a.op = NGW_OP_INVALID;
+            if (action >= 0 && action < cfg.n_actions) {
+                uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
+                memcpy(&a, &raw, sizeof(a));
+            }
+            counts = 1u;
+            if (a.op == NGW_OP_INVALID) {                             // wrappers.py:76 / pogostick_v1_env.py:236 would raise
+                counts |= 1u << 24;
+                p.err[e] |= NGW_ERR_INVALID_ACTION;
+            } else {
+                if (!(p.dbg_skip & 1)) step_env(env, cfg, a, o);
+                int finished = o.done;
+                if (p.max_episode_steps > 0) {
+                    int len = p.ep_len[e] + 1;
+                    if (len >= p.max_episode_steps) { finished = 1; o.done = 1; }   // harness truncation knob
+                    p.ep_len[e] = finished && p.auto_reset ? 0 : len;
+                }
+                did_reset = finished && p.auto_reset;
+                counts |= ((uint32_t)o.done << 6) | ((uint32_t)o.goal << 12) | ((uint32_t)did_reset << 18);
+            }
+            ps = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing, (unsigned char)env.sel);
+        }
+        if (p.auto_reset) {                                           // queue the finished envs for reset_list_kernel
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, did_reset);
+            if (bal != 0) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(p.reset_count, __popc(bal));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (did_reset) p.reset_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)e;
+            }
+        }
+        // ---- store 1: the inventory tile leaves as soon as the step is done
+        if (full_tile && !p.plain_store) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(p.dbg_skip & 16)) { bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes); bulk_commit(); }
+        } else {
+            __syncwarp();
+            const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
+            uint4* d4 = reinterpret_cast<uint4*>(ginv);
+            for (int i = lane; i < (p.inv_bytes >> 4); i += 32) d4[i] = s4[i];
+        }
+    }
+
+    // ---- LidarInFront of the new state, into registers
+    if (p.obs != nullptr) {
+        RegSink<NT> sink;
+        sink.init(p.obs_u8);
+        const bool look = valid && cfg.n_beams > 0;
+        if (look && !(p.dbg_skip & 2)) {
+            LidarLuts luts;
+            if (NC > 0) { luts.slot = sslot + cfg_i * NGW_MAX_ITEMS; luts.firstk = sfirstk; }
+            else { luts.slot = p.dcfgs[cfg_i].c.lidar_slot; luts.firstk = p.dcfgs[cfg_i].lidar.firstk; }
+            lidar_lines<false, RegSink<NT> >(env, cfg, (NC > 0) ? args.cfg[0].lidar : dc.lidar, luts, sink, 0xF);
+            obs_tail<RegSink<NT>, NT>(env, cfg, sink, dc.lidar.tail_first);
+        }
+        // ---- store 2: the rows have been consumed (and read by the inventory store) -> the region becomes the observation tile
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+        zero_span(region_a + (uint32_t)lane * 16u, region_a + (in_bytes < obs_tile ? in_bytes : obs_tile));
+        __syncwarp();
+        if (look) {
+            const int n_lidar = cfg.n_lidar_items * cfg.n_beams;
+            sink.flush(sobs + lane * p.obs_srow, p.obs_u8 ? ((n_lidar + 3) & ~3) : 4 * n_lidar, cfg.n_inv_obs);
+        }
+        if (full_tile && !p.plain_store) {
+            fence_async_smem();
+            __syncwarp();
+            if (!(p.dbg_skip & 8)) {
+                unsigned char* gobs = p.obs + e0 * p.obs_row_bytes;
+                if (p.obs_srow == p.obs_row_bytes) {                  // the tile is one contiguous span on both sides
+                    if (lane == 0) {
+                        if (p.cache_hints & 2) bulk_s2g_hint(gobs, sobs, (uint32_t)p.obs_bytes, pol_first);
+                        else bulk_s2g(gobs, sobs, (uint32_t)p.obs_bytes);
+                    }
+                } else {                                              // padded rows in shared memory: lane l stores row l
+                    if (p.cache_hints & 2) bulk_s2g_hint(gobs + lane * p.obs_row_bytes, sobs + lane * p.obs_srow,
+                                                         (uint32_t)p.obs_row_bytes, pol_first);
+                    else bulk_s2g(gobs + lane * p.obs_row_bytes, sobs + lane * p.obs_srow, (uint32_t)p.obs_row_bytes);
+                }
+            }
+            bulk_commit();
+        } else {
+            __syncwarp();
+            const int rows = (int)(p.env_end - e0 < 32 ? p.env_end - e0 : 32), words = p.obs_row_bytes >> 2;
+            for (int r = 0; r < rows; r++) {
+                uint32_t* grow = reinterpret_cast<uint32_t*>(p.obs + (e0 + r) * p.obs_row_bytes);
+                const uint32_t* srow = reinterpret_cast<const uint32_t*>(sobs + r * p.obs_srow);
+                for (int i = lane; i < words; i += 32) grow[i] = srow[i];
+            }
+        }
+    }
+
+    // ---- per-env outputs (lane = env: full lines) and episode statistics
+    if (stepping && !(p.dbg_skip & 4)) {
+        if (valid) {
+            p.pose[e] = ps;
+            p.reward[e] = (float)o.reward;
+            p.done[e] = (uint8_t)o.done;
+            p.cost[e] = o.cost;
+            p.result[e] = (uint8_t)o.result;
+            if (p.msg != nullptr) p.msg[e] = (uint16_t)o.msg;
+        }
+        if (p.stats != nullptr) {
+            // warp reductions -> this warp's slot in shared memory; the last warp of the CTA to arrive folds the slots and
+            // issues one set of global atomics per CTA
+            const uint32_t c_all = __reduce_add_sync(0xFFFFFFFFu, counts);            // five counts <= 32: 6 bits apiece
+            const int r_sum = __reduce_add_sync(0xFFFFFFFFu, o.reward);
+            const float c_sum = warp_sum(o.cost);
+            int4* slots = reinterpret_cast<int4*>(smem + 64);
+            const int n_tiles_cta = min(p.tiles_per_cta, p.n_tiles - (int)blockIdx.x * p.tiles_per_cta);
+            int last = 0;
+            if (lane == 0) {
+                slots[wid] = make_int4((int)c_all, r_sum, __float_as_int(c_sum), 0);
+                __threadfence_block();
+                last = atomicAdd(&scta[0], 1) == n_tiles_cta - 1;
+            }
+            if (__shfl_sync(0xFFFFFFFFu, last, 0)) {
+                __threadfence_block();
+                int4 v = make_int4(0, 0, 0, 0);
+                if (lane < n_tiles_cta) {
+                    const volatile int* sv = reinterpret_cast<const volatile int*>(&slots[lane]);
+                    v.x = sv[0]; v.y = sv[1]; v.z = sv[2];
+                }
+                // counts of up to 16 warps x 32 lanes need 10 bits: widen before the second reduction
+                const uint32_t lo = ((uint32_t)v.x & 63u) | ((((uint32_t)v.x >> 6) & 63u) << 10) | ((((uint32_t)v.x >> 12) & 63u) << 20);
+                const uint32_t hi = (((uint32_t)v.x >> 18) & 63u) | ((((uint32_t)v.x >> 24) & 63u) << 10);
+                const uint32_t a_tot = __reduce_add_sync(0xFFFFFFFFu, lo), b_tot = __reduce_add_sync(0xFFFFFFFFu, hi);
+                const int r_tot = __reduce_add_sync(0xFFFFFFFFu, v.y);
+                const float c_tot = warp_sum(__int_as_float(v.z));
+                if (lane == 0) {
+                    const int n_step = a_tot & 1023, n_done = (a_tot >> 10) & 1023, n_succ = (a_tot >> 20) & 1023;
+                    const int n_reset = b_tot & 1023, n_inv = (b_tot >> 10) & 1023;
+                    double* sg = p.stats + (size_t)(blockIdx.x % NGW_STAT_SLOTS) * NGW_STAT_COUNT;
+                    atomicAdd(&sg[NGW_STAT_STEPS], (double)(n_step - n_inv));
+                    atomicAdd(&sg[NGW_STAT_REWARD_SUM], (double)r_tot);
+                    atomicAdd(&sg[NGW_STAT_COST_SUM], (double)c_tot);
+                    if (n_done) atomicAdd(&sg[NGW_STAT_EPISODES], (double)n_done);
+                    if (n_succ) atomicAdd(&sg[NGW_STAT_SUCCESSES], (double)n_succ);
+                    if (n_reset) atomicAdd(&sg[NGW_STAT_RESETS], (double)n_reset);
+                    if (n_inv) atomicAdd(&sg[NGW_STAT_INVALID], (double)n_inv);
+                }
+            }
+        }
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    bulk_wait_read<0>();                                              // shared memory must outlive the bulk stores' reads
 }
 
 }  // namespace ngw

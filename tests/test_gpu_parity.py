@@ -448,7 +448,7 @@ def test_warps_per_tile_and_action_class_split(warps, ctiles):
     selects, warp 1: moves and block-in-front actions) and the lidar lines are shared out over the warps; a CTA runs
     several tile groups side by side (named barriers).  Same results for every shape, single and mixed configs, layered
     novelties, partial last tile / partial last CTA, auto-reset queueing from both stepping warps, CTA-level statistics."""
-    os.environ['NGW_WARPS'], os.environ['NGW_CTILES'] = str(warps), str(ctiles)
+    os.environ['NGW_WARPS'], os.environ['NGW_CTILES'], os.environ['NGW_WSHAPE'] = str(warps), str(ctiles), '0'
     try:
         _parity_vs_oracle([_compiled(C2_DESC)], 32 * 37 + 5, 40, seed0=warps * 100)
         _parity_vs_oracle([_compiled(golden_util.get('bow_C3_axe_medium_fence_hard')['meta'])], 32 * 21 + 1, 24, seed0=warps)
@@ -467,7 +467,62 @@ def test_warps_per_tile_and_action_class_split(warps, ctiles):
         assert dones == 3 * n and (h.episode.cpu().numpy() == 4).all() and st[0] == 12 * n and st[5] == 3 * n
         assert st[1] == dones
     finally:
-        del os.environ['NGW_WARPS'], os.environ['NGW_CTILES']
+        del os.environ['NGW_WARPS'], os.environ['NGW_CTILES'], os.environ['NGW_WSHAPE']
+
+
+@pytest.mark.parametrize('wshape,ctiles,extra', [(1, 0, ''), (1, 1, ''), (1, 5, ''), (2, 14, ''), (2, 3, 'NGW_NO_EARLY_STATE'),
+                                                 (1, 0, 'NGW_PLAIN_STORE'), (1, 0, 'NGW_GLOBAL_CFG'), (1, 0, 'NGW_NO_PDL')])
+def test_warp_per_tile_shape(wshape, ctiles, extra):
+    """step1w_kernel: one warp per tile, the observation tile aliases the grid / inventory rows in shared memory (hits and
+    inventory tail wait in registers), two consecutive launches share an SM.  Same results as the oracle for single and
+    mixed configs, layered novelties, partial last tile / partial last CTA, u8 rows, observe-only launches, auto-reset
+    queueing and CTA-level statistics; back-to-back launches of rotating handles (early state loads under PDL)."""
+    os.environ['NGW_WSHAPE'], os.environ['NGW_CTILES'] = str(wshape), str(ctiles)
+    if extra:
+        os.environ[extra] = '1'
+    try:
+        _parity_vs_oracle([_compiled(C2_DESC)], 32 * 37 + 5, 40, seed0=wshape * 100 + ctiles)
+        _parity_vs_oracle([_compiled(golden_util.get('bow_C3_axe_medium_fence_hard')['meta'])], 32 * 21 + 1, 24, seed0=ctiles)
+        _parity_vs_oracle([_compiled(golden_util.get('pogo_crate_over_fr_hard')['meta'])], 700, 24, seed0=3)
+        _parity_vs_oracle([_compiled({'env': scenarios.POGO, 'map_size': 23, 'chain': [['lidar', 8]]})], 333, 24, seed0=11)
+        cc = _compiled(C2_DESC)
+        n = 1000
+        h = BatchHandle([cc], n, seed=2)
+        h.reset()
+        rng = np.random.RandomState(1)
+        dones = 0
+        for t in range(12):
+            a = torch.from_numpy(rng.randint(0, cc.c.n_actions, size=n).astype(np.int32)).cuda()
+            dones += int(h.step(a, auto_reset=True, max_episode_steps=4)[2].sum().item())
+        st = h.stats().cpu().numpy()
+        assert dones == 3 * n and (h.episode.cpu().numpy() == 4).all() and st[0] == 12 * n and st[5] == 3 * n
+        assert st[1] == dones
+        # rotating handles back to back on one stream, no host synchronisation in between (early state loads, co-resident
+        # launches), u8 and i32 rows, against handles stepped one at a time with a synchronise after every launch
+        n = 32 * 150 + 7
+        rng = np.random.RandomState(5)
+        for fmt in ('i32', 'u8'):
+            hs = [BatchHandle([cc], n, seed=40 + k, obs_format=fmt) for k in range(3)]
+            ref = [BatchHandle([cc], n, seed=40 + k, obs_format=fmt) for k in range(3)]
+            for x in hs + ref:
+                x.reset()
+            torch.cuda.synchronize()
+            acts = [torch.from_numpy(rng.randint(0, cc.c.n_actions, size=n).astype(np.int32)).cuda() for _ in range(30)]
+            outs = []
+            for t in range(30):
+                outs.append([x.clone() for x in hs[t % 3].step(acts[t])])
+            torch.cuda.synchronize()
+            for t in range(30):
+                want = ref[t % 3].step(acts[t])
+                torch.cuda.synchronize()
+                for x, y in zip(outs[t], want):
+                    assert torch.equal(x, y), "launch %d (%s)" % (t, fmt)
+            for a, b in zip(hs, ref):
+                assert torch.equal(a.map, b.map) and torch.equal(a.inventory, b.inventory) and torch.equal(a.pose, b.pose)
+    finally:
+        del os.environ['NGW_WSHAPE'], os.environ['NGW_CTILES']
+        if extra:
+            del os.environ[extra]
 
 
 @pytest.mark.parametrize('knob', ['NGW_NO_LINE_LIDAR', 'NGW_NO_FAST_LIDAR'])

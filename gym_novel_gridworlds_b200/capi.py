@@ -8,7 +8,7 @@ from . import opcodes as oc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libngw_b200.so')
-ABI_VERSION = 9
+ABI_VERSION = 10
 OBS_I32, OBS_U8 = 0, 1
 
 
@@ -98,6 +98,7 @@ EXPORTS = {
     'ngw_agent_map': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'ngw_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'ngw_launch_count': (C.c_int64, [C.c_void_p]),
+    'ngw_concurrent_launch_count': (C.c_int64, [C.c_void_p]),
 }
 
 _lib = None

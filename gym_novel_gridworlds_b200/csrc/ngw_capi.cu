@@ -37,7 +37,10 @@ struct ngw_handle {
     bool use_tma = true, collect_stats = true, force_global_cfg = false, plain_store = false, use_pdl = true;
     bool pdl_in_graph = true, early_state = true, pdl_early = true;
     bool lidar_uniform = false;
-    int wshape = 1;                                // 1: one-wave launches take the warp-per-tile kernel, 0: never, 2: always
+    int wshape = 1;                                // 1: launches take the warp-per-tile kernel when it supports them, 0: never
+    bool concurrent = true;                        // independent consecutive launches may overlap (NGW_NO_CONCURRENT)
+    bool concurrent_waves = true;                  // ... also launches of several waves (NGW_NO_CONCURRENT_WAVES)
+    bool rollout2 = true;                          // lane-pair rollout kernel (NGW_NO_ROLLOUT2)
     DevConfig* d_cfgs = nullptr;
     std::vector<int16_t*> d_luts;
     std::vector<DevConfig> h_cfgs;
@@ -47,7 +50,7 @@ struct ngw_handle {
     uint16_t* msg = nullptr;                       // caller-owned message-code buffer (ngw_set_message_buffer)
     int32_t* reset_list = nullptr; int32_t* reset_ctl = nullptr;   // auto-reset queue; ctl[0] = count, ctl[1] = finished CTAs
     int sm_count = 148;
-    long long launches = 0;
+    long long launches = 0, concurrent_launches = 0;
     // host-buffer path: its own stream, ordered against the caller's streams with events
     cudaStream_t hs = nullptr;
     cudaEvent_t ev_dev = nullptr;                  // recorded on the caller's stream when the host path has to wait for it
@@ -68,25 +71,74 @@ struct ngw_handle {
 // before that writer had completed.  Launches the library cannot see (the caller's own kernels, copies) only add
 // distance.  The first launch of a stream capture is always conservative: a graph can be replayed after anything.
 static std::mutex g_order_mu;
-static std::unordered_map<cudaStream_t, std::pair<ngw_handle*, unsigned long long>> g_last_writer;   // stream -> (handle, capture id)
+struct MemRange { uintptr_t lo, hi; };
+struct StreamTail {                       // the latest library launch on a stream
+    ngw_handle* h = nullptr;
+    unsigned long long cap_id = 0;        // stream capture it was recorded in, 0 = eager
+    cudaGraphNode_t node = nullptr;       // its graph node (captures only)
+    bool pure_step = false;               // a one-step kernel launch with nothing behind it (no queued-reset kernel)
+    MemRange rd[2], wr[6];                // caller buffers it reads (actions) / writes (obs, reward, done, cost, result, msg)
+    int n_rd = 0, n_wr = 0;
+};
+static std::unordered_map<cudaStream_t, StreamTail> g_last_writer;
 
-static bool claim_stream(ngw_handle* h, cudaStream_t s, bool want_early) {
+static bool overlaps(const MemRange* a, int na, const MemRange* b, int nb) {
+    for (int i = 0; i < na; i++)
+        for (int j = 0; j < nb; j++)
+            if (a[i].lo < b[j].hi && b[j].lo < a[i].hi) return true;
+    return false;
+}
+
+// Returns 0 (conservative), 1 (state loads may precede griddepcontrol.wait) or 2 (the launch is independent of its
+// predecessor: see step1w_kernel's gate warp).  2 needs PROOF that nothing sits between the two launches: inside a stream
+// capture the stream's dependency set must be exactly the graph node of the previous launch; that launch must be a plain
+// one-step launch of ANOTHER handle, and the caller buffers of the two launches must not overlap.  Then everything this
+// launch reads besides its own state (the actions) was complete before the predecessor was let go by ITS gate.
+static int claim_stream(ngw_handle* h, cudaStream_t s, bool want_early, const StreamTail* mine = nullptr) {
     unsigned long long cap_id = 0;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamGetCaptureInfo(s, &cap, &cap_id) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
-    if (cap == cudaStreamCaptureStatusNone) cap_id = 0;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t n_deps = 0;
+    if (cudaStreamGetCaptureInfo(s, &cap, &cap_id, nullptr, &deps, &n_deps) != cudaSuccess) {
+        cudaGetLastError(); cap = cudaStreamCaptureStatusNone; n_deps = 0;
+    }
+    if (cap != cudaStreamCaptureStatusActive) { cap_id = 0; n_deps = 0; }
     std::lock_guard<std::mutex> lk(g_order_mu);
     auto it = g_last_writer.find(s);
-    const bool early = want_early && it != g_last_writer.end() && it->second.first != nullptr && it->second.first != h &&
-                       it->second.second == cap_id;
-    g_last_writer[s] = std::make_pair(h, cap_id);
-    return early;
+    int mode = 0;
+    if (want_early && it != g_last_writer.end() && it->second.h != nullptr && it->second.h != h && it->second.cap_id == cap_id) {
+        mode = 1;
+        const StreamTail& t = it->second;
+        if (mine != nullptr && cap_id != 0 && t.pure_step && n_deps == 1 && t.node != nullptr && deps[0] == t.node &&
+            !overlaps(mine->wr, mine->n_wr, t.wr, t.n_wr) && !overlaps(mine->wr, mine->n_wr, t.rd, t.n_rd) &&
+            !overlaps(mine->rd, mine->n_rd, t.wr, t.n_wr))
+            mode = 2;
+    }
+    StreamTail now;
+    if (mine != nullptr) now = *mine;
+    now.h = h; now.cap_id = cap_id; now.node = nullptr; now.pure_step = false;
+    g_last_writer[s] = now;
+    return mode;
+}
+
+// after a launch inside a capture: remember its graph node, so that the next launch can prove it is adjacent
+static void note_launched(cudaStream_t s, bool pure_step) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    unsigned long long cap_id = 0;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t n_deps = 0;
+    if (cudaStreamGetCaptureInfo(s, &cap, &cap_id, nullptr, &deps, &n_deps) != cudaSuccess) { cudaGetLastError(); return; }
+    std::lock_guard<std::mutex> lk(g_order_mu);
+    auto it = g_last_writer.find(s);
+    if (it == g_last_writer.end()) return;
+    it->second.pure_step = pure_step;
+    it->second.node = (cap == cudaStreamCaptureStatusActive && n_deps == 1) ? deps[0] : nullptr;
 }
 
 static void forget_handle(ngw_handle* h) {
     std::lock_guard<std::mutex> lk(g_order_mu);
     for (auto& kv : g_last_writer)
-        if (kv.second.first == h) kv.second.first = nullptr;
+        if (kv.second.h == h) kv.second.h = nullptr;
 }
 
 static int before_device_call(ngw_handle* h, cudaStream_t s) {
@@ -245,6 +297,9 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     h->pdl_in_graph = getenv("NGW_NO_PDL_GRAPH") == nullptr;
     h->early_state = getenv("NGW_NO_EARLY_STATE") == nullptr;
     h->wshape = getenv("NGW_WSHAPE") ? atoi(getenv("NGW_WSHAPE")) : 1;
+    h->concurrent = getenv("NGW_NO_CONCURRENT") == nullptr;
+    h->concurrent_waves = getenv("NGW_NO_CONCURRENT_WAVES") == nullptr;
+    h->rollout2 = getenv("NGW_NO_ROLLOUT2") == nullptr;
     h->pdl_early = getenv("NGW_NO_PDL_EARLY") == nullptr;   // trigger right after the wait: C2 7.70 -> 7.60 us/step
     // streaming data (each tile is read once and its observations written once per step) should not linger in L2:
     // measured on C2 9.15 -> 8.82 us/step, C3 29.3 -> 28.0, C5 278 -> 274 (hinting the inventory store as well: 9.0)
@@ -585,7 +640,7 @@ static cudaError_t launch_step1_nc(ngw_handle* h, StepParams p, cudaStream_t s) 
     // launches write no state, but they are ordered like steps: they read it)
     // only for one-wave launches: with several waves the loads of later waves never wait anyway, and issuing them ahead
     // of the tile's zero-fill measured 4 % slower (C4 122 vs 127 us)
-    p.early_state = claim_stream(h, s, h->early_state && h->use_pdl && C > 1) ? 1 : 0;
+    p.early_state = claim_stream(h, s, h->early_state && h->use_pdl && C > 1) >= 1 ? 1 : 0;
     p.pdl_early = h->pdl_early ? 1 : 0;
     const size_t smem = (size_t)p.off_groups + (size_t)C * p.group_bytes;
     args.p = p;
@@ -622,7 +677,7 @@ static cudaError_t launch_step1w_nc(ngw_handle* h, StepParams p, cudaStream_t s)
     const long long tiles = (p.env_end - p.env_begin + 31) / 32;
     // half an SM per launch: two CTAs (of this launch and the next) share an SM's 228 KB, 1 KB of each is the system's
     int c_cap = (int)((115712 - p.off_groups) / p.group_bytes);
-    if (c_cap > 16) c_cap = 16;
+    if (c_cap > 15) c_cap = 15;                     // 15 tile warps + the gate warp = 512 threads
     if (c_cap < 1) return cudaErrorNotSupported;
     int C = h->tiles_per_cta;
     if (C <= 0) {
@@ -636,19 +691,84 @@ static cudaError_t launch_step1w_nc(ngw_handle* h, StepParams p, cudaStream_t s)
     p.tiles_per_cta = C;
     p.n_tiles = (int)tiles;
     p.lidar_mode = h->lidar_mode;
-    p.early_state = claim_stream(h, s, h->early_state && h->use_pdl) ? 1 : 0;
+    // caller buffers of this launch (for the independence proof of the NEXT launch, and of this one)
+    StreamTail me;
+    const long long n_env = p.env_end - p.env_begin;
+    auto add = [](MemRange* r, int& n, const void* ptr, size_t bytes) {
+        if (ptr != nullptr && bytes > 0) { r[n].lo = (uintptr_t)ptr; r[n].hi = (uintptr_t)ptr + bytes; n++; }
+    };
+    add(me.rd, me.n_rd, p.actions, (size_t)n_env * 4);
+    add(me.wr, me.n_wr, p.obs, (size_t)n_env * p.obs_row_bytes);
+    add(me.wr, me.n_wr, p.reward, (size_t)n_env * 4); add(me.wr, me.n_wr, p.cost, (size_t)n_env * 4);
+    add(me.wr, me.n_wr, p.done, (size_t)n_env); add(me.wr, me.n_wr, p.result, (size_t)n_env);
+    add(me.wr, me.n_wr, p.msg, (size_t)n_env * 2);
+    const bool one_wave = tiles <= (long long)C * h->sm_count;
+    const int mode = claim_stream(h, s, h->early_state && h->use_pdl, &me);
+    p.early_state = mode >= 1 ? 1 : 0;
+    // (one-wave launches overlap whole; with several waves the next launch fills the SMs as the last wave drains)
+    p.concurrent = (mode == 2 && h->concurrent && (one_wave || h->concurrent_waves) && p.actions != nullptr && !p.auto_reset) ? 1 : 0;
     p.pdl_early = h->pdl_early ? 1 : 0;
     const size_t smem = (size_t)p.off_groups + (size_t)C * p.group_bytes;
     args.p = p;
     for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3((unsigned)((tiles + C - 1) / C)); lc.blockDim = dim3(32 * C); lc.dynamicSmemBytes = smem;
+    lc.gridDim = dim3((unsigned)((tiles + C - 1) / C)); lc.blockDim = dim3(32 * (C + 1)); lc.dynamicSmemBytes = smem;
     lc.stream = s;
     cudaLaunchAttribute attr[1];
     pdl_attr(h, s, lc, attr);
-    if (max_tail <= 8) return cudaLaunchKernelEx(&lc, step1w_kernel<NC, 8>, args);
-    return cudaLaunchKernelEx(&lc, step1w_kernel<NC, 16>, args);
+    cudaError_t e;
+    if (max_tail <= 8) e = cudaLaunchKernelEx(&lc, step1w_kernel<NC, 8>, args);
+    else e = cudaLaunchKernelEx(&lc, step1w_kernel<NC, 16>, args);
+    if (e == cudaSuccess) {
+        note_launched(s, p.actions != nullptr && !p.auto_reset && lc.numAttrs == 1);
+        h->concurrent_launches += p.concurrent;
+    }
+    return e;
+}
+
+// K-step rollout launches in the lane-pair shape (rollout2_kernel); cudaErrorNotSupported -> rollout_kernel
+template <int NC, int A4>
+static cudaError_t launch_rollout2_na(ngw_handle* h, StepParams p, cudaStream_t s) {
+    static thread_local StepArgs<NC> args;
+    const int in_bytes = p.map_bytes + p.inv_bytes;
+    const int luts = (NGW_MAX_MAP_SIZE + NGW_MAX_ITEMS * (NC > 0 ? NC : 0) + 127) & ~127;
+    p.off_luts = NGW_R2_HDR;
+    p.off_scratch = p.off_luts + luts;
+    p.off_policy = p.off_scratch + (p.auto_reset ? ((2 * NGW_RESET_SCRATCH_WORDS * 4 + 127) & ~127) : 0);
+    p.off_in = p.off_policy + (A4 > 0 ? ((16 + p.obs_dim * 4 * A4) * 4 + 127) & ~127 : 0);
+    const int obs_tile = p.obs ? p.obs_bytes : 0;
+    const size_t smem = (size_t)p.off_in + (in_bytes > obs_tile ? in_bytes : obs_tile);
+    if (smem > 200 * 1024) return cudaErrorNotSupported;
+    const long long tiles = (p.env_end - p.env_begin + 31) / 32;
+    claim_stream(h, s, false);
+    args.p = p;
+    for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)tiles); lc.blockDim = dim3(64); lc.dynamicSmemBytes = smem;
+    lc.stream = s;
+    cudaLaunchAttribute attr[1];
+    pdl_attr(h, s, lc, attr);
+    static bool attr_set = false;       // per instantiation
+    if (!attr_set) { cudaFuncSetAttribute(rollout2_kernel<NC, A4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+    return cudaLaunchKernelEx(&lc, rollout2_kernel<NC, A4>, args);
+}
+
+template <int NC>
+static cudaError_t launch_rollout2_nc(ngw_handle* h, const StepParams& p, cudaStream_t s) {
+    if (h->wshape == 0 || !h->use_tma || h->ms > 32 || !h->rollout2) return cudaErrorNotSupported;
+    if (h->obs_dim > 0 && h->lidar_mode != 1) return cudaErrorNotSupported;
+    if (h->obs_u8 && p.obs && p.obs_row_bytes % 16 != 0 && false) return cudaErrorNotSupported;
+    for (const DevConfig& dc : h->h_cfgs)
+        if (dc.c.n_inv_obs > NGW_REGSINK_TAIL) return cudaErrorNotSupported;
+    if (p.policy_w == nullptr) return launch_rollout2_na<NC, 0>(h, p, s);
+    switch ((p.policy_actions + 3) / 4) {
+        case 1: return launch_rollout2_na<NC, 1>(h, p, s);
+        case 2: return launch_rollout2_na<NC, 2>(h, p, s);
+        case 3: return launch_rollout2_na<NC, 3>(h, p, s);
+        default: return launch_rollout2_na<NC, 4>(h, p, s);
+    }
 }
 
 static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
@@ -656,7 +776,9 @@ static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
     int nc = h->force_global_cfg ? 0 : h->n_cfgs;
     cudaError_t e;
     if (is_multi(p)) {
-        if (nc == 0 || nc > 16) e = launch_rollout_nc<0>(h, p, s);
+        e = nc == 1 ? launch_rollout2_nc<1>(h, p, s) : launch_rollout2_nc<0>(h, p, s);
+        if (e != cudaErrorNotSupported) { /* taken */ }
+        else if (nc == 0 || nc > 16) e = launch_rollout_nc<0>(h, p, s);
         else if (nc == 1) e = launch_rollout_nc<1>(h, p, s);
         else if (nc <= 4) e = launch_rollout_nc<4>(h, p, s);
         else e = launch_rollout_nc<16>(h, p, s);
@@ -855,5 +977,6 @@ int ngw_stats(ngw_handle* h, double* out8_dev, int32_t reset_after, void* stream
 }
 
 int64_t ngw_launch_count(ngw_handle* h) { return h ? h->launches : 0; }
+int64_t ngw_concurrent_launch_count(ngw_handle* h) { return h ? h->concurrent_launches : 0; }
 
 }  // extern "C"

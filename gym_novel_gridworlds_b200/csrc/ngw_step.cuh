@@ -112,6 +112,8 @@ struct StepParams {
     int lidar_mode;             // 1: every config takes the line-gather path with one shared geometry (the common case)
     int early_state;            // 1: this handle's state is complete already, state loads may precede griddepcontrol.wait
     int pdl_early;              // 1: trigger the dependent launch right after the wait (A/B knob NGW_PDL_EARLY)
+    int concurrent;             // step1w_kernel: 1 = this launch is independent of its predecessor (another handle's step, proven
+                                // adjacent in a stream capture, disjoint buffers): the tile warps do not wait for it, only the gate warp
     int auto_reset, max_episode_steps;
     int lidar_uniform;          // every config has the same beam tables (then config 0's are read, warp-uniformly)
     int cache_hints;            // bit 0: state tiles are loaded L2::evict_first, bit 1: the observation tile is stored evict_first
@@ -836,7 +838,7 @@ __global__ void __launch_bounds__(512, 2) step1w_kernel(const __grid_constant__ 
 
     // ---- prologue without global state
     if (threadIdx.x == 0) scta[0] = 0;
-    if (lane == 0) mbar_init(bar, 1);
+    if (lane == 0 && wid < p.tiles_per_cta) mbar_init(bar, 1);   // (the CTA's last warp is the gate warp: it owns no tile)
     if (NC > 0) {
         if (threadIdx.x < NGW_MAX_MAP_SIZE / 4)
             reinterpret_cast<uint32_t*>(sfirstk)[threadIdx.x] =
@@ -848,6 +850,17 @@ __global__ void __launch_bounds__(512, 2) step1w_kernel(const __grid_constant__ 
                     reinterpret_cast<const uint32_t*>(args.cfg[k].c.lidar_slot)[threadIdx.x];
     }
     __syncthreads();                                                  // the only CTA-wide barrier
+
+    // The GATE warp (the CTA's last) keeps the stream's order: it waits for the preceding grid and only then lets the
+    // next launch start, so at most two consecutive launches are ever in flight and this grid cannot complete before its
+    // predecessor has.  In concurrent mode the tile warps below never wait: the two launches step different batches.
+    if (wid == p.tiles_per_cta) {
+        if (p.concurrent || p.pdl_early) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        }
+        return;
+    }
 
     const int8_t* gmap = p.map + e0 * p.cells;
     int32_t* ginv = p.inv + e0 * p.inv_stride;
@@ -869,28 +882,26 @@ __global__ void __launch_bounds__(512, 2) step1w_kernel(const __grid_constant__ 
     const bool early = p.early_state && active && !(p.dbg_skip & 64);
     if (early) {                                                      // see step1_kernel: this handle's state is complete already
         issue_loads();
-        ps = p.pose[e];
+        ps = __ldcg(&p.pose[e]);   // L2 only: launches overlap, an SM's L1 is not a safe place for another grid's data
     }
     // the part of the observation tile that lies beyond the rows it aliases is zeroed while the loads fly
     zero_span(region_a + in_bytes + (uint32_t)lane * 16u, region_a + obs_tile);
-    asm volatile("griddepcontrol.wait;" ::: "memory");                // previous kernel of the stream done + visible
-    // the dependent launch may start now: it is co-resident (half an SM per launch) and blocks in its own wait until
-    // this grid has completed
-    if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (!active || (p.dbg_skip & 64)) { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); return; }
+    if (!p.concurrent) asm volatile("griddepcontrol.wait;" ::: "memory");   // previous kernel of the stream done + visible
+    // (the gate warp has let the dependent launch start by now or will: it is co-resident — half an SM per launch)
+    if (!active || (p.dbg_skip & 64)) return;
     if (!early) {
         issue_loads();
-        ps = p.pose[e];
+        ps = __ldcg(&p.pose[e]);   // L2 only: launches overlap, an SM's L1 is not a safe place for another grid's data
     }
 
-    const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[e];
+    const int cfg_i = (NC == 1) ? 0 : (int)__ldcg(&p.cfg_id[e]);
     const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
     const ngw_config& cfg = dc.c;
     int action = 0;
-    if (stepping && valid) action = p.actions[e];
+    if (stepping && valid) action = __ldcg(&p.actions[e]);
 
     mbar_wait(bar, 0);
-    if (p.dbg_skip & 128) { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); return; }
+    if (p.dbg_skip & 128) return;
 
     EnvRow env;
     env.m = smap + lane * p.cells;
@@ -915,12 +926,12 @@ __global__ void __launch_bounds__(512, 2) step1w_kernel(const __grid_constant__ 
             counts = 1u;
             if (a.op == NGW_OP_INVALID) {                             // wrappers.py:76 / pogostick_v1_env.py:236 would raise
                 counts |= 1u << 24;
-                p.err[e] |= NGW_ERR_INVALID_ACTION;
+                atomicOr(&p.err[e], NGW_ERR_INVALID_ACTION);
             } else {
                 if (!(p.dbg_skip & 1)) step_env(env, cfg, a, o);
                 int finished = o.done;
                 if (p.max_episode_steps > 0) {
-                    int len = p.ep_len[e] + 1;
+                    int len = __ldcg(&p.ep_len[e]) + 1;
                     if (len >= p.max_episode_steps) { finished = 1; o.done = 1; }   // harness truncation knob
                     p.ep_len[e] = finished && p.auto_reset ? 0 : len;
                 }
@@ -1054,6 +1065,342 @@ __global__ void __launch_bounds__(512, 2) step1w_kernel(const __grid_constant__ 
     }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     bulk_wait_read<0>();                                              // shared memory must outlive the bulk stores' reads
+}
+
+// ------------------------------------------------------------------ the K-STEP ROLLOUT kernel, LANE-PAIR shape
+// (ngw_rollout / ngw_rollout_policy on grids up to 32x32 with the canonical 8-beam geometry; everything else takes
+// rollout_kernel above.)  A rollout never leaves the SM between steps, so it is bound by the latency of one warp's
+// dependent instruction chain, not by memory: 14 tiles per SM at one warp per tile issue ~0.35 instructions per cycle and
+// scheduler.  Here a tile of 32 envs is stepped by TWO warps of 16 envs each, and every env is owned by a PAIR of lanes
+// (l, l + 16): the low lane runs the step; for the LidarInFront observation each lane gathers two of the four lines
+// through the agent — low lane row + column, high lane the two diagonals — in the SAME instruction stream (per-lane line
+// base, stride and beam directions: no divergence); each lane accumulates the policy scores of its own <= 4 hits (and of
+// every other inventory-tail entry), W rows read as 128-bit words, and one butterfly exchange adds the halves.
+// Per-step statistics stay in registers and are folded once per launch.  The final observation tile aliases the
+// grid / inventory rows like step1w_kernel's.
+struct PairLine {
+    const int8_t* p0;       // cell of the line in grid row 0 (row line: grid column 0)
+    int stride;             // linear offset between consecutive cells of the line
+    int pos;                // the agent's bit on the line
+    uint32_t mask;          // bits whose cell lies inside the grid
+    int a_pos, a_neg;       // compass directions of the two beams
+};
+
+template <int MS>
+__device__ __forceinline__ uint32_t pair_gather(const PairLine& ln, int ms_rt) {
+    const int ms = MS > 0 ? MS : ms_rt;
+    const uint8_t* q = reinterpret_cast<const uint8_t*>(ln.p0);
+    uint32_t occ = 0;
+    if (MS > 0) {
+#pragma unroll
+        for (int i = 0; i < ms; i++) occ |= (q[i * ln.stride] != 0 ? 1u : 0u) << i;
+    } else {
+#pragma unroll 4
+        for (int i = 0; i < ms; i++) occ |= (q[i * ln.stride] != 0 ? 1u : 0u) << i;
+    }
+    return occ & ln.mask;
+}
+
+// the two beams of one line -> (observation index << 8) | range, 0 = nothing reported
+__device__ __forceinline__ void pair_beams(uint32_t occ, const PairLine& ln, const int8_t* here, bool diagonal, int K, int L,
+                                           int rot, const LidarLuts& luts, uint32_t& hit_pos, uint32_t& hit_neg) {
+    const int p = ln.pos;
+    const uint32_t hi = (occ >> p) >> 1;
+    const uint32_t lo = occ & ((1u << p) - 1u);
+    const int n_pos = __ffs((int)hi);
+    const int n_neg = lo != 0 ? p - (31 - __clz((int)lo)) : 0;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int n = side ? n_neg : n_pos;
+        const int a = side ? ln.a_neg : ln.a_pos;
+        const int kd = (int)luts.firstk[n > 0 ? n - 1 : 0];
+        const int k = diagonal ? kd : (n <= K ? n : 0);
+        const int id = here[side ? -n * ln.stride : n * ln.stride];
+        const int slot = luts.slot[id];                               // -1: occludes but is not a lidar item (Q2)
+        const uint32_t h = (slot >= 0 && n != 0 && k != 0) ? ((uint32_t)(((a - rot) & 7) * L + slot) << 8) | (uint32_t)k : 0u;
+        if (side) hit_neg = h; else hit_pos = h;
+    }
+}
+
+// the four hits of this lane's two lines (half 0: row, column; half 1: diagonal, anti-diagonal)
+template <int MS>
+__device__ __forceinline__ void pair_lidar(const EnvRow& e, const ngw_config& cfg, const LidarDev& t, const LidarLuts& luts,
+                                           int half, uint32_t hit[4]) {
+    const int ms = MS > 0 ? MS : e.ms;
+    const int r = e.r, c = e.c;
+    const uint32_t full = 0xFFFFFFFFu >> (32 - ms);
+    const int dlo = r - c, alo = c + r - (ms - 1);
+    PairLine l1, l2;
+    l1.p0 = e.m + (half ? (c - r) : r * ms);      l1.stride = half ? ms + 1 : 1;   l1.pos = half ? r : c;
+    l1.mask = half ? (dlo >= 0 ? (full << dlo) : (full >> (-dlo))) & full : full;
+    l1.a_pos = half ? 1 : 2;                      l1.a_neg = half ? 5 : 6;
+    l2.p0 = e.m + (half ? (c + r) : c);           l2.stride = half ? ms - 1 : ms;  l2.pos = r;
+    l2.mask = half ? (alo >= 0 ? (full << alo) : (full >> (-alo))) & full : full;
+    l2.a_pos = half ? 7 : 0;                      l2.a_neg = half ? 3 : 4;
+    const uint32_t o1 = pair_gather<MS>(l1, ms), o2 = pair_gather<MS>(l2, ms);
+    const int K = cfg.max_range, L = cfg.n_lidar_items;
+    const int rot = (int)((*reinterpret_cast<const uint32_t*>(t.rot) >> (8 * e.facing)) & 7u);
+    const int8_t* here = e.m + r * ms + c;
+    pair_beams(o1, l1, here, half != 0, K, L, rot, luts, hit[0], hit[1]);
+    pair_beams(o2, l2, here, half != 0, K, L, rot, luts, hit[2], hit[3]);
+}
+
+// score[a] += v * W[idx][a], a < 4 * A4; W rows are 16 * A4 bytes in shared memory
+template <int A4>
+__device__ __forceinline__ void policy_mac(int (&acc)[16], const int32_t* w, int idx, int v) {
+    const int4* row = reinterpret_cast<const int4*>(w + idx * (4 * A4));
+#pragma unroll
+    for (int q = 0; q < A4; q++) {
+        const int4 x = row[q];
+        acc[4 * q] += v * x.x; acc[4 * q + 1] += v * x.y; acc[4 * q + 2] += v * x.z; acc[4 * q + 3] += v * x.w;
+    }
+}
+
+#define NGW_R2_HDR 128
+// A4: ceil(policy actions / 4) for the closed loop, 0 = actions given or drawn (no per-step observation)
+template <int NC, int A4>
+__global__ void __launch_bounds__(64, 14) rollout2_kernel(const __grid_constant__ StepArgs<NC> args) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const StepParams& p = args.p;
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int half = lane >> 4, el = (lane & 15) + 16 * g;            // lane pair (l, l + 16) owns env el of the tile
+    const bool low = half == 0;
+    const long long e0 = p.env_begin + (long long)blockIdx.x * 32;
+    const long long e = e0 + el;
+    const bool valid = e < p.env_end;
+    const bool full_tile = e0 + 32 <= p.env_end;
+
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    uint8_t* sfirstk = smem + p.off_luts;
+    int8_t* sslot = reinterpret_cast<int8_t*>(smem + p.off_luts + NGW_MAX_MAP_SIZE);
+    uint32_t* sscratch = reinterpret_cast<uint32_t*>(smem + p.off_scratch) + g * NGW_RESET_SCRATCH_WORDS;   // auto-reset, per warp
+    int32_t* spol = reinterpret_cast<int32_t*>(smem + p.off_policy);  // bias [16] | W [obs_dim][4 * A4]
+    unsigned char* region = smem + p.off_in;
+    int8_t* smap = reinterpret_cast<int8_t*>(region);
+    int32_t* sinv = reinterpret_cast<int32_t*>(region + p.map_bytes);
+    unsigned char* sobs = region;                                     // aliases the rows above (written after the last step)
+    const uint32_t in_bytes = (uint32_t)(p.map_bytes + p.inv_bytes);
+
+    const int8_t* gmap = p.map + e0 * p.cells;
+    int32_t* ginv = p.inv + e0 * p.inv_stride;
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    if (NC > 0) {
+        if (threadIdx.x < NGW_MAX_MAP_SIZE / 4)
+            reinterpret_cast<uint32_t*>(sfirstk)[threadIdx.x] =
+                reinterpret_cast<const uint32_t*>(args.cfg[0].lidar.firstk)[threadIdx.x];
+#pragma unroll
+        for (int k = 0; k < NC; k++)
+            if (threadIdx.x < NGW_MAX_ITEMS / 4)
+                reinterpret_cast<uint32_t*>(sslot + k * NGW_MAX_ITEMS)[threadIdx.x] =
+                    reinterpret_cast<const uint32_t*>(args.cfg[k].c.lidar_slot)[threadIdx.x];
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, in_bytes);
+        bulk_g2s(smap, gmap, (uint32_t)p.map_bytes, bar);
+        bulk_g2s(sinv, ginv, (uint32_t)p.inv_bytes, bar);
+    }
+    if (A4 > 0) {                                                     // policy: bias, then W with rows padded to 4 * A4 entries
+        const int A = p.policy_actions, AP = A4 > 0 ? 4 * A4 : 4;
+        for (int i = threadIdx.x; i < 16; i += 64) spol[i] = i < A ? p.policy_b[i] : 0;
+        for (int i = threadIdx.x; i < p.obs_dim * AP; i += 64) {
+            const int j = i / AP, a = i - j * AP;
+            spol[16 + i] = a < A ? p.policy_w[j * A + a] : 0;
+        }
+    }
+    const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[valid ? e : e0];
+    const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
+    const ngw_config& cfg = dc.c;
+    const LidarDev& geom = (NC > 0) ? args.cfg[0].lidar : dc.lidar;
+    LidarLuts luts;
+    if (NC > 0) { luts.slot = sslot + cfg_i * NGW_MAX_ITEMS; luts.firstk = sfirstk; }
+    else { luts.slot = p.dcfgs[cfg_i].c.lidar_slot; luts.firstk = p.dcfgs[cfg_i].lidar.firstk; }
+    const bool given_actions = A4 == 0 && !p.random_policy;
+    uchar4 ps = p.pose[valid ? e : e0];
+    int action = 0;
+    if (given_actions && valid && low) action = p.actions[e];
+    mbar_wait(bar, 0);
+    __syncthreads();                                                  // policy weights staged
+
+    EnvRow env;
+    env.m = smap + el * p.cells;
+    env.gm = p.map + e * p.cells;
+    env.inv = sinv + el * p.inv_stride;
+    env.ms = p.ms;
+    env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+
+    StepOut o;
+    o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0; o.goal = 0;
+    float cost_sum = 0.0f;
+    int reward_sum = 0, n_done = 0, n_succ = 0, n_reset = 0, n_invalid = 0;
+    const int n_lidar = cfg.n_lidar_items * cfg.n_beams;
+    for (int t = 0; t < p.n_steps; t++) {
+        int next_action = 0;
+        if (given_actions && t + 1 < p.n_steps && valid && low) next_action = p.actions[(t + 1) * p.act_stride + e];
+        if (A4 > 0) {                                                 // observe (two lines per lane), score, exchange, argmax
+            int acc[16];
+#pragma unroll
+            for (int a = 0; a < 16; a++) acc[a] = (a < 4 * A4 && low) ? spol[a] : 0;
+            if (cfg.n_beams > 0) {
+                uint32_t hit[4];
+                if (p.ms == 10) pair_lidar<10>(env, cfg, geom, luts, half, hit);
+                else pair_lidar<0>(env, cfg, geom, luts, half, hit);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (hit[j]) policy_mac<A4>(acc, spol + 16, (int)(hit[j] >> 8), (int)(hit[j] & 0xFFu));
+                // inventory tail: entry i = 2 q + half
+                const int n_tail = cfg.n_inv_obs, tf = dc.lidar.tail_first;
+                for (int i = half; i < n_tail; i += 2) {
+                    const int v = env.inv[tf >= 0 ? tf + i : (int)cfg.inv_obs_item[i]];
+                    if (v != 0) policy_mac<A4>(acc, spol + 16, n_lidar + i, v);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 4 * A4; a++) acc[a] += __shfl_xor_sync(0xFFFFFFFFu, acc[a], 16);
+            const int n_valid = cfg.n_actions < p.policy_actions ? cfg.n_actions : p.policy_actions;
+            int best = 0, best_v = acc[0];
+#pragma unroll
+            for (int a = 1; a < 4 * A4; a++) if (a < n_valid && acc[a] > best_v) { best_v = acc[a]; best = a; }
+            action = best;
+        } else if (p.random_policy && valid && low) {
+            Philox pr;
+            pr.init(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, 0xFFF);
+            action = (int)pr.below((uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
+        }
+        int did_reset = 0;
+        __syncwarp();                                                 // the high lanes have read the rows
+        if (valid && low) {
+            if (p.actions_out != nullptr) p.actions_out[t * p.act_stride + e] = action;
+            o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0; o.goal = 0;
+            ngw_action_entry a;
+            a.op = NGW_OP_INVALID;
+            if (action >= 0 && action < cfg.n_actions) {
+                uint2 raw = *reinterpret_cast<const uint2*>(&cfg.actions[action]);
+                memcpy(&a, &raw, sizeof(a));
+            }
+            if (a.op == NGW_OP_INVALID) {
+                n_invalid++;
+                p.err[e] |= NGW_ERR_INVALID_ACTION;
+            } else {
+                step_env(env, cfg, a, o);
+                n_succ += o.goal;
+                int finished = o.done;
+                if (p.max_episode_steps > 0) {
+                    int len = p.ep_len[e] + 1;
+                    if (len >= p.max_episode_steps) { finished = 1; o.done = 1; }
+                    p.ep_len[e] = finished && p.auto_reset ? 0 : len;
+                }
+                if (finished && p.auto_reset) { did_reset = 1; n_reset++; }
+            }
+            reward_sum += o.reward; cost_sum += o.cost; n_done += o.done;
+        }
+        if (p.auto_reset) {
+            if (__ballot_sync(0xFFFFFFFFu, did_reset) != 0) {         // regenerate in place, warp-cooperatively (this warp's 16 envs)
+                uchar4 q = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing, (unsigned char)env.sel);
+                auto_reset_warp(p, p.dcfgs, cfg_i, did_reset != 0, smap + 16 * g * p.cells, sinv + 16 * g * p.inv_stride,
+                                sscratch, e0 + 16 * g, q);
+                env.r = q.x; env.c = q.y; env.facing = q.z; env.sel = q.w;
+            }
+        }
+        // the pair's high lane follows the low lane's pose; the step's writes to the tile become visible to it
+        {
+            uint32_t pose = (uint32_t)env.r | ((uint32_t)env.c << 8) | ((uint32_t)env.facing << 16) | ((uint32_t)env.sel << 24);
+            __syncwarp();
+            pose = __shfl_sync(0xFFFFFFFFu, pose, lane & 15);
+            env.r = pose & 0xFF; env.c = (pose >> 8) & 0xFF; env.facing = (pose >> 16) & 0xFF; env.sel = pose >> 24;
+        }
+        action = next_action;
+    }
+
+    // ---- outputs and statistics (low lanes own them)
+    if (valid && low) {
+        p.pose[e] = make_uchar4((unsigned char)env.r, (unsigned char)env.c, (unsigned char)env.facing, (unsigned char)env.sel);
+        p.reward[e] = (float)reward_sum;
+        p.done[e] = (uint8_t)o.done;
+        p.cost[e] = cost_sum;
+        p.result[e] = (uint8_t)o.result;
+        if (p.done_count != nullptr) p.done_count[e] = n_done;
+        if (p.msg != nullptr) p.msg[e] = (uint16_t)o.msg;
+    }
+    if (p.stats != nullptr) {
+        const int steps = (valid && low) ? p.n_steps - n_invalid : 0;
+        const int s_steps = __reduce_add_sync(0xFFFFFFFFu, steps), s_rew = __reduce_add_sync(0xFFFFFFFFu, reward_sum);
+        const int s_done = __reduce_add_sync(0xFFFFFFFFu, n_done), s_succ = __reduce_add_sync(0xFFFFFFFFu, n_succ);
+        const int s_reset = __reduce_add_sync(0xFFFFFFFFu, n_reset), s_inv = __reduce_add_sync(0xFFFFFFFFu, n_invalid);
+        const float s_cost = warp_sum(cost_sum);
+        if (lane == 0) {
+            double* sg = p.stats + (size_t)(blockIdx.x % NGW_STAT_SLOTS) * NGW_STAT_COUNT;
+            atomicAdd(&sg[NGW_STAT_STEPS], (double)s_steps);
+            atomicAdd(&sg[NGW_STAT_REWARD_SUM], (double)s_rew);
+            atomicAdd(&sg[NGW_STAT_COST_SUM], (double)s_cost);
+            if (s_done) atomicAdd(&sg[NGW_STAT_EPISODES], (double)s_done);
+            if (s_succ) atomicAdd(&sg[NGW_STAT_SUCCESSES], (double)s_succ);
+            if (s_reset) atomicAdd(&sg[NGW_STAT_RESETS], (double)s_reset);
+            if (s_inv) atomicAdd(&sg[NGW_STAT_INVALID], (double)s_inv);
+        }
+    }
+
+    // ---- inventory tile out, final observation into the aliased region, observation tile out
+    fence_async_smem();
+    __syncthreads();                                                  // both warps are done stepping
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const bool tma_store = full_tile && !p.plain_store;
+    if (tma_store) {
+        if (threadIdx.x == 0) { bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes); bulk_commit(); }
+    } else {
+        const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
+        uint4* d4 = reinterpret_cast<uint4*>(ginv);
+        for (int i = threadIdx.x; i < (p.inv_bytes >> 4); i += 64) d4[i] = s4[i];
+    }
+    if (p.obs != nullptr) {
+        uint32_t hit[4] = {0u, 0u, 0u, 0u};
+        int32_t tail[NGW_REGSINK_TAIL];
+        const bool look = valid && cfg.n_beams > 0;
+        const int n_tail = cfg.n_inv_obs, tf = dc.lidar.tail_first;
+        if (look) {
+            if (p.ms == 10) pair_lidar<10>(env, cfg, geom, luts, half, hit);
+            else pair_lidar<0>(env, cfg, geom, luts, half, hit);
+#pragma unroll
+            for (int i = 0; i < NGW_REGSINK_TAIL; i++)
+                tail[i] = i < n_tail ? env.inv[tf >= 0 ? tf + i : (int)cfg.inv_obs_item[i]] : 0;
+        }
+        if (threadIdx.x == 0) bulk_wait_read<0>();
+        __syncthreads();                                              // rows consumed by everyone (and by the inventory store)
+        const uint32_t region_a = smem_u32(region);
+        for (uint32_t a = region_a + threadIdx.x * 16u; a < region_a + (uint32_t)p.obs_bytes; a += 1024u)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
+        __syncthreads();
+        if (look) {
+            ObsRow orow;
+            orow.p = sobs + el * p.obs_row_bytes;
+            orow.u8 = p.obs_u8;
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (hit[j]) orow.put((int)(hit[j] >> 8), (int)(hit[j] & 0xFFu));
+            if (low) {
+                int32_t* tl = orow.tail(n_lidar);
+#pragma unroll
+                for (int i = 0; i < NGW_REGSINK_TAIL; i++) if (i < n_tail) tl[i] = tail[i];
+            }
+        }
+        if (tma_store) {
+            fence_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned char* gobs = p.obs + e0 * p.obs_row_bytes;
+                if (p.cache_hints & 2) bulk_s2g_hint(gobs, sobs, (uint32_t)p.obs_bytes, policy_evict_first());
+                else bulk_s2g(gobs, sobs, (uint32_t)p.obs_bytes);
+                bulk_commit();
+            }
+        } else {
+            __syncthreads();
+            const int n = (int)((p.env_end - e0 < 32 ? p.env_end - e0 : 32)) * (p.obs_row_bytes >> 2);
+            uint32_t* gobs = reinterpret_cast<uint32_t*>(p.obs + e0 * p.obs_row_bytes);
+            const uint32_t* so = reinterpret_cast<const uint32_t*>(sobs);
+            for (int i = threadIdx.x; i < n; i += 64) gobs[i] = so[i];
+        }
+    }
+    if (threadIdx.x == 0) bulk_wait_read<0>();                        // shared memory must outlive the bulk stores' reads
 }
 
 }  // namespace ngw

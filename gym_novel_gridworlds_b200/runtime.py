@@ -308,6 +308,11 @@ class BatchHandle(object):
     def launch_count(self):
         return int(self.lib.ngw_launch_count(self._h))
 
+    def concurrent_launch_count(self):
+        """One-step launches that ran overlapped with their predecessor (another handle's step, proven adjacent in a
+        stream capture; see include/ngw.h)."""
+        return int(self.lib.ngw_concurrent_launch_count(self._h))
+
 
 _MSG_FIXED = {0: '', 1: 'Block in path', 3: 'Block tree_tap placed', 5: 'Item not found in inventory',
               6: 'No tree_log near tree_tap', 7: 'No tree_tap found', 8: 'No wool found',

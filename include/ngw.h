@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NGW_ABI_VERSION 9
+#define NGW_ABI_VERSION 10
 
 #define NGW_MAX_ITEMS 24          /* reference asserts len(items) <= 20 (pogostick_v1_env.py:75,220) */
 #define NGW_MAX_ACTIONS 48
@@ -326,6 +326,15 @@ int ngw_stats(ngw_handle* h, double* out8_dev, int32_t reset_after, void* stream
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches claim). */
 int64_t ngw_launch_count(ngw_handle* h);
+
+/* Of those, the one-step launches that ran OVERLAPPED with their predecessor.  Two consecutive ngw_step launches on one
+ * stream are independent when they step different handles and share no caller buffer (actions, observations, reward,
+ * done, step_cost, result, messages); the library overlaps them only when it can PROVE that nothing was enqueued between
+ * them, which it can inside a stream capture (the stream's dependency set is exactly the previous launch's graph node):
+ * the tile warps of the second launch then do not wait for the first grid, while one gate warp per CTA does and only
+ * then lets the third launch start — at most two launches are in flight, completion stays in stream order, results are
+ * identical.  Eager launches always wait.  NGW_NO_CONCURRENT=1 (read by ngw_create) turns the overlap off. */
+int64_t ngw_concurrent_launch_count(ngw_handle* h);
 
 #ifdef __cplusplus
 }

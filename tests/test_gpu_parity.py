@@ -519,6 +519,41 @@ def test_warp_per_tile_shape(wshape, ctiles, extra):
                     assert torch.equal(x, y), "launch %d (%s)" % (t, fmt)
             for a, b in zip(hs, ref):
                 assert torch.equal(a.map, b.map) and torch.equal(a.inventory, b.inventory) and torch.equal(a.pose, b.pose)
+            # the same rotation as ONE captured graph: launches 2.. are proven independent of their predecessor and overlap
+            # it (gate warp); replayed three times against the one-at-a-time handles
+            stream = torch.cuda.Stream()
+            graph = torch.cuda.CUDAGraph()
+            keep = []
+            c0 = sum(x.concurrent_launch_count() for x in hs)
+            with torch.cuda.stream(stream):
+                with torch.cuda.graph(graph, stream=stream):
+                    for t in range(12):
+                        keep.append(hs[t % 3].step(acts[t]))
+            n_conc = sum(x.concurrent_launch_count() for x in hs) - c0
+            if not extra:
+                assert n_conc == 11, n_conc
+            if extra == 'NGW_NO_PDL':
+                assert n_conc == 0
+            for rep in range(3):
+                graph.replay()
+                torch.cuda.synchronize()
+                for t in range(12):
+                    want = ref[t % 3].step(acts[t])
+                    torch.cuda.synchronize()
+                    if t >= 9:                                        # each handle's buffers hold its latest step
+                        for x, y in zip(keep[t], want):
+                            assert torch.equal(x, y), "graph replay %d launch %d (%s)" % (rep, t, fmt)
+                for a, b in zip(hs, ref):
+                    assert torch.equal(a.map, b.map) and torch.equal(a.inventory, b.inventory) and torch.equal(a.pose, b.pose)
+                    np.testing.assert_allclose(a.stats(reset=False).cpu().numpy(), b.stats(reset=False).cpu().numpy(), rtol=1e-9)
+            # a handle stepped twice in a row, or buffers shared between neighbours, are never overlapped
+            c0 = hs[0].concurrent_launch_count() + hs[1].concurrent_launch_count()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(stream):
+                with torch.cuda.graph(g2, stream=stream):
+                    hs[0].step(acts[0]); hs[0].step(acts[1])
+                    hs[1].step(hs[0].reward.view(torch.int32))        # actions alias the predecessor's output
+            assert hs[0].concurrent_launch_count() + hs[1].concurrent_launch_count() == c0
     finally:
         del os.environ['NGW_WSHAPE'], os.environ['NGW_CTILES']
         if extra:

@@ -402,6 +402,9 @@ class Workload(object):
     def launches(self):
         return sum(h.launch_count() for h in self.batches)
 
+    def concurrent_launches(self):
+        return sum(h.concurrent_launch_count() for h in self.batches)
+
     def close(self):
         for h in self.batches:
             h.close()
@@ -440,9 +443,10 @@ def time_regions(wl, K, dev, world, floor_ms=VALUE_FLOOR_MS, n_streams=1, max_re
                         stream.wait_stream(s_)
         return g
 
-    before = wl.launches()
+    before, before_c = wl.launches(), wl.concurrent_launches()
     graph = capture(g_steps)
     launches_per_step = (wl.launches() - before) / g_steps
+    wl.overlapped_launches_per_graph = wl.concurrent_launches() - before_c     # launches proven independent of their predecessor
     replays, rem = K // g_steps, K % g_steps
     graph_rem = capture(rem, replays * g_steps) if rem else None
 
@@ -590,6 +594,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     regions, (t_wall0, t_wall1), launches_per_step, g_steps = time_regions(wl, K, dev, world)
     ms_region = float(np.median(regions))
+    overlapped_per_graph = wl.overlapped_launches_per_graph
     ov_regions = time_regions(wl, K, dev, world, n_streams=min(3, n_batches))[0]
     ms_overlap = float(np.median(ov_regions))
 
@@ -604,6 +609,20 @@ def run_ours(args, rank, world, local_rank):
             reg2 = time_regions(w2, K, dev, world, floor_ms=20.0)[0]
             l2_sens[nb] = float(np.median(reg2)) / K
             w2.close()
+
+    # ---- the same K-step graph with every launch waiting for its predecessor (NGW_NO_CONCURRENT): what the overlap buys
+    ms_serial = 0.0
+    if args.workload == 'C2' and not args.no_workloads:
+        os.environ['NGW_NO_CONCURRENT'] = '1'
+        try:
+            w3 = Workload('C2', rank, world, dev, n_batches=n_batches)
+        finally:
+            del os.environ['NGW_NO_CONCURRENT']
+        for i in range(n_batches):
+            w3.step(i)
+        torch.cuda.synchronize(dev)
+        ms_serial = float(np.median(time_regions(w3, K, dev, world, floor_ms=20.0)[0]))
+        w3.close()
 
     # ---- K-step rollout kernel: 64 steps per launch, uniform random policy drawn on the device
     roll_T = 64
@@ -701,6 +720,7 @@ def run_ours(args, rank, world, local_rank):
         extra[name] = {"workload": w.desc, "scaling": w.scaling, "envs_per_gpu": w.envs, "total_envs": w.total_envs,
                        "batches_rotated": w.n_batches, "steps": K_x, "regions": len(reg),
                        "launches_per_step": lps, "algorithmic_bytes_per_env_step": w.bytes_step,
+                       "overlapped_launches_per_graph": w.overlapped_launches_per_graph,
                        "reset_error_flags": w.reset_error_flags}
         extra_times.append(float(np.median(reg)))
         st = torch.zeros(8, dtype=torch.float64, device=dev)
@@ -720,10 +740,10 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)                     # episode statistics over NCCL
     red = reduce_max([ms_region, ms_overlap, t_e2e, t_block, t_e2e_i32, t_block_i32, roll_ms, roll_policy_ms, eager_ms,
-                      probe["ms_per_step_bytes"], torch_policy_ms] + extra_times)
+                      probe["ms_per_step_bytes"], torch_policy_ms, ms_serial] + extra_times)
     (ms_region, ms_overlap, t_e2e, t_block, t_e2e_i32, t_block_i32, roll_ms, roll_policy_ms, eager_ms, probe_ms,
-     torch_policy_ms) = red[:11]
-    extra_times = red[11:]
+     torch_policy_ms, ms_serial) = red[:12]
+    extra_times = red[12:]
 
     if rank == 0:
         ms_per_step = ms_region / K
@@ -769,7 +789,17 @@ def run_ours(args, rank, world, local_rank):
                     "numa": numa},
             "gpu_launches": int(round(launches_per_step * K)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "ngw::step_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "ngw::step1w_kernel",
+                         "launch_overlap": {
+                             "overlapped_launches_per_graph": overlapped_per_graph, "launches_per_graph": g_steps,
+                             "note": "consecutive launches of the K-step graph step DIFFERENT batches (rotation) and share no "
+                                     "buffer; inside a stream capture the library proves they are adjacent and lets the "
+                                     "second start while the first computes (one gate warp per CTA keeps stream order); "
+                                     "avg_launch_us = region / K, i.e. the launch-to-launch interval",
+                             "serialized": None if not ms_serial else {
+                                 "note": "same graph with NGW_NO_CONCURRENT=1 (every launch waits for its predecessor)",
+                                 "us_per_step": ms_serial / K * 1e3,
+                                 "frac": envs * bytes_step / (ms_serial / K * 1e-3) / 1e9 / peak}},
                          "peak_source": peak_src, "algorithmic_bytes_per_env_step": bytes_step,
                          "algorithmic_bytes_per_launch": envs * bytes_step, "avg_launch_us": ms_per_step * 1e3,
                          "l2_sensitivity": {"%d_batches_%.0f_MB" % (nb, nb * envs * bytes_step / 1e6):
@@ -778,7 +808,7 @@ def run_ours(args, rank, world, local_rank):
             "timing": {"regions": len(regions),
                        "region_ms_min_med_max": [min(regions), float(np.median(regions)), max(regions)],
                        "timed_ms_total": float(sum(regions)), "graph_steps": g_steps,
-                       "launch": "one stream, CUDA-graph replay (one kernel launch per step)",
+                       "launch": "one stream, CUDA-graph replay (one kernel launch per step; launches of different batches overlap)",
                        "reset_error_flags": headline_flags, "per_gpu_envs_resident": n_batches * envs},
             "overlapped": {"note": "same K steps, independent batches on %d parallel graph branches (launches overlap)"
                                    % min(3, n_batches), "value": total_envs * K / (ms_overlap * 1e-3), "unit": "env-steps/s",

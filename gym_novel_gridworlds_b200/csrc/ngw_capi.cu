@@ -41,6 +41,7 @@ struct ngw_handle {
     bool concurrent = true;                        // independent consecutive launches may overlap (NGW_NO_CONCURRENT)
     bool concurrent_waves = true;                  // ... also launches of several waves (NGW_NO_CONCURRENT_WAVES)
     bool rollout2 = true;                          // lane-pair rollout kernel (NGW_NO_ROLLOUT2)
+    bool alias = true;                             // tile-group kernel, one tile per CTA: observation tile aliases the rows (NGW_NO_ALIAS)
     DevConfig* d_cfgs = nullptr;
     std::vector<int16_t*> d_luts;
     std::vector<DevConfig> h_cfgs;
@@ -300,6 +301,7 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     h->concurrent = getenv("NGW_NO_CONCURRENT") == nullptr;
     h->concurrent_waves = getenv("NGW_NO_CONCURRENT_WAVES") == nullptr;
     h->rollout2 = getenv("NGW_NO_ROLLOUT2") == nullptr;
+    h->alias = getenv("NGW_NO_ALIAS") == nullptr;
     h->pdl_early = getenv("NGW_NO_PDL_EARLY") == nullptr;   // trigger right after the wait: C2 7.70 -> 7.60 us/step
     // streaming data (each tile is read once and its observations written once per step) should not linger in L2:
     // measured on C2 9.15 -> 8.82 us/step, C3 29.3 -> 28.0, C5 278 -> 274 (hinting the inventory store as well: 9.0)
@@ -406,6 +408,8 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     NGW_SMEM_ATTR4(step1_kernel, true, true); NGW_SMEM_ATTR4(step1_kernel, true, false);
     NGW_SMEM_ATTR4(step1_kernel, false, true);
 #undef NGW_SMEM_ATTR4
+    NGW_SMEM_ATTR((step1_kernel<true, 0, true, true>)); NGW_SMEM_ATTR((step1_kernel<true, 1, true, true>));
+    NGW_SMEM_ATTR((step1_kernel<true, 4, true, true>)); NGW_SMEM_ATTR((step1_kernel<true, 16, true, true>));
     NGW_SMEM_ATTR((step1w_kernel<0, 8>)); NGW_SMEM_ATTR((step1w_kernel<1, 8>)); NGW_SMEM_ATTR((step1w_kernel<4, 8>)); NGW_SMEM_ATTR((step1w_kernel<16, 8>));
     NGW_SMEM_ATTR((step1w_kernel<0, 16>)); NGW_SMEM_ATTR((step1w_kernel<1, 16>)); NGW_SMEM_ATTR((step1w_kernel<4, 16>)); NGW_SMEM_ATTR((step1w_kernel<16, 16>));
     NGW_SMEM_ATTR((rollout_kernel<true, 0>)); NGW_SMEM_ATTR((rollout_kernel<true, 1>)); NGW_SMEM_ATTR((rollout_kernel<true, 4>));
@@ -608,6 +612,11 @@ static cudaError_t launch_step1_nc(ngw_handle* h, StepParams p, cudaStream_t s) 
     // shared-memory row stride of the observation tile: rows of a multiple of 8 words get 16 bytes of padding
     p.obs_srow = p.obs_row_bytes + (((p.obs_row_bytes >> 2) % 8 == 0 && p.obs_row_bytes > 0 && !getenv("NGW_NO_ROW_PAD")) ? 16 : 0);
     p.group_bytes = (NGW_GROUP_HDR + p.map_bytes + p.inv_bytes + 32 * p.obs_srow + 127) & ~127;
+    // alias plan (one tile per CTA, see step1_kernel<.., kAlias>): the observation tile shares the rows' shared memory
+    bool alias = h->alias && h->use_tma && h->tiles_per_cta <= 1;
+    for (const DevConfig& dc : h->h_cfgs)
+        if (dc.c.n_inv_obs > NGW_REGSINK_TAIL || (dc.c.n_beams > 0 && !dc.lidar.lines && !dc.lidar.fast)) alias = false;
+    const int alias_bytes = (NGW_GROUP_HDR + ((p.map_bytes + p.inv_bytes) > 32 * p.obs_srow ? (p.map_bytes + p.inv_bytes) : 32 * p.obs_srow) + 127) & ~127;
     const int G = h->warps;
     p.g_shift = G == 4 ? 2 : (G == 2 ? 1 : 0);
     const long long tiles = (p.env_end - p.env_begin + 31) / 32;
@@ -633,6 +642,8 @@ static cudaError_t launch_step1_nc(ngw_handle* h, StepParams p, cudaStream_t s) 
     while (C > 1 && (size_t)p.off_groups + (size_t)C * p.group_bytes > 227 * 1024) C--;
     if (C < 1) C = 1;
     if (C > tiles) C = (int)tiles;
+    alias = alias && C == 1;
+    if (alias) p.group_bytes = alias_bytes;
     p.tiles_per_cta = C;
     p.n_tiles = (int)tiles;
     p.lidar_mode = h->lidar_mode;
@@ -652,6 +663,7 @@ static cudaError_t launch_step1_nc(ngw_handle* h, StepParams p, cudaStream_t s) 
     cudaLaunchAttribute attr[1];
     pdl_attr(h, s, lc, attr);
     if (C == 1) {
+        if (alias) return cudaLaunchKernelEx(&lc, (step1_kernel<true, NC, true, true>), args);
         if (h->use_tma) return cudaLaunchKernelEx(&lc, step1_kernel<true, NC, true>, args);
         return cudaLaunchKernelEx(&lc, step1_kernel<false, NC, true>, args);
     }

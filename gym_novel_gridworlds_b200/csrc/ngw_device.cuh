@@ -421,6 +421,7 @@ struct RegSink {
 #pragma unroll
         for (int j = 0; j < NT; j++) if (j == i) tail[j] = v;
     }
+    __device__ __forceinline__ void put(int, int) {}                 // (generic LUT walk: never taken with this sink)
     // row: the lane's (zeroed) observation row in shared memory
     __device__ __forceinline__ void flush(unsigned char* row, int tail_off, int n_tail) const {
         if (sh) {
@@ -570,8 +571,8 @@ __device__ __forceinline__ int lidar_line_share(int g, int G) {
 // obs row must be zero-filled for the lidar part by the caller; `zero` points at a byte that always reads 0 and lives in
 // the same address space as the grid row.  A tile can be shared by G warps: warp `g` of `G` casts beams
 // [g*NB, (g+1)*NB) with NB = 8/G (fast path) or beams g, g+G, ... (generic path).
-template <int NB>
-__device__ __forceinline__ void lidar_fast(const EnvRow& e, const ngw_config& cfg, const LidarDev& lidar, const ObsRow& obs,
+template <int NB, typename Sink>
+__device__ __forceinline__ void lidar_fast(const EnvRow& e, const ngw_config& cfg, const LidarDev& lidar, Sink& obs,
                                            const int8_t* zero, int b0) {
     // Each beam keeps a running cell pointer; axis beams advance one unit step per sample, diagonal beams advance
     // when round(0.71 k) grows (disp[1][k] - disp[1][k-1] is 0 or 1).  A beam that lands parks on `zero`, a cell
@@ -606,11 +607,9 @@ __device__ __forceinline__ void lidar_fast(const EnvRow& e, const ngw_config& cf
         for (int j = 0; j < NB; j++) flying |= u[j];
     }
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-        if (hit[j]) {
-            int slot = cfg.lidar_slot[hit[j] & 0xFF];                 // -1: occludes but is not a lidar item (Q2)
-            if (slot >= 0) obs.put((b0 + j) * L + slot, (int)(hit[j] >> 8));
-        }
+    for (int j = 0; j < NB; j++) {                                    // (sinks with positions: j-th beam of this warp's share)
+        const int slot = hit[j] ? (int)cfg.lidar_slot[hit[j] & 0xFF] : -1;   // -1: occludes but is not a lidar item (Q2)
+        obs.put_beam(j, slot >= 0, (b0 + j) * L + slot, (int)(hit[j] >> 8));
     }
 }
 
@@ -633,22 +632,21 @@ __device__ __forceinline__ void obs_tail(const EnvRow& e, const ngw_config& cfg,
 // geometry) config 0's, so that the table reads stay warp-uniform even when the lanes of a warp differ in config.
 // `luts` (line path only): where the per-lane indexed slot / firstk tables live; luts.slot == nullptr selects the
 // pointer-walking path even when the geometry is canonical.
-template <bool kSafe>
+template <bool kSafe, typename Sink = ObsRow>
 __device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& dc, const LidarDev& tables,
-                                              const LidarLuts& luts, const ObsRow& obs, const int8_t* zero, int g, int G,
+                                              const LidarLuts& luts, Sink& obs, const int8_t* zero, int g, int G,
                                               bool with_tail) {
     const ngw_config& cfg = dc.c;
     const int B = cfg.n_beams, K = cfg.max_range, L = cfg.n_lidar_items;
     if (dc.lidar.lines && luts.slot != nullptr && (e.ms <= 32 || !dc.lidar.fast || dc.lidar.lines == 2)) {
         const int sel = lidar_line_share(g, G);
-        ObsRow sink = obs;
-        if (sel) lidar_lines<kSafe, ObsRow>(e, cfg, tables, luts, sink, sel);
+        if (sel) lidar_lines<kSafe, Sink>(e, cfg, tables, luts, obs, sel);
     } else if (dc.lidar.fast) {
-        if (G == 1) lidar_fast<8>(e, cfg, tables, obs, zero, 0);
-        else if (G == 2) lidar_fast<4>(e, cfg, tables, obs, zero, g * 4);
-        else if (G == 3) { if (g < 2) lidar_fast<3>(e, cfg, tables, obs, zero, g * 3); else lidar_fast<2>(e, cfg, tables, obs, zero, 6); }
-        else if (G == 4) lidar_fast<2>(e, cfg, tables, obs, zero, g * 2);
-        else lidar_fast<1>(e, cfg, tables, obs, zero, g);
+        if (G == 1) lidar_fast<8, Sink>(e, cfg, tables, obs, zero, 0);
+        else if (G == 2) lidar_fast<4, Sink>(e, cfg, tables, obs, zero, g * 4);
+        else if (G == 3) { if (g < 2) lidar_fast<3, Sink>(e, cfg, tables, obs, zero, g * 3); else lidar_fast<2, Sink>(e, cfg, tables, obs, zero, 6); }
+        else if (G == 4) lidar_fast<2, Sink>(e, cfg, tables, obs, zero, g * 2);
+        else lidar_fast<1, Sink>(e, cfg, tables, obs, zero, g);
     } else {
         const int cells = e.ms * e.ms;
         const int pos = e.r * e.ms + e.c;
@@ -666,7 +664,7 @@ __device__ __forceinline__ void lidar_observe(const EnvRow& e, const DevConfig& 
             }
         }
     }
-    if (with_tail) { ObsRow sink = obs; obs_tail<ObsRow>(e, cfg, sink, dc.lidar.tail_first); }
+    if (with_tail) obs_tail<Sink>(e, cfg, obs, dc.lidar.tail_first);
 }
 
 // ------------------------------------------------------------------ reset (pogostick_v1_env.py:86-181 + novelty resets)

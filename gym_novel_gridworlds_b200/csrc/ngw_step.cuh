@@ -489,7 +489,10 @@ __device__ __forceinline__ void group_sync(int grp, int G) {
     else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(G * 32) : "memory");
 }
 
-template <bool kTma, int NC, bool kOne>
+// kAlias (one tile per CTA only): the observation tile ALIASES the grid / inventory rows, as in step1w_kernel — the lidar
+// hits and the inventory tail wait in registers (RegSink) until the rows have been consumed.  A 40x40 tile is then 52 KB
+// instead of 61 KB: four tiles per SM instead of three (C5).
+template <bool kTma, int NC, bool kOne, bool kAlias = false>
 __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ StepArgs<NC> args) {
     extern __shared__ __align__(128) unsigned char smem[];
     const StepParams& p = args.p;
@@ -514,7 +517,8 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
     TileOut* sout = reinterpret_cast<TileOut*>(gbase + 64);
     int8_t* smap = reinterpret_cast<int8_t*>(gbase + NGW_GROUP_HDR);
     int32_t* sinv = reinterpret_cast<int32_t*>(gbase + NGW_GROUP_HDR + p.map_bytes);
-    unsigned char* sobs = gbase + NGW_GROUP_HDR + p.map_bytes + p.inv_bytes;
+    unsigned char* sobs = gbase + NGW_GROUP_HDR + (kAlias ? 0 : p.map_bytes + p.inv_bytes);
+    const uint32_t in_bytes = (uint32_t)(p.map_bytes + p.inv_bytes);
 
     // ---- prologue without global state: barriers, zero pad, lidar tables
     if (threadIdx.x < 8) scta[threadIdx.x] = 0;
@@ -572,7 +576,7 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
         if (g < n_cls) ps = p.pose[e];
     }
     if (p.obs != nullptr) {                                           // the group zeroes its observation tile while the loads fly
-        uint32_t a = smem_u32(sobs) + (uint32_t)gt * 16u;
+        uint32_t a = smem_u32(sobs) + (uint32_t)gt * 16u + (kAlias ? in_bytes : 0u);   // (alias: only the part beyond the rows)
         const uint32_t end = smem_u32(sobs) + 32u * (uint32_t)p.obs_srow, st = 512u * (uint32_t)G;
         for (; a + 3u * st < end; a += 4u * st) {
             asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
@@ -664,8 +668,47 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
     group_sync<kOne>(grp, G);                                               // step results (grid, inventory, hand-over) visible to the group
     ps = sout[lane].ps;
     env.r = ps.x; env.c = ps.y; env.facing = ps.z; env.sel = ps.w;
+    const bool tma_store = kTma && full_tile && !p.plain_store;
+    if (kAlias && stepping) {                                         // the inventory tile leaves before its rows are overwritten
+        if (tma_store) {
+            fence_async_smem();
+            group_sync<kOne>(grp, G);
+            if (gt == 0 && !(p.dbg_skip & 16)) { bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes); bulk_commit(); }
+        } else {
+            const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
+            uint4* d4 = reinterpret_cast<uint4*>(ginv);
+            for (int i = gt; i < (p.inv_bytes >> 4); i += 32 * G) d4[i] = s4[i];
+        }
+    }
 
     // ---- LidarInFront observation of the new state into the shared-memory tile
+    if (kAlias) {
+        if (p.obs != nullptr) {
+            RegSink<NGW_REGSINK_TAIL> sink;
+            sink.init(p.obs_u8);
+            const bool look = valid && cfg.n_beams > 0;
+            if (look && !(p.dbg_skip & 2)) {
+                LidarLuts luts;
+                if (NC > 0) { luts.slot = sslot + cfg_i * NGW_MAX_ITEMS; luts.firstk = sfirstk; }
+                else { luts.slot = p.dcfgs[cfg_i].c.lidar_slot; luts.firstk = p.dcfgs[cfg_i].lidar.firstk; }
+                if (NC > 1 && !p.lidar_uniform) luts.slot = nullptr;
+                lidar_observe<false, RegSink<NGW_REGSINK_TAIL> >(env, dc, (NC > 1 && p.lidar_uniform) ? args.cfg[0].lidar : dc.lidar,
+                                                                 luts, sink, szero, g, G, g == G - 1);
+            }
+            if (gt == 0) bulk_wait_read<0>();                         // the inventory store has read its rows
+            group_sync<kOne>(grp, G);                                 // ... and every warp is done with the grid rows
+            {
+                const uint32_t z0 = smem_u32(sobs), zend = z0 + min(in_bytes, 32u * (uint32_t)p.obs_srow);
+                for (uint32_t a = z0 + (uint32_t)gt * 16u; a < zend; a += 512u * (uint32_t)G)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
+            }
+            group_sync<kOne>(grp, G);
+            if (look) {
+                const int n_lidar = cfg.n_lidar_items * cfg.n_beams;
+                sink.flush(sobs + lane * p.obs_srow, p.obs_u8 ? ((n_lidar + 3) & ~3) : 4 * n_lidar, g == G - 1 ? cfg.n_inv_obs : 0);
+            }
+        }
+    } else
     if (p.obs != nullptr && valid && cfg.n_beams > 0 && !(p.dbg_skip & 2)) {
         ObsRow orow;
         orow.p = sobs + lane * p.obs_srow;
@@ -690,7 +733,7 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
     group_sync<kOne>(grp, G);
     const bool padded_rows = p.obs_srow != p.obs_row_bytes;
     if (kTma && full_tile && !p.plain_store) {
-        if (gt == 0 && stepping && !(p.dbg_skip & 16)) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
+        if (!kAlias && gt == 0 && stepping && !(p.dbg_skip & 16)) bulk_s2g(ginv, sinv, (uint32_t)p.inv_bytes);
         if (p.obs != nullptr && !(p.dbg_skip & 8)) {
             unsigned char* gobs = p.obs + e0 * p.obs_row_bytes;
             if (!padded_rows) {                                       // the tile is one contiguous span on both sides
@@ -706,7 +749,7 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
         }
         if (g == 0) bulk_commit();
     } else {
-        if (stepping) {
+        if (stepping && !kAlias) {
             const uint4* s4 = reinterpret_cast<const uint4*>(sinv);
             uint4* d4 = reinterpret_cast<uint4*>(ginv);
             for (int i = gt; i < (p.inv_bytes >> 4); i += 32 * G) d4[i] = s4[i];

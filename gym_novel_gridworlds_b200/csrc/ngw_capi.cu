@@ -52,6 +52,8 @@ struct ngw_handle {
     int32_t* reset_list = nullptr; int32_t* reset_ctl = nullptr;   // auto-reset queue; ctl[0] = count, ctl[1] = finished CTAs
     int sm_count = 148;
     long long launches = 0, concurrent_launches = 0;
+    int reset_grid = 1;                            // CTAs per SM of the queued-reset kernel when it overlaps the next step (NGW_RESET_GRID)
+    bool last_step_concurrent = false;             // the latest one-step launch overlapped its predecessor
     // host-buffer path: its own stream, ordered against the caller's streams with events
     cudaStream_t hs = nullptr;
     cudaEvent_t ev_dev = nullptr;                  // recorded on the caller's stream when the host path has to wait for it
@@ -77,7 +79,8 @@ struct StreamTail {                       // the latest library launch on a stre
     ngw_handle* h = nullptr;
     unsigned long long cap_id = 0;        // stream capture it was recorded in, 0 = eager
     cudaGraphNode_t node = nullptr;       // its graph node (captures only)
-    bool pure_step = false;               // a one-step kernel launch with nothing behind it (no queued-reset kernel)
+    bool pure_step = false;               // 'gated': a one-step launch or the queued-reset kernel behind one — kernels that let
+                                          // their dependents start only after everything before THEM has completed
     MemRange rd[2], wr[6];                // caller buffers it reads (actions) / writes (obs, reward, done, cost, result, msg)
     int n_rd = 0, n_wr = 0;
 };
@@ -302,6 +305,7 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     h->concurrent_waves = getenv("NGW_NO_CONCURRENT_WAVES") == nullptr;
     h->rollout2 = getenv("NGW_NO_ROLLOUT2") == nullptr;
     h->alias = getenv("NGW_NO_ALIAS") == nullptr;
+    if (const char* rg = getenv("NGW_RESET_GRID")) { int v = atoi(rg); if (v >= 1 && v <= 4) h->reset_grid = v; }
     h->pdl_early = getenv("NGW_NO_PDL_EARLY") == nullptr;   // trigger right after the wait: C2 7.70 -> 7.60 us/step
     // streaming data (each tile is read once and its observations written once per step) should not linger in L2:
     // measured on C2 9.15 -> 8.82 us/step, C3 29.3 -> 28.0, C5 278 -> 274 (hinting the inventory store as well: 9.0)
@@ -408,6 +412,9 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     NGW_SMEM_ATTR4(step1_kernel, true, true); NGW_SMEM_ATTR4(step1_kernel, true, false);
     NGW_SMEM_ATTR4(step1_kernel, false, true);
 #undef NGW_SMEM_ATTR4
+    // the queued-reset kernel shares SMs with the next handle's step CTAs: both must want the same (maximal) shared-memory
+    // carve-out, or the SM would have to drain before it can be reconfigured
+    CK(cudaFuncSetAttribute(reset_list_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     NGW_SMEM_ATTR((step1_kernel<true, 0, true, true>)); NGW_SMEM_ATTR((step1_kernel<true, 1, true, true>));
     NGW_SMEM_ATTR((step1_kernel<true, 4, true, true>)); NGW_SMEM_ATTR((step1_kernel<true, 16, true, true>));
     NGW_SMEM_ATTR((step1w_kernel<0, 8>)); NGW_SMEM_ATTR((step1w_kernel<1, 8>)); NGW_SMEM_ATTR((step1w_kernel<4, 8>)); NGW_SMEM_ATTR((step1w_kernel<16, 8>));
@@ -601,6 +608,21 @@ static cudaError_t launch_rollout_nc(ngw_handle* h, StepParams p, cudaStream_t s
     return cudaLaunchKernelEx(&lc, rollout_kernel<false, NC>, args);
 }
 
+// caller buffers of a one-step launch (for the independence proof of this launch and of the next one)
+static StreamTail launch_tail(const StepParams& p) {
+    StreamTail me;
+    const long long n_env = p.env_end - p.env_begin;
+    auto add = [](MemRange* r, int& n, const void* ptr, size_t bytes) {
+        if (ptr != nullptr && bytes > 0) { r[n].lo = (uintptr_t)ptr; r[n].hi = (uintptr_t)ptr + bytes; n++; }
+    };
+    add(me.rd, me.n_rd, p.actions, (size_t)n_env * 4);
+    add(me.wr, me.n_wr, p.obs, (size_t)n_env * p.obs_row_bytes);
+    add(me.wr, me.n_wr, p.reward, (size_t)n_env * 4); add(me.wr, me.n_wr, p.cost, (size_t)n_env * 4);
+    add(me.wr, me.n_wr, p.done, (size_t)n_env); add(me.wr, me.n_wr, p.result, (size_t)n_env);
+    add(me.wr, me.n_wr, p.msg, (size_t)n_env * 2);
+    return me;
+}
+
 // one-step launches (ngw_step / ngw_step_host / ngw_observe): several tile groups per CTA
 template <int NC>
 static cudaError_t launch_step1_nc(ngw_handle* h, StepParams p, cudaStream_t s) {
@@ -651,23 +673,36 @@ static cudaError_t launch_step1_nc(ngw_handle* h, StepParams p, cudaStream_t s) 
     // launches write no state, but they are ordered like steps: they read it)
     // only for one-wave launches: with several waves the loads of later waves never wait anyway, and issuing them ahead
     // of the tile's zero-fill measured 4 % slower (C4 122 vs 127 us)
-    p.early_state = claim_stream(h, s, h->early_state && h->use_pdl && C > 1) >= 1 ? 1 : 0;
+    const StreamTail me = launch_tail(p);
+    const int mode = claim_stream(h, s, h->early_state && h->use_pdl, &me);
+    // independent of the predecessor (see claim_stream): no thread waits for it except the gate CTA (block 0)
+    p.concurrent = (mode == 2 && h->concurrent && h->concurrent_waves && p.actions != nullptr) ? 1 : 0;
+    p.early_state = (p.concurrent || (mode >= 1 && C > 1)) ? 1 : 0;
     p.pdl_early = h->pdl_early ? 1 : 0;
     const size_t smem = (size_t)p.off_groups + (size_t)C * p.group_bytes;
     args.p = p;
     for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3((unsigned)((tiles + C - 1) / C)); lc.blockDim = dim3(32 * G * C); lc.dynamicSmemBytes = smem;
+    lc.gridDim = dim3((unsigned)((tiles + C - 1) / C) + (p.concurrent ? 1u : 0u)); lc.blockDim = dim3(32 * G * C);
+    lc.dynamicSmemBytes = smem;
     lc.stream = s;
     cudaLaunchAttribute attr[1];
     pdl_attr(h, s, lc, attr);
+    cudaError_t e;
     if (C == 1) {
-        if (alias) return cudaLaunchKernelEx(&lc, (step1_kernel<true, NC, true, true>), args);
-        if (h->use_tma) return cudaLaunchKernelEx(&lc, step1_kernel<true, NC, true>, args);
-        return cudaLaunchKernelEx(&lc, step1_kernel<false, NC, true>, args);
+        if (alias) e = cudaLaunchKernelEx(&lc, (step1_kernel<true, NC, true, true>), args);
+        else if (h->use_tma) e = cudaLaunchKernelEx(&lc, step1_kernel<true, NC, true>, args);
+        else e = cudaLaunchKernelEx(&lc, step1_kernel<false, NC, true>, args);
+    } else {
+        e = cudaLaunchKernelEx(&lc, step1_kernel<true, NC, false>, args);
     }
-    return cudaLaunchKernelEx(&lc, step1_kernel<true, NC, false>, args);
+    if (e == cudaSuccess) {
+        note_launched(s, p.actions != nullptr && lc.numAttrs == 1);
+        h->concurrent_launches += p.concurrent;
+        h->last_step_concurrent = p.concurrent != 0;
+    }
+    return e;
 }
 
 // one-step launches in the warp-per-tile shape (step1w_kernel): returns cudaErrorNotSupported when the launch does not
@@ -703,22 +738,12 @@ static cudaError_t launch_step1w_nc(ngw_handle* h, StepParams p, cudaStream_t s)
     p.tiles_per_cta = C;
     p.n_tiles = (int)tiles;
     p.lidar_mode = h->lidar_mode;
-    // caller buffers of this launch (for the independence proof of the NEXT launch, and of this one)
-    StreamTail me;
-    const long long n_env = p.env_end - p.env_begin;
-    auto add = [](MemRange* r, int& n, const void* ptr, size_t bytes) {
-        if (ptr != nullptr && bytes > 0) { r[n].lo = (uintptr_t)ptr; r[n].hi = (uintptr_t)ptr + bytes; n++; }
-    };
-    add(me.rd, me.n_rd, p.actions, (size_t)n_env * 4);
-    add(me.wr, me.n_wr, p.obs, (size_t)n_env * p.obs_row_bytes);
-    add(me.wr, me.n_wr, p.reward, (size_t)n_env * 4); add(me.wr, me.n_wr, p.cost, (size_t)n_env * 4);
-    add(me.wr, me.n_wr, p.done, (size_t)n_env); add(me.wr, me.n_wr, p.result, (size_t)n_env);
-    add(me.wr, me.n_wr, p.msg, (size_t)n_env * 2);
+    const StreamTail me = launch_tail(p);
     const bool one_wave = tiles <= (long long)C * h->sm_count;
     const int mode = claim_stream(h, s, h->early_state && h->use_pdl, &me);
     p.early_state = mode >= 1 ? 1 : 0;
     // (one-wave launches overlap whole; with several waves the next launch fills the SMs as the last wave drains)
-    p.concurrent = (mode == 2 && h->concurrent && (one_wave || h->concurrent_waves) && p.actions != nullptr && !p.auto_reset) ? 1 : 0;
+    p.concurrent = (mode == 2 && h->concurrent && (one_wave || h->concurrent_waves) && p.actions != nullptr) ? 1 : 0;
     p.pdl_early = h->pdl_early ? 1 : 0;
     const size_t smem = (size_t)p.off_groups + (size_t)C * p.group_bytes;
     args.p = p;
@@ -733,8 +758,9 @@ static cudaError_t launch_step1w_nc(ngw_handle* h, StepParams p, cudaStream_t s)
     if (max_tail <= 8) e = cudaLaunchKernelEx(&lc, step1w_kernel<NC, 8>, args);
     else e = cudaLaunchKernelEx(&lc, step1w_kernel<NC, 16>, args);
     if (e == cudaSuccess) {
-        note_launched(s, p.actions != nullptr && !p.auto_reset && lc.numAttrs == 1);
+        note_launched(s, p.actions != nullptr && lc.numAttrs == 1);
         h->concurrent_launches += p.concurrent;
+        h->last_step_concurrent = p.concurrent != 0;
     }
     return e;
 }
@@ -811,9 +837,23 @@ static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
     if (p.actions != nullptr && p.auto_reset && !is_multi(p)) {     // regenerate the episodes the step kernel queued
         ResetParams rp = reset_params(h, nullptr, 2);
         rp.obs = p.obs;
-        reset_list_kernel<<<h->sm_count * 4, 32 * NGW_RESET_WARPS, 0, s>>>(rp);
+        // Grid: alone, four CTAs per SM regenerate the queue fastest (C5: ~2000 envs in 52 us).  When this step overlapped
+        // its predecessor — rotating handles inside a capture — the NEXT handle's step will overlap this kernel: then ONE
+        // CTA per SM (11 KB, 16 K registers) fits next to that step's full set of CTAs and the resets hide behind it.
+        const int rl_ctas = h->sm_count * (h->last_step_concurrent ? h->reset_grid : 4);
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof(lc));
+        lc.gridDim = dim3((unsigned)rl_ctas); lc.blockDim = dim3(32 * NGW_RESET_WARPS);
+        lc.dynamicSmemBytes = NGW_RESET_WARPS * reset_list_scratch_bytes(h->cells);
+        lc.stream = s;
+        // a PLAIN launch: it starts once the step has completed.  (Launched programmatically behind an overlapped step it
+        // could start under that step's tail, but that measured no faster — 250.2 vs 250.7 us on C5.)
+        CK(cudaLaunchKernelEx(&lc, reset_list_kernel, rp));
         h->launches++;
         CK(cudaGetLastError());
+        // a plain launch: it starts once the step has completed and lets the stream's next launch start right away
+        // (griddepcontrol.launch_dependents at its top) — the next handle's step may overlap it
+        note_launched(s, true);
     }
     return 0;
 }

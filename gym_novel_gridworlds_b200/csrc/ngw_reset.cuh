@@ -88,10 +88,26 @@ __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_kernel(const Reset
 // was computed).  The last CTA to finish empties the queue for the next step.
 // (Measured and rejected: a whole CTA of 4 warps per env, reset_env_team<4> — at 96 registers only 5 such CTAs fit an SM, the
 // ~2000 queued envs of a C5 step then take three rounds instead of one: 356 vs 315 us per step.)
+// Shared memory is sized for the batch's grid (dynamic: NGW_RESET_WARPS x reset_list_scratch_bytes(cells)), so that one
+// CTA of this kernel fits next to a full set of step CTAs when the next handle's step overlaps it (C5: 11 KB).
+__host__ __device__ inline int reset_list_scratch_bytes(int cells) {
+    return NGW_RESET_SCRATCH_WORDS * 4 + NGW_MAX_ITEMS * 4 + ((cells + 15) & ~15);
+}
+struct ResetScratchView { uint32_t* hist; int32_t* inv; int8_t* row; };
+
 __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_list_kernel(const ResetParams p) {
-    __shared__ ResetScratch scratch[NGW_RESET_WARPS];
+    extern __shared__ __align__(16) unsigned char rl_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    ResetScratch& sc = scratch[warp];
+    ResetScratchView sc;
+    {
+        unsigned char* base = rl_smem + warp * reset_list_scratch_bytes(p.cells);
+        sc.hist = reinterpret_cast<uint32_t*>(base);
+        sc.inv = reinterpret_cast<int32_t*>(base + NGW_RESET_SCRATCH_WORDS * 4);
+        sc.row = reinterpret_cast<int8_t*>(base + NGW_RESET_SCRATCH_WORDS * 4 + NGW_MAX_ITEMS * 4);
+    }
+    // This kernel is launched plainly, so everything before it has completed; the stream's next launch (another handle's
+    // step, if it can prove its independence) may start now and overlap the resets.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int count = *reinterpret_cast<volatile int32_t*>(p.reset_count);
     for (int i = blockIdx.x * NGW_RESET_WARPS + warp; i < count; i += gridDim.x * NGW_RESET_WARPS) {
         const long long e = p.reset_list[i];
@@ -131,7 +147,9 @@ __global__ void __launch_bounds__(32 * NGW_RESET_WARPS) reset_list_kernel(const 
         if (k_obs < dc.c.n_reset_ops)
             err |= reset_env_warp(&dc.c, sc.row, sc.inv, p.ms, p.inv_stride, p.seed, gid, ep, false, k_obs,
                                   NGW_MAX_RESET_OPS, sc.hist, r, c, f, sel, p.key_mask);
-        rows_from_smem(sc, m, inv, p.cells, p.inv_stride, lane);
+        __syncwarp();
+        for (int k = lane; k < p.cells; k += 32) m[k] = sc.row[k];
+        for (int k = lane; k < p.inv_stride; k += 32) inv[k] = sc.inv[k];
         if (lane == 0) {
             p.episode[e] = ep;
             p.pose[e] = make_uchar4((unsigned char)r, (unsigned char)c, (unsigned char)f, (unsigned char)sel);

@@ -500,7 +500,14 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
     const int G = 1 << p.g_shift;
     const int grp = wid >> p.g_shift, g = wid & (G - 1);
     const int gt = threadIdx.x & (32 * G - 1);                        // thread index inside the tile group
-    const int tile = (int)blockIdx.x * p.tiles_per_cta + grp;
+    // concurrent mode (see step1w_kernel): block 0 is the GATE — it waits for the preceding grid and only then lets the
+    // next launch start; the tile CTAs never wait
+    if (p.concurrent && blockIdx.x == 0) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        return;
+    }
+    const int tile = ((int)blockIdx.x - p.concurrent) * p.tiles_per_cta + grp;
     const bool active = tile < p.n_tiles;
     const long long e0 = p.env_begin + (long long)tile * 32;
     const long long e = e0 + lane;
@@ -573,7 +580,7 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
     const bool early = p.early_state && active && !(p.dbg_skip & 64);
     if (early) {
         issue_loads();
-        if (g < n_cls) ps = p.pose[e];
+        if (g < n_cls) ps = __ldcg(&p.pose[e]);
     }
     if (p.obs != nullptr) {                                           // the group zeroes its observation tile while the loads fly
         uint32_t a = smem_u32(sobs) + (uint32_t)gt * 16u + (kAlias ? in_bytes : 0u);   // (alias: only the part beyond the rows)
@@ -586,19 +593,21 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
         }
         for (; a < end; a += st) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
     }
-    asm volatile("griddepcontrol.wait;" ::: "memory");                // previous kernel of the stream done + visible
-    if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!p.concurrent) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");            // previous kernel of the stream done + visible
+        if (p.pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     if (!active || (p.dbg_skip & 64)) { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); return; }
     if (!early) issue_loads();
 
     // ---- while the copies fly: per-lane scalars
-    const int cfg_i = (NC == 1) ? 0 : (int)p.cfg_id[e];
+    const int cfg_i = (NC == 1) ? 0 : (int)__ldcg(&p.cfg_id[e]);
     const DevConfig& dc = (NC == 1) ? args.cfg[0] : (NC > 1 ? args.cfg[cfg_i] : p.dcfgs[cfg_i]);
     const ngw_config& cfg = dc.c;
     int action = 0;
     if (g < n_cls) {
-        if (!early) ps = p.pose[e];
-        if (stepping && valid) action = p.actions[e];
+        if (!early) ps = __ldcg(&p.pose[e]);
+        if (stepping && valid) action = __ldcg(&p.actions[e]);
     }
 
     if (kTma) mbar_wait(bar, 0);
@@ -631,13 +640,13 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
                 bits = 1u << 21;
                 if (a.op == NGW_OP_INVALID) {                         // wrappers.py:76 / pogostick_v1_env.py:236 would raise
                     bits |= 1u << 20;
-                    p.err[e] |= NGW_ERR_INVALID_ACTION;
+                    atomicOr(&p.err[e], NGW_ERR_INVALID_ACTION);
                 } else {
                     if (!(p.dbg_skip & 1)) step_env(env, cfg, a, o);
                     if (o.goal) bits |= 1u << 18;
                     int finished = o.done;
                     if (p.max_episode_steps > 0) {
-                        int len = p.ep_len[e] + 1;
+                        int len = __ldcg(&p.ep_len[e]) + 1;
                         if (len >= p.max_episode_steps) { finished = 1; o.done = 1; }   // harness truncation knob
                         p.ep_len[e] = finished && p.auto_reset ? 0 : len;
                     }
@@ -798,7 +807,7 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
                     atomicAdd(&scta[2], r_tot);
                     atomicAdd(reinterpret_cast<float*>(&scta[3]), c_tot);
                     __threadfence_block();
-                    const int n_groups = min(p.tiles_per_cta, p.n_tiles - (int)blockIdx.x * p.tiles_per_cta);
+                    const int n_groups = min(p.tiles_per_cta, p.n_tiles - ((int)blockIdx.x - p.concurrent) * p.tiles_per_cta);
                     flush = atomicAdd(&scta[4], 1) == n_groups - 1;
                     if (flush) {
                         __threadfence_block();

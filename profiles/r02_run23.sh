@@ -1,0 +1,3 @@
+# round 2, run 23: queued-reset kernel sized to hide behind the next handle's step (C5)
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_reset.py -m gpu -q -x -k "overlapped or auto_reset or compact_u8 or reset" 2>&1 | tail -4
+python profiles/sweep.py C5 "" "NGW_RESET_GRID4=1" "NGW_NO_CONCURRENT=1" 2>&1 | cut -c1-160 | tee gpurun_out/r02_sweep23.jsonl

@@ -560,6 +560,50 @@ def test_warp_per_tile_shape(wshape, ctiles, extra):
             del os.environ[extra]
 
 
+@pytest.mark.parametrize('case', ['C2', 'ms40', 'bow12_16beams'])
+def test_overlapped_steps_with_queued_resets_in_a_graph(case):
+    """Inside one captured graph, handle B's step is independent of handle A's step AND of A's queued-reset kernel behind
+    it: the library proves adjacency and overlaps them (gate warp / gate CTA keep stream order).  Rotating handles with
+    auto-reset and truncation, replayed several times, against handles stepped one launch at a time."""
+    if case == 'C2':
+        cc, n = _compiled(C2_DESC), 32 * 90 + 5                        # warp-per-tile kernel
+    elif case == 'ms40':
+        cc, n = _compiled(golden_util.get('pogo_ms40_additem_hard')['meta']), 32 * 20 + 3   # tile-group kernel, alias plan
+    else:
+        cc, n = _compiled({'env': scenarios.BOW, 'map_size': 12, 'chain': [['lidar', 16]]}), 500   # generic lidar, no alias
+    rng = np.random.RandomState(12)
+    hs = [BatchHandle([cc], n, seed=70 + k) for k in range(3)]
+    ref = [BatchHandle([cc], n, seed=70 + k) for k in range(3)]
+    for x in hs + ref:
+        x.reset()
+    torch.cuda.synchronize()
+    acts = [torch.from_numpy(rng.randint(0, cc.c.n_actions, size=n).astype(np.int32)).cuda() for _ in range(12)]
+    stream = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    keep = []
+    c0 = sum(x.concurrent_launch_count() for x in hs)
+    with torch.cuda.stream(stream):
+        with torch.cuda.graph(graph, stream=stream):
+            for t in range(12):
+                keep.append(hs[t % 3].step(acts[t], auto_reset=True, max_episode_steps=3))
+    n_conc = sum(x.concurrent_launch_count() for x in hs) - c0
+    assert n_conc == 11, n_conc
+    for rep in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        for t in range(12):
+            want = ref[t % 3].step(acts[t], auto_reset=True, max_episode_steps=3)
+            torch.cuda.synchronize()
+            if t >= 9:
+                for x, y in zip(keep[t], want):
+                    assert torch.equal(x, y), "replay %d launch %d" % (rep, t)
+        for a, b in zip(hs, ref):
+            assert torch.equal(a.map, b.map) and torch.equal(a.inventory, b.inventory) and torch.equal(a.pose, b.pose)
+            assert torch.equal(a.episode, b.episode) and torch.equal(a.ep_len, b.ep_len)
+            np.testing.assert_allclose(a.stats(reset=False).cpu().numpy(), b.stats(reset=False).cpu().numpy(), rtol=1e-9)
+    assert int(hs[0].episode.min().item()) >= 4
+
+
 @pytest.mark.parametrize('knob', ['NGW_NO_LINE_LIDAR', 'NGW_NO_FAST_LIDAR'])
 def test_older_lidar_paths_still_match(knob):
     os.environ[knob] = '1'

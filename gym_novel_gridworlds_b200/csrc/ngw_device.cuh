@@ -56,6 +56,32 @@ struct Philox {
     }
 };
 
+// On-device uniform random policy of the rollout kernels: one Philox block (counter = step / 4, stream 0xFFF) yields the
+// draws of four consecutive steps; a draw becomes an action id in [0, n) by multiply-shift with Lemire's rejection (exact
+// uniformity; a rejection — probability n / 2^32 — continues on stream 0xFFE of that step).
+struct RandomPolicy {
+    uint32_t w[4];
+    __device__ __forceinline__ int draw(uint64_t seed, uint64_t gid, uint32_t t, uint32_t n) {
+        if ((t & 3u) == 0u || t == first) {
+            Philox pr;
+            pr.init(seed, gid, t >> 2, 0xFFF);
+            pr.refill();
+            w[0] = pr.buf[0]; w[1] = pr.buf[1]; w[2] = pr.buf[2]; w[3] = pr.buf[3];
+        }
+        const uint32_t k = t & 3u;
+        uint32_t x = k == 0 ? w[0] : k == 1 ? w[1] : k == 2 ? w[2] : w[3];
+        uint64_t m = (uint64_t)x * n;
+        if ((uint32_t)m < n) {                                        // rare: exact rejection threshold
+            const uint32_t thr = (0u - n) % n;
+            Philox pr;
+            pr.init(seed, gid, t, 0xFFE);
+            while ((uint32_t)m < thr) { x = pr.next(); m = (uint64_t)x * n; }
+        }
+        return (int)(m >> 32);
+    }
+    uint32_t first;                                                   // first step of this launch (its block must be generated)
+};
+
 // ------------------------------------------------------------------ per-env view
 struct EnvRow {
     int8_t* m;                            // staged grid row [cells]
@@ -411,6 +437,8 @@ struct RegSink {
         sh = u8 ? 0 : 2;
 #pragma unroll
         for (int a = 0; a < 8; a++) hit[a] = 0u;
+#pragma unroll
+        for (int i = 0; i < NT; i++) tail[i] = 0;
     }
     __device__ __forceinline__ void put_beam(int a, bool on, int idx, int v) {   // every position is written exactly once
         const uint32_t packed = on ? (((uint32_t)idx << sh) << 8) | (uint32_t)v : 0u;
@@ -422,18 +450,22 @@ struct RegSink {
         for (int j = 0; j < NT; j++) if (j == i) tail[j] = v;
     }
     __device__ __forceinline__ void put(int, int) {}                 // (generic LUT walk: never taken with this sink)
-    // row: the lane's (zeroed) observation row in shared memory
-    __device__ __forceinline__ void flush(unsigned char* row, int tail_off, int n_tail) const {
+    // row: the lane's (zeroed) observation row, dump: a scratch word, both as shared-memory addresses.  Branch-free: a
+    // beam that saw nothing and a tail slot beyond n_tail store to the dump word instead.
+    __device__ __forceinline__ void flush(uint32_t row, uint32_t dump, int tail_off, int n_tail) const {
         if (sh) {
 #pragma unroll
-            for (int a = 0; a < 8; a++) if (hit[a]) *reinterpret_cast<uint32_t*>(row + (hit[a] >> 8)) = hit[a] & 0xFFu;
+            for (int a = 0; a < 8; a++)
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(hit[a] ? row + (hit[a] >> 8) : dump), "r"(hit[a] & 0xFFu) : "memory");
         } else {
 #pragma unroll
-            for (int a = 0; a < 8; a++) if (hit[a]) row[hit[a] >> 8] = (unsigned char)hit[a];
+            for (int a = 0; a < 8; a++)
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(hit[a] ? row + (hit[a] >> 8) : dump), "r"(hit[a]) : "memory");
         }
-        int32_t* t = reinterpret_cast<int32_t*>(row + tail_off);
+        const uint32_t t = row + (uint32_t)tail_off;
 #pragma unroll
-        for (int i = 0; i < NT; i++) if (i < n_tail) t[i] = tail[i];
+        for (int i = 0; i < NT; i++)
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(i < n_tail ? t + 4u * i : dump), "r"(tail[i]) : "memory");
     }
 };
 

@@ -335,6 +335,8 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ St
         // the sink needs the line-gather lidar (lidar_observe would take the same branch); otherwise the observation row
         // is materialised and scanned
         const bool use_sink = closed_loop && dc.lidar.lines && luts.slot != nullptr && (p.ms <= 32 || !dc.lidar.fast);
+        RandomPolicy rpol;
+        rpol.first = 0u; rpol.w[0] = rpol.w[1] = rpol.w[2] = rpol.w[3] = 0u;
         for (int t = 0; t < p.n_steps; t++) {
             int next_action = 0;                                      // prefetch the next step's action behind this step
             if (given_actions && t + 1 < p.n_steps && valid) next_action = p.actions[(t + 1) * p.act_stride + e];
@@ -362,9 +364,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ St
                     action = sink.argmax(n_valid);
                 }
             } else if (p.random_policy && valid) {                    // uniform over the config's action ids
-                Philox pr;
-                pr.init(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, 0xFFF);
-                action = (int)pr.below((uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
+                action = rpol.draw(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, (uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
             }
             if (p.actions_out != nullptr && valid) p.actions_out[t * p.act_stride + e] = action;
             o.reward = 0; o.done = 0; o.result = 0; o.cost = 0.0f; o.msg = 0; o.goal = 0;
@@ -714,7 +714,8 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
             group_sync<kOne>(grp, G);
             if (look) {
                 const int n_lidar = cfg.n_lidar_items * cfg.n_beams;
-                sink.flush(sobs + lane * p.obs_srow, p.obs_u8 ? ((n_lidar + 3) & ~3) : 4 * n_lidar, g == G - 1 ? cfg.n_inv_obs : 0);
+                sink.flush(smem_u32(sobs) + (uint32_t)(lane * p.obs_srow), smem_u32(gbase + 16),
+                       p.obs_u8 ? ((n_lidar + 3) & ~3) : 4 * n_lidar, g == G - 1 ? cfg.n_inv_obs : 0);
             }
         }
     } else
@@ -1033,7 +1034,8 @@ __global__ void __launch_bounds__(512, 2) step1w_kernel(const __grid_constant__ 
         __syncwarp();
         if (look) {
             const int n_lidar = cfg.n_lidar_items * cfg.n_beams;
-            sink.flush(sobs + lane * p.obs_srow, p.obs_u8 ? ((n_lidar + 3) & ~3) : 4 * n_lidar, cfg.n_inv_obs);
+            sink.flush(region_a + (uint32_t)(lane * p.obs_srow), smem_u32(gbase + 16),
+                       p.obs_u8 ? ((n_lidar + 3) & ~3) : 4 * n_lidar, cfg.n_inv_obs);
         }
         if (full_tile && !p.plain_store) {
             fence_async_smem();
@@ -1287,6 +1289,8 @@ __global__ void __launch_bounds__(64, 14) rollout2_kernel(const __grid_constant_
     float cost_sum = 0.0f;
     int reward_sum = 0, n_done = 0, n_succ = 0, n_reset = 0, n_invalid = 0;
     const int n_lidar = cfg.n_lidar_items * cfg.n_beams;
+    RandomPolicy rpol;
+    rpol.first = 0u; rpol.w[0] = rpol.w[1] = rpol.w[2] = rpol.w[3] = 0u;
     for (int t = 0; t < p.n_steps; t++) {
         int next_action = 0;
         if (given_actions && t + 1 < p.n_steps && valid && low) next_action = p.actions[(t + 1) * p.act_stride + e];
@@ -1316,9 +1320,7 @@ __global__ void __launch_bounds__(64, 14) rollout2_kernel(const __grid_constant_
             for (int a = 1; a < 4 * A4; a++) if (a < n_valid && acc[a] > best_v) { best_v = acc[a]; best = a; }
             action = best;
         } else if (p.random_policy && valid && low) {
-            Philox pr;
-            pr.init(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, 0xFFF);
-            action = (int)pr.below((uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
+            action = rpol.draw(p.policy_seed, (uint64_t)(p.first_gid + e), (uint32_t)t, (uint32_t)(cfg.n_actions > 0 ? cfg.n_actions : 1));
         }
         int did_reset = 0;
         __syncwarp();                                                 // the high lanes have read the rows

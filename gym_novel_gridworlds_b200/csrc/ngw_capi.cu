@@ -730,8 +730,13 @@ static cudaError_t launch_step1w_nc(ngw_handle* h, StepParams p, cudaStream_t s)
     if (C <= 0) {
         // one wave: one CTA per SM and launch.  Several waves: CTAs of four tiles (small CTAs retire independently, which
         // staggers the phases of neighbouring tiles; C4 123 / 116 / 116 / 113 us with 1 / 2 / 3 / 4 tiles, C3 flat)
-        if (tiles > (long long)c_cap * h->sm_count) C = h->wshape == 3 ? c_cap : 4;
-        else C = (int)((tiles + h->sm_count - 1) / h->sm_count);
+        // (with overlapped launches, r02_sweep29..31: C2 5.68 us with 7 tiles per CTA — two CTAs per SM and launch, of
+        // which THREE fit an SM: one and a half launches resident — vs 5.89 with 14 tiles per CTA, and 5.89 again when a
+        // slimmer header lets four 7-tile CTAs in; C3 19.5 / 20.3 / 20.4 with 8 / 4 / 6, C4 98.6 / 99.9 / 99.7; odd counts
+        // leave partial CTAs)
+        if (tiles > (long long)c_cap * h->sm_count) C = h->wshape == 3 ? c_cap : 8;
+        else C = (int)((tiles + 2 * h->sm_count - 1) / (2 * h->sm_count));
+        if (C < 1) C = 1;
     }
     if (C > c_cap) C = c_cap;
     if (C > tiles) C = (int)tiles;
@@ -739,7 +744,7 @@ static cudaError_t launch_step1w_nc(ngw_handle* h, StepParams p, cudaStream_t s)
     p.n_tiles = (int)tiles;
     p.lidar_mode = h->lidar_mode;
     const StreamTail me = launch_tail(p);
-    const bool one_wave = tiles <= (long long)C * h->sm_count;
+    const bool one_wave = tiles <= (long long)c_cap * h->sm_count;
     const int mode = claim_stream(h, s, h->early_state && h->use_pdl, &me);
     p.early_state = mode >= 1 ? 1 : 0;
     // (one-wave launches overlap whole; with several waves the next launch fills the SMs as the last wave drains)

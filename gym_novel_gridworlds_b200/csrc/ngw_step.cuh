@@ -854,7 +854,7 @@ __global__ void __launch_bounds__(512) step1_kernel(const __grid_constant__ Step
 //   lidar   line gather into a RegSink: hits and inventory tail stay in registers
 //   store 2 once the inventory store has read its rows: zero the region, write the <= 8 hits + tail per row, TMA bulk store
 //   outputs pose / reward / step_cost / done / result straight from registers (lane = env: full lines), statistics
-#define NGW_WTILE_HDR 128
+#define NGW_WTILE_HDR 128            // mbarrier (8) | dump word at +16
 #define NGW_WCTA_HDR 384            // [0] tiles done | per-warp statistics partials at +64: int4[16]
 
 __device__ __forceinline__ void zero_span(uint32_t a, uint32_t end) {      // 16 bytes per lane, 512 per warp and pass

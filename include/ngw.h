@@ -290,7 +290,8 @@ int ngw_step_host(ngw_handle* h, const int32_t* actions, void* obs, float* rewar
 
 /* K-step rollout in ONE launch: every tile stays in shared memory for n_steps consecutive steps.
  * actions: DEVICE int32[n_steps][n_envs], or NULL = uniform random policy drawn on the device with Philox
- * (policy_seed, global env id, step index) — the tests/random_action.py loop without the host.  reward_sum / cost_sum
+ * (policy_seed, global env id, step index / 4: one block serves four steps; exact uniformity by multiply-shift with
+ * rejection) — the tests/random_action.py loop without the host.  reward_sum / cost_sum
  * accumulate over the steps, done_count counts finished episodes, last_done / last_result are the final step's, obs is
  * the observation after the last step; actions_out (DEVICE int32[n_steps][n_envs], NULL = skip) records the actions. */
 int ngw_rollout(ngw_handle* h, const int32_t* actions, int32_t n_steps, uint64_t policy_seed, void* obs,

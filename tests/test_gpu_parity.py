@@ -560,20 +560,23 @@ def test_warp_per_tile_shape(wshape, ctiles, extra):
             del os.environ[extra]
 
 
-@pytest.mark.parametrize('case', ['C2', 'ms40', 'bow12_16beams'])
+@pytest.mark.parametrize('case', ['C2', 'ms40', 'bow12_16beams', 'C2-two', 'ms40-two', 'C3-waves-two'])
 def test_overlapped_steps_with_queued_resets_in_a_graph(case):
     """Inside one captured graph, handle B's step is independent of handle A's step AND of A's queued-reset kernel behind
     it: the library proves adjacency and overlaps them (gate warp / gate CTA keep stream order).  Rotating handles with
     auto-reset and truncation, replayed several times, against handles stepped one launch at a time."""
-    if case == 'C2':
-        cc, n = _compiled(C2_DESC), 32 * 90 + 5                        # warp-per-tile kernel
-    elif case == 'ms40':
+    H = 2 if case.endswith('-two') else 3      # two handles: launch N + 2 steps the handle of launch N again
+    if case.startswith('C2'):
+        cc, n = _compiled(C2_DESC), 32 * 90 + 5                        # warp-per-tile kernel, one wave
+    elif case.startswith('C3'):
+        cc, n = _compiled(golden_util.get('bow_C3_axe_medium_fence_hard')['meta']), 32 * 148 * 28 + 17   # several waves
+    elif case.startswith('ms40'):
         cc, n = _compiled(golden_util.get('pogo_ms40_additem_hard')['meta']), 32 * 20 + 3   # tile-group kernel, alias plan
     else:
         cc, n = _compiled({'env': scenarios.BOW, 'map_size': 12, 'chain': [['lidar', 16]]}), 500   # generic lidar, no alias
     rng = np.random.RandomState(12)
-    hs = [BatchHandle([cc], n, seed=70 + k) for k in range(3)]
-    ref = [BatchHandle([cc], n, seed=70 + k) for k in range(3)]
+    hs = [BatchHandle([cc], n, seed=70 + k) for k in range(H)]
+    ref = [BatchHandle([cc], n, seed=70 + k) for k in range(H)]
     for x in hs + ref:
         x.reset()
     torch.cuda.synchronize()
@@ -585,16 +588,16 @@ def test_overlapped_steps_with_queued_resets_in_a_graph(case):
     with torch.cuda.stream(stream):
         with torch.cuda.graph(graph, stream=stream):
             for t in range(12):
-                keep.append(hs[t % 3].step(acts[t], auto_reset=True, max_episode_steps=3))
+                keep.append(hs[t % H].step(acts[t], auto_reset=True, max_episode_steps=3))
     n_conc = sum(x.concurrent_launch_count() for x in hs) - c0
     assert n_conc == 11, n_conc
     for rep in range(3):
         graph.replay()
         torch.cuda.synchronize()
         for t in range(12):
-            want = ref[t % 3].step(acts[t], auto_reset=True, max_episode_steps=3)
+            want = ref[t % H].step(acts[t], auto_reset=True, max_episode_steps=3)
             torch.cuda.synchronize()
-            if t >= 9:
+            if t >= 12 - H:
                 for x, y in zip(keep[t], want):
                     assert torch.equal(x, y), "replay %d launch %d" % (rep, t)
         for a, b in zip(hs, ref):

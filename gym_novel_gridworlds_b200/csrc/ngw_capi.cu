@@ -726,23 +726,6 @@ static cudaError_t launch_step1w_nc(ngw_handle* h, StepParams p, cudaStream_t s)
     int c_cap = (int)((115712 - p.off_groups) / p.group_bytes);
     if (c_cap > 15) c_cap = 15;                     // 15 tile warps + the gate warp = 512 threads
     if (c_cap < 1) return cudaErrorNotSupported;
-    int C = h->tiles_per_cta;
-    if (C <= 0) {
-        // one wave: one CTA per SM and launch.  Several waves: CTAs of four tiles (small CTAs retire independently, which
-        // staggers the phases of neighbouring tiles; C4 123 / 116 / 116 / 113 us with 1 / 2 / 3 / 4 tiles, C3 flat)
-        // (with overlapped launches, r02_sweep29..31: C2 5.68 us with 7 tiles per CTA — two CTAs per SM and launch, of
-        // which THREE fit an SM: one and a half launches resident — vs 5.89 with 14 tiles per CTA, and 5.89 again when a
-        // slimmer header lets four 7-tile CTAs in; C3 19.5 / 20.3 / 20.4 with 8 / 4 / 6, C4 98.6 / 99.9 / 99.7; odd counts
-        // leave partial CTAs)
-        if (tiles > (long long)c_cap * h->sm_count) C = h->wshape == 3 ? c_cap : 8;
-        else C = (int)((tiles + 2 * h->sm_count - 1) / (2 * h->sm_count));
-        if (C < 1) C = 1;
-    }
-    if (C > c_cap) C = c_cap;
-    if (C > tiles) C = (int)tiles;
-    p.tiles_per_cta = C;
-    p.n_tiles = (int)tiles;
-    p.lidar_mode = h->lidar_mode;
     const StreamTail me = launch_tail(p);
     const bool one_wave = tiles <= (long long)c_cap * h->sm_count;
     const int mode = claim_stream(h, s, h->early_state && h->use_pdl, &me);
@@ -750,6 +733,23 @@ static cudaError_t launch_step1w_nc(ngw_handle* h, StepParams p, cudaStream_t s)
     // (one-wave launches overlap whole; with several waves the next launch fills the SMs as the last wave drains)
     p.concurrent = (mode == 2 && h->concurrent && (one_wave || h->concurrent_waves) && p.actions != nullptr) ? 1 : 0;
     p.pdl_early = h->pdl_early ? 1 : 0;
+    int C = h->tiles_per_cta;
+    if (C <= 0) {
+        // Tiles per CTA (r02_sweep16, 29..31).  One wave, waiting for the predecessor: one CTA per SM (C2 7.3 us; two
+        // 7-tile CTAs: 8.5).  One wave, overlapped: two CTAs per SM and launch, of which THREE fit an SM — one and a half
+        // launches resident: C2 5.68 us vs 5.89 with 14 tiles per CTA, and 5.89 again when a slimmer header lets four
+        // 7-tile CTAs in.  Several waves: 8 (C3 19.5 / 20.3 / 20.4 us with 8 / 4 / 6, C4 98.6 / 99.9 / 99.7; odd counts
+        // leave partial CTAs).
+        if (!one_wave) C = h->wshape == 3 ? c_cap : 8;
+        else if (p.concurrent) C = (int)((tiles + 2 * h->sm_count - 1) / (2 * h->sm_count));
+        else C = (int)((tiles + h->sm_count - 1) / h->sm_count);
+        if (C < 1) C = 1;
+    }
+    if (C > c_cap) C = c_cap;
+    if (C > tiles) C = (int)tiles;
+    p.tiles_per_cta = C;
+    p.n_tiles = (int)tiles;
+    p.lidar_mode = h->lidar_mode;
     const size_t smem = (size_t)p.off_groups + (size_t)C * p.group_bytes;
     args.p = p;
     for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];

@@ -545,7 +545,7 @@ def test_warp_per_tile_shape(wshape, ctiles, extra):
                             assert torch.equal(x, y), "graph replay %d launch %d (%s)" % (rep, t, fmt)
                 for a, b in zip(hs, ref):
                     assert torch.equal(a.map, b.map) and torch.equal(a.inventory, b.inventory) and torch.equal(a.pose, b.pose)
-                    np.testing.assert_allclose(a.stats(reset=False).cpu().numpy(), b.stats(reset=False).cpu().numpy(), rtol=1e-9)
+                    np.testing.assert_allclose(a.stats(reset=False).cpu().numpy(), b.stats(reset=False).cpu().numpy(), rtol=1e-6)   # cost sums: float partials per CTA, the CTA shape depends on the launch mode
             # a handle stepped twice in a row, or buffers shared between neighbours, are never overlapped
             c0 = hs[0].concurrent_launch_count() + hs[1].concurrent_launch_count()
             g2 = torch.cuda.CUDAGraph()
@@ -603,7 +603,7 @@ def test_overlapped_steps_with_queued_resets_in_a_graph(case):
         for a, b in zip(hs, ref):
             assert torch.equal(a.map, b.map) and torch.equal(a.inventory, b.inventory) and torch.equal(a.pose, b.pose)
             assert torch.equal(a.episode, b.episode) and torch.equal(a.ep_len, b.ep_len)
-            np.testing.assert_allclose(a.stats(reset=False).cpu().numpy(), b.stats(reset=False).cpu().numpy(), rtol=1e-9)
+            np.testing.assert_allclose(a.stats(reset=False).cpu().numpy(), b.stats(reset=False).cpu().numpy(), rtol=1e-6)   # cost sums: float partials per CTA, the CTA shape depends on the launch mode
     assert int(hs[0].episode.min().item()) >= 4
 
 

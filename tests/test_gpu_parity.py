@@ -711,6 +711,76 @@ def test_closed_loop_rollout_final_observation_is_clean():
         assert np.array_equal(out[0].cpu().numpy()[:, :cc.obs_dim], after), "T=%d" % T
 
 
+def _c4_descs():
+    return [dict(C2_DESC, chain=[['limit', scenarios.C2_SET + ex], ['lidar', 8], nov]) for ex, nov in (
+        (['Chop'], ['novelty', 'addchop', 'hard', '', '']), (['Jump'], ['novelty', 'addjump', 'hard', '', '']),
+        ([], ['novelty', 'additem', 'medium', 'spring', '']), ([], ['novelty', 'remapaction', 'hard', '', '']))]
+
+
+@pytest.mark.parametrize('case', ['pogo_ms23', 'bow_ms13', 'c4_mixed', 'c3_layers', 'pogo_ms40', 'bow12_16beams'])
+@pytest.mark.parametrize('mode', ['given', 'given+autoreset', 'policy', 'random'])
+def test_rollout_kernels_equal_repeated_steps_on_other_shapes(case, mode):
+    """The K-step rollout kernels (lane-pair kernel on grids up to 32x32 incl. its generic-size lidar, mixed configs through
+    the global config table, layered novelties; the one-warp-per-tile kernel on 40x40 grids and 16 beams) against the same
+    steps issued one launch at a time: states, sums, final observation, episode counters; closed loop: every action is the
+    argmax of the integer policy on the twin's observation; auto-reset with truncation regenerates the same episodes."""
+    cfg_id = None
+    if case == 'pogo_ms23':
+        compiled, n = [_compiled({'env': scenarios.POGO, 'map_size': 23, 'chain': [['limit', scenarios.C2_SET], ['lidar', 8]]})], 32 * 9 + 7
+    elif case == 'bow_ms13':
+        compiled, n = [_compiled(golden_util.get('bow_ms13_lidar')['meta'])], 32 * 11 + 1
+    elif case == 'c4_mixed':
+        compiled, n = [_compiled(d) for d in _c4_descs()], 32 * 14 + 19
+        cfg_id = (np.arange(n) % 4).astype(np.int32)
+    elif case == 'c3_layers':
+        compiled, n = [_compiled(golden_util.get('bow_C3_axe_medium_fence_hard')['meta'])], 32 * 8 + 3
+    elif case == 'pogo_ms40':
+        compiled, n = [_compiled(golden_util.get('pogo_ms40_additem_hard')['meta'])], 32 * 3 + 5
+    else:
+        compiled, n = [_compiled({'env': scenarios.BOW, 'map_size': 12, 'chain': [['lidar', 16]]})], 200
+    T = 24
+    kw = dict(auto_reset=True, max_episode_steps=7) if mode == 'given+autoreset' else {}
+    h1 = BatchHandle(compiled, n, seed=21, cfg_id=cfg_id)             # one launch per step
+    h2 = BatchHandle(compiled, n, seed=21, cfg_id=cfg_id)             # one launch for all T steps
+    h1.reset(); h2.reset()
+    n_act = torch.tensor([cc.c.n_actions for cc in compiled], device='cuda')[h1.cfg_id.long()]
+    A = int(n_act.max().item())
+    rng = np.random.RandomState(17)
+    if mode == 'policy':
+        if A > 16:
+            pytest.skip("the device policy scores at most 16 actions")
+        W = torch.from_numpy(rng.randint(-9, 10, size=(h1.obs_dim, A)).astype(np.int32)).cuda()
+        b = torch.from_numpy(rng.randint(-30, 31, size=A).astype(np.int32)).cuda()
+        out = h2.rollout(T, policy=(W, b), record_actions=True, **kw)
+        acts = out[-1]
+    elif mode == 'random':
+        out = h2.rollout(T, None, policy_seed=5, record_actions=True, **kw)
+        acts = out[-1]
+        assert int(acts.min().item()) >= 0 and bool((acts < n_act[None, :]).all().item())
+    else:
+        acts = torch.from_numpy((rng.randint(0, 1 << 30, size=(T, n)) % n_act.cpu().numpy()[None, :]).astype(np.int32)).cuda()
+        out = h2.rollout(T, acts, **kw)
+    rew = torch.zeros(n, device='cuda'); cost = torch.zeros(n, dtype=torch.float64, device='cuda')
+    dones = torch.zeros(n, dtype=torch.int64, device='cuda')
+    obs = h1.observe().clone()
+    for t in range(T):
+        if mode == 'policy':                                          # the action the device must have taken: first maximum
+            score = obs[:, :h1.obs_dim].double() @ W.double() + b.double()[None, :]      # exact: small integers
+            score = torch.where(torch.arange(A, device='cuda')[None, :] < n_act[:, None], score, torch.full_like(score, -1e18))
+            assert torch.equal(torch.argmax(score, dim=1).to(torch.int32), acts[t]), "step %d" % t
+        o, r, d, c, res = h1.step(acts[t].contiguous(), **kw)
+        obs = o.clone()
+        rew += r; cost += c.double(); dones += d.long()
+    assert torch.equal(h1.map, h2.map) and torch.equal(h1.pose, h2.pose) and torch.equal(h1.inventory, h2.inventory)
+    assert torch.equal(h1.episode, h2.episode) and torch.equal(h1.ep_len, h2.ep_len)
+    assert torch.equal(out[0], o) and torch.equal(out[4], d) and torch.equal(out[5], res)
+    assert torch.equal(out[1], rew) and torch.equal(out[3].long(), dones)
+    np.testing.assert_allclose(out[2].cpu().numpy(), cost.cpu().numpy(), rtol=1e-5)
+    s1, s2 = h1.stats().cpu().numpy(), h2.stats().cpu().numpy()
+    assert np.array_equal(s1[[0, 1, 2, 3, 5, 6]], s2[[0, 1, 2, 3, 5, 6]])
+    np.testing.assert_allclose(s1[4], s2[4], rtol=1e-6)
+
+
 def _long_case(names):
     """(compiled configs, cfg ids, per-env trace rows) for one or several long-trace configs run as ONE batch; several
     configs are interleaved env i -> config i mod len(names), like BASELINE config C4."""

@@ -8,7 +8,7 @@ from . import opcodes as oc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libngw_b200.so')
-ABI_VERSION = 10
+ABI_VERSION = 11
 OBS_I32, OBS_U8 = 0, 1
 
 
@@ -83,6 +83,7 @@ EXPORTS = {
     'ngw_reset': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'ngw_step': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_int32, C.c_int32, C.c_void_p]),
+    'ngw_step_many': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'ngw_set_message_buffer': (C.c_int, [C.c_void_p, C.c_void_p]),
     'ngw_step_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int32, C.c_int32]),
@@ -102,6 +103,12 @@ EXPORTS = {
 }
 
 _lib = None
+
+
+class StepItem(C.Structure):
+    """struct ngw_step_item (include/ngw.h): one handle's pointers in an ngw_step_many call."""
+    _fields_ = [('h', C.c_void_p), ('actions', C.c_void_p), ('obs', C.c_void_p), ('reward', C.c_void_p),
+                ('done', C.c_void_p), ('step_cost', C.c_void_p), ('result', C.c_void_p)]
 
 
 def load_library(path=None):

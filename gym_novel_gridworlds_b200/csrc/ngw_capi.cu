@@ -85,6 +85,7 @@ struct StreamTail {                       // the latest library launch on a stre
     int n_rd = 0, n_wr = 0;
 };
 static std::unordered_map<cudaStream_t, StreamTail> g_last_writer;
+static thread_local bool g_adjacent_hint = false;   // ngw_step_many: this launch directly follows the library's previous launch on the stream
 
 static bool overlaps(const MemRange* a, int na, const MemRange* b, int nb) {
     for (int i = 0; i < na; i++)
@@ -113,7 +114,9 @@ static int claim_stream(ngw_handle* h, cudaStream_t s, bool want_early, const St
     if (want_early && it != g_last_writer.end() && it->second.h != nullptr && it->second.h != h && it->second.cap_id == cap_id) {
         mode = 1;
         const StreamTail& t = it->second;
-        if (mine != nullptr && cap_id != 0 && t.pure_step && n_deps == 1 && t.node != nullptr && deps[0] == t.node &&
+        const bool adjacent = (cap_id != 0 && n_deps == 1 && t.node != nullptr && deps[0] == t.node) ||   // proven by the capture
+                              (g_adjacent_hint && (cap_id == 0 || n_deps == 1));                        // issued back to back by one call
+        if (mine != nullptr && t.pure_step && adjacent &&
             !overlaps(mine->wr, mine->n_wr, t.wr, t.n_wr) && !overlaps(mine->wr, mine->n_wr, t.rd, t.n_rd) &&
             !overlaps(mine->rd, mine->n_rd, t.wr, t.n_wr))
             mode = 2;
@@ -874,6 +877,29 @@ int ngw_step(ngw_handle* h, const int32_t* actions, void* obs, float* reward, ui
     before_device_call(h, (cudaStream_t)stream);
     return launch_step(h, step_params(h, actions, obs, reward, done, step_cost, result, auto_reset, max_episode_steps,
                                       0, h->n), (cudaStream_t)stream);
+}
+
+int ngw_step_many(const ngw_step_item* items, int32_t n_items, int32_t auto_reset, int32_t max_episode_steps, void* stream) {
+    if (!items || n_items < 0) return fail("ngw_step_many: null items");
+    for (int i = 0; i < n_items; i++) {
+        const ngw_step_item& it = items[i];
+        if (!it.h) return fail("ngw_step_many: null handle");
+        if (!it.actions || !it.reward || !it.done || !it.step_cost || !it.result) return fail("ngw_step_many: null output/action pointer");
+        if (it.h->obs_dim > 0 && it.obs && ((uintptr_t)it.obs & 15)) return fail("ngw_step_many: obs must be 16-byte aligned");
+        if (it.h->device != items[0].h->device) return fail("ngw_step_many: all handles must live on one device");
+    }
+    if (n_items == 0) return 0;
+    CK(cudaSetDevice(items[0].h->device));
+    int rc = 0;
+    for (int i = 0; i < n_items && rc == 0; i++) {
+        const ngw_step_item& it = items[i];
+        before_device_call(it.h, (cudaStream_t)stream);
+        g_adjacent_hint = i > 0;                        // nothing was enqueued between item i - 1's launches and this one
+        rc = launch_step(it.h, step_params(it.h, it.actions, it.obs, it.reward, it.done, it.step_cost, it.result, auto_reset,
+                                           max_episode_steps, 0, it.h->n), (cudaStream_t)stream);
+        g_adjacent_hint = false;
+    }
+    return rc;
 }
 
 int ngw_rollout(ngw_handle* h, const int32_t* actions, int32_t n_steps, uint64_t policy_seed, void* obs,

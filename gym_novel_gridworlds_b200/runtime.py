@@ -314,6 +314,45 @@ class BatchHandle(object):
         return int(self.lib.ngw_concurrent_launch_count(self._h))
 
 
+class StepGroup(object):
+    """ngw_step_many over a fixed list of BatchHandles (env pools): one library call steps them all, in order, on the
+    current stream; the launches of different handles overlap (eager mode too).  The ngw_step_item array is built once."""
+
+    def __init__(self, handles):
+        import ctypes as C
+        assert len(handles) > 0
+        self.handles = list(handles)
+        self._arr = (capi.StepItem * len(self.handles))()
+        for i, h in enumerate(self.handles):
+            it = self._arr[i]
+            it.h = h._h
+            it.obs = _ptr(h.obs) if h.obs_dim else None
+            it.reward, it.done = _ptr(h.reward), _ptr(h.done)
+            it.step_cost, it.result = _ptr(h.step_cost), _ptr(h.result)
+        self._arr_p = C.cast(self._arr, C.c_void_p)
+        self._outs = [(h.obs, h.reward, h.done, h.step_cost, h.result) for h in self.handles]
+
+    def step(self, actions, auto_reset=False, max_episode_steps=0):
+        """`actions`: one contiguous int32 CUDA tensor per handle.  Returns the handles' output tuples (reused tensors)."""
+        hs = self.handles
+        assert len(actions) == len(hs)
+        keep = []
+        for i, a in enumerate(actions):
+            if a.dtype != torch.int32 or not a.is_cuda or not a.is_contiguous():
+                a = a.to(device=hs[i].device, dtype=torch.int32).contiguous()
+                keep.append(a)
+            self._arr[i].actions = a.data_ptr()
+        h0 = hs[0]
+        capi.check(h0.lib, h0.lib.ngw_step_many(self._arr_p, len(hs), int(bool(auto_reset)), int(max_episode_steps),
+                                                h0._stream()))
+        return self._outs
+
+
+def step_many(handles, actions, auto_reset=False, max_episode_steps=0):
+    """One-off form of StepGroup(handles).step(actions)."""
+    return StepGroup(handles).step(actions, auto_reset=auto_reset, max_episode_steps=max_episode_steps)
+
+
 _MSG_FIXED = {0: '', 1: 'Block in path', 3: 'Block tree_tap placed', 5: 'Item not found in inventory',
               6: 'No tree_log near tree_tap', 7: 'No tree_tap found', 8: 'No wool found',
               10: 'Need to be in front of crafting_table', 14: 'Cannot break due to fence restriction',

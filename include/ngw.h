@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NGW_ABI_VERSION 10
+#define NGW_ABI_VERSION 11
 
 #define NGW_MAX_ITEMS 24          /* reference asserts len(items) <= 20 (pogostick_v1_env.py:75,220) */
 #define NGW_MAX_ACTIONS 48
@@ -275,6 +275,22 @@ int ngw_reset(ngw_handle* h, const uint8_t* mask, void* obs, void* stream);
  * 16-byte aligned; obs may be NULL when obs_dim == 0. */
 int ngw_step(ngw_handle* h, const int32_t* actions, void* obs, float* reward, uint8_t* done,
              float* step_cost, uint8_t* result, int32_t auto_reset, int32_t max_episode_steps, void* stream);
+
+/* Several handles stepped by ONE call, in the order given, on one stream (the loop over env pools a driver would write
+ * around ngw_step, tests/random_action.py:51-55 per pool).  The library issues the launches back to back, so it knows
+ * that nothing sits between them: consecutive items that step different handles and share no caller buffer overlap
+ * exactly as consecutive ngw_step calls do inside a stream capture (see ngw_concurrent_launch_count) — in eager mode too.
+ * The caller must not enqueue work on `stream` from another thread during the call.  Pointers as in ngw_step. */
+typedef struct ngw_step_item {
+    ngw_handle* h;
+    const int32_t* actions;
+    void* obs;
+    float* reward;
+    uint8_t* done;
+    float* step_cost;
+    uint8_t* result;
+} ngw_step_item;
+int ngw_step_many(const ngw_step_item* items, int32_t n_items, int32_t auto_reset, int32_t max_episode_steps, void* stream);
 
 /* Optional: DEVICE uint16[n_envs] that every following ngw_step / ngw_rollout fills with the step's message code
  * (NULL switches it off again; off by default — the hot path then writes nothing). */

@@ -711,6 +711,39 @@ def test_closed_loop_rollout_final_observation_is_clean():
         assert np.array_equal(out[0].cpu().numpy()[:, :cc.obs_dim], after), "T=%d" % T
 
 
+def test_step_many_overlaps_handles_in_eager_mode():
+    """ngw_step_many: one call steps several handles back to back, so the library knows the launches are adjacent and
+    overlaps them without a stream capture; same results as one ngw_step per handle with a synchronise in between.  The
+    same handle twice in one call, or a shared output buffer, are never overlapped."""
+    from gym_novel_gridworlds_b200.runtime import step_many
+    for desc, n in ((C2_DESC, 32 * 120 + 9), (golden_util.get('pogo_ms40_additem_hard')['meta'], 32 * 12 + 1)):
+        cc = _compiled(desc)
+        hs = [BatchHandle([cc], n, seed=90 + k) for k in range(4)]
+        ref = [BatchHandle([cc], n, seed=90 + k) for k in range(4)]
+        for x in hs + ref:
+            x.reset()
+        torch.cuda.synchronize()
+        rng = np.random.RandomState(2)
+        c0 = sum(x.concurrent_launch_count() for x in hs)
+        for rnd in range(8):
+            acts = [torch.from_numpy(rng.randint(0, cc.c.n_actions, size=n).astype(np.int32)).cuda() for _ in range(4)]
+            outs = step_many(hs, acts, auto_reset=True, max_episode_steps=5)
+            torch.cuda.synchronize()
+            for k in range(4):
+                want = ref[k].step(acts[k], auto_reset=True, max_episode_steps=5)
+                torch.cuda.synchronize()
+                for x, y in zip(outs[k], want):
+                    assert torch.equal(x, y), "round %d handle %d" % (rnd, k)
+        assert sum(x.concurrent_launch_count() for x in hs) - c0 == 8 * 3          # items 2..4 of every call
+        for a, b in zip(hs, ref):
+            assert torch.equal(a.map, b.map) and torch.equal(a.inventory, b.inventory) and torch.equal(a.pose, b.pose)
+            assert torch.equal(a.episode, b.episode)
+        c0 = sum(x.concurrent_launch_count() for x in hs)
+        a0 = torch.zeros(n, dtype=torch.int32, device='cuda')
+        step_many([hs[0], hs[0], hs[1]], [a0, a0, a0])                                # same handle twice: item 2 waits
+        assert sum(x.concurrent_launch_count() for x in hs) - c0 == 1
+
+
 def _c4_descs():
     return [dict(C2_DESC, chain=[['limit', scenarios.C2_SET + ex], ['lidar', 8], nov]) for ex, nov in (
         (['Chop'], ['novelty', 'addchop', 'hard', '', '']), (['Jump'], ['novelty', 'addjump', 'hard', '', '']),

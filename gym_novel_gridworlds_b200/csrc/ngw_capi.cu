@@ -11,6 +11,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "ngw_host.h"
 #include "ngw_reset.cuh"
 
 
@@ -18,51 +19,14 @@
 using namespace ngw;
 
 static thread_local std::string g_err;
-static int fail(const std::string& m) { g_err = m; return 1; }
+int fail(const std::string& m) { g_err = m; return 1; }
 #define CK(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t _e = (call);                                                                         \
         if (_e != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(_e));          \
     } while (0)
 
-struct ngw_handle {
-    int device = 0;
-    long long n = 0, np = 0, first_gid = 0;
-    unsigned long long seed = 0;
-    int ms = 0, cells = 0, inv_stride = 0, obs_dim = 0, n_cfgs = 0;
-    int map_bytes = 0, inv_bytes = 0, obs_bytes = 0, warps = 2, tiles_per_cta = 0, lidar_mode = 0;
-    int obs_u8 = 0, obs_row_bytes = 0;             // observation row layout (ngw_set_obs_format)
-    int cache_hints = 3, dbg_skip = 0;
-    uint32_t key_mask = 0xFFFFFFFFu;
-    bool use_tma = true, collect_stats = true, force_global_cfg = false, plain_store = false, use_pdl = true;
-    bool pdl_in_graph = true, early_state = true, pdl_early = true;
-    bool lidar_uniform = false;
-    int wshape = 1;                                // 1: launches take the warp-per-tile kernel when it supports them, 0: never
-    bool concurrent = true;                        // independent consecutive launches may overlap (NGW_NO_CONCURRENT)
-    bool concurrent_waves = true;                  // ... also launches of several waves (NGW_NO_CONCURRENT_WAVES)
-    bool rollout2 = true;                          // lane-pair rollout kernel (NGW_NO_ROLLOUT2)
-    bool alias = true;                             // tile-group kernel, one tile per CTA: observation tile aliases the rows (NGW_NO_ALIAS)
-    DevConfig* d_cfgs = nullptr;
-    std::vector<int16_t*> d_luts;
-    std::vector<DevConfig> h_cfgs;
-    int8_t* map = nullptr; uchar4* pose = nullptr; int32_t* inv = nullptr; uint8_t* cfg_id = nullptr;
-    uint32_t* episode = nullptr; int32_t* ep_len = nullptr; uint32_t* err = nullptr; double* stats = nullptr;
-    uint8_t* zero_byte = nullptr;
-    uint16_t* msg = nullptr;                       // caller-owned message-code buffer (ngw_set_message_buffer)
-    int32_t* reset_list = nullptr; int32_t* reset_ctl = nullptr;   // auto-reset queue; ctl[0] = count, ctl[1] = finished CTAs
-    int sm_count = 148;
-    long long launches = 0, concurrent_launches = 0;
-    int reset_grid = 1;                            // CTAs per SM of the queued-reset kernel when it overlaps the next step (NGW_RESET_GRID)
-    bool last_step_concurrent = false;             // the latest one-step launch overlapped its predecessor
-    // host-buffer path: its own stream, ordered against the caller's streams with events
-    cudaStream_t hs = nullptr;
-    cudaEvent_t ev_dev = nullptr;                  // recorded on the caller's stream when the host path has to wait for it
-    cudaStream_t last_dev_stream = nullptr;        // stream of the latest device-path call ...
-    bool dev_dirty = false;                        // ... whose work the host stream has not been ordered after yet
-    bool host_dirty = false;                       // host-path work enqueued and not yet waited for
-    int32_t* h_actions = nullptr; unsigned char* h_obs = nullptr; size_t h_obs_bytes = 0; float* h_reward = nullptr;
-    uint8_t* h_done = nullptr; float* h_cost = nullptr; uint8_t* h_result = nullptr;
-};
+
 
 // Device-path entry points run on the caller's stream, the host-buffer path on the handle's own non-blocking stream.
 // These two keep them ordered: a device-path call first waits for unfinished host-path work, and the host path waits
@@ -74,16 +38,6 @@ struct ngw_handle {
 // before that writer had completed.  Launches the library cannot see (the caller's own kernels, copies) only add
 // distance.  The first launch of a stream capture is always conservative: a graph can be replayed after anything.
 static std::mutex g_order_mu;
-struct MemRange { uintptr_t lo, hi; };
-struct StreamTail {                       // the latest library launch on a stream
-    ngw_handle* h = nullptr;
-    unsigned long long cap_id = 0;        // stream capture it was recorded in, 0 = eager
-    cudaGraphNode_t node = nullptr;       // its graph node (captures only)
-    bool pure_step = false;               // 'gated': a one-step launch or the queued-reset kernel behind one — kernels that let
-                                          // their dependents start only after everything before THEM has completed
-    MemRange rd[2], wr[6];                // caller buffers it reads (actions) / writes (obs, reward, done, cost, result, msg)
-    int n_rd = 0, n_wr = 0;
-};
 static std::unordered_map<cudaStream_t, StreamTail> g_last_writer;
 static thread_local bool g_adjacent_hint = false;   // ngw_step_many: this launch directly follows the library's previous launch on the stream
 
@@ -99,7 +53,7 @@ static bool overlaps(const MemRange* a, int na, const MemRange* b, int nb) {
 // capture the stream's dependency set must be exactly the graph node of the previous launch; that launch must be a plain
 // one-step launch of ANOTHER handle, and the caller buffers of the two launches must not overlap.  Then everything this
 // launch reads besides its own state (the actions) was complete before the predecessor was let go by ITS gate.
-static int claim_stream(ngw_handle* h, cudaStream_t s, bool want_early, const StreamTail* mine = nullptr) {
+int claim_stream(ngw_handle* h, cudaStream_t s, bool want_early, const StreamTail* mine) {
     unsigned long long cap_id = 0;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     const cudaGraphNode_t* deps = nullptr;
@@ -422,9 +376,7 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     NGW_SMEM_ATTR((step1_kernel<true, 4, true, true>)); NGW_SMEM_ATTR((step1_kernel<true, 16, true, true>));
     NGW_SMEM_ATTR((step1w_kernel<0, 8>)); NGW_SMEM_ATTR((step1w_kernel<1, 8>)); NGW_SMEM_ATTR((step1w_kernel<4, 8>)); NGW_SMEM_ATTR((step1w_kernel<16, 8>));
     NGW_SMEM_ATTR((step1w_kernel<0, 16>)); NGW_SMEM_ATTR((step1w_kernel<1, 16>)); NGW_SMEM_ATTR((step1w_kernel<4, 16>)); NGW_SMEM_ATTR((step1w_kernel<16, 16>));
-    NGW_SMEM_ATTR((rollout_kernel<true, 0>)); NGW_SMEM_ATTR((rollout_kernel<true, 1>)); NGW_SMEM_ATTR((rollout_kernel<true, 4>));
-    NGW_SMEM_ATTR((rollout_kernel<true, 16>)); NGW_SMEM_ATTR((rollout_kernel<false, 0>)); NGW_SMEM_ATTR((rollout_kernel<false, 1>));
-    NGW_SMEM_ATTR((rollout_kernel<false, 4>)); NGW_SMEM_ATTR((rollout_kernel<false, 16>));
+    if (ngw_rollout_init()) return 1;
 #undef NGW_SMEM_ATTR
     return 0;
 }
@@ -567,7 +519,7 @@ static bool is_multi(const StepParams& p) {
     return p.n_steps > 1 || p.random_policy || p.done_count != nullptr || p.actions_out != nullptr || p.policy_w != nullptr;
 }
 
-static void pdl_attr(ngw_handle* h, cudaStream_t s, cudaLaunchConfig_t& lc, cudaLaunchAttribute* attr) {
+void pdl_attr(ngw_handle* h, cudaStream_t s, cudaLaunchConfig_t& lc, cudaLaunchAttribute* attr) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     // PDL (trigger once a CTA's stores are issued, see the kernels): the next launch's prologue overlaps this launch's
@@ -579,36 +531,6 @@ static void pdl_attr(ngw_handle* h, cudaStream_t s, cudaLaunchConfig_t& lc, cuda
         pdl = cap == cudaStreamCaptureStatusNone;
     }
     lc.attrs = attr; lc.numAttrs = pdl ? 1 : 0;
-}
-
-// K-step rollout launches (ngw_rollout / ngw_rollout_policy): one tile per CTA, tile resident across the steps
-template <int NC>
-static cudaError_t launch_rollout_nc(ngw_handle* h, StepParams p, cudaStream_t s) {
-    static thread_local StepArgs<NC> args;          // host staging of the argument block (copied by the launch); per thread,
-                                                    // so distinct handles stay independent across host threads
-    // ---- shared-memory plan: header | lidar tables | reset scratch | grid + inventory tile | observation tile
-    const int in_bytes = p.map_bytes + p.inv_bytes;
-    const int luts = (NGW_MAX_MAP_SIZE + NGW_MAX_ITEMS * (NC > 0 ? NC : 0) + 127) & ~127;
-    p.off_luts = NGW_SMEM_HDR;
-    p.off_scratch = p.off_luts + luts;
-    p.off_policy = p.off_scratch + ((NGW_RESET_SCRATCH_WORDS * 4 + 127) & ~127);
-    p.off_in = p.off_policy + (p.policy_w ? ((16 + p.obs_dim * p.policy_actions) * 4 + 127) & ~127 : 0);
-    const long long tiles = (p.env_end - p.env_begin + 31) / 32;
-    p.off_obs = p.off_in + in_bytes;
-    const size_t smem = (size_t)p.off_obs + p.obs_bytes;
-    // the K-step rollout is all step logic (one lidar pass at the end): one warp per tile keeps more tiles resident
-    const int warps = (smem * 12 <= 227 * 1024) ? 1 : h->warps;
-    claim_stream(h, s, false);
-    args.p = p;
-    for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
-    cudaLaunchConfig_t lc;
-    memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3((unsigned)tiles); lc.blockDim = dim3(32 * warps); lc.dynamicSmemBytes = smem;
-    lc.stream = s;
-    cudaLaunchAttribute attr[1];
-    pdl_attr(h, s, lc, attr);
-    if (h->use_tma) return cudaLaunchKernelEx(&lc, rollout_kernel<true, NC>, args);
-    return cudaLaunchKernelEx(&lc, rollout_kernel<false, NC>, args);
 }
 
 // caller buffers of a one-step launch (for the independence proof of this launch and of the next one)
@@ -773,61 +695,12 @@ static cudaError_t launch_step1w_nc(ngw_handle* h, StepParams p, cudaStream_t s)
     return e;
 }
 
-// K-step rollout launches in the lane-pair shape (rollout2_kernel); cudaErrorNotSupported -> rollout_kernel
-template <int NC, int A4>
-static cudaError_t launch_rollout2_na(ngw_handle* h, StepParams p, cudaStream_t s) {
-    static thread_local StepArgs<NC> args;
-    const int in_bytes = p.map_bytes + p.inv_bytes;
-    const int luts = (NGW_MAX_MAP_SIZE + NGW_MAX_ITEMS * (NC > 0 ? NC : 0) + 127) & ~127;
-    p.off_luts = NGW_R2_HDR;
-    p.off_scratch = p.off_luts + luts;
-    p.off_policy = p.off_scratch + (p.auto_reset ? ((2 * NGW_RESET_SCRATCH_WORDS * 4 + 127) & ~127) : 0);
-    p.off_in = p.off_policy + (A4 > 0 ? ((16 + p.obs_dim * 4 * A4) * 4 + 127) & ~127 : 0);
-    const int obs_tile = p.obs ? p.obs_bytes : 0;
-    const size_t smem = (size_t)p.off_in + (in_bytes > obs_tile ? in_bytes : obs_tile);
-    if (smem > 200 * 1024) return cudaErrorNotSupported;
-    const long long tiles = (p.env_end - p.env_begin + 31) / 32;
-    claim_stream(h, s, false);
-    args.p = p;
-    for (int i = 0; i < NC && i < h->n_cfgs; i++) args.cfg[i] = h->h_cfgs[i];
-    cudaLaunchConfig_t lc;
-    memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3((unsigned)tiles); lc.blockDim = dim3(64); lc.dynamicSmemBytes = smem;
-    lc.stream = s;
-    cudaLaunchAttribute attr[1];
-    pdl_attr(h, s, lc, attr);
-    static bool attr_set = false;       // per instantiation
-    if (!attr_set) { cudaFuncSetAttribute(rollout2_kernel<NC, A4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
-    return cudaLaunchKernelEx(&lc, rollout2_kernel<NC, A4>, args);
-}
-
-template <int NC>
-static cudaError_t launch_rollout2_nc(ngw_handle* h, const StepParams& p, cudaStream_t s) {
-    if (h->wshape == 0 || !h->use_tma || h->ms > 32 || !h->rollout2) return cudaErrorNotSupported;
-    if (h->obs_dim > 0 && h->lidar_mode != 1) return cudaErrorNotSupported;
-    if (h->obs_u8 && p.obs && p.obs_row_bytes % 16 != 0 && false) return cudaErrorNotSupported;
-    for (const DevConfig& dc : h->h_cfgs)
-        if (dc.c.n_inv_obs > NGW_REGSINK_TAIL) return cudaErrorNotSupported;
-    if (p.policy_w == nullptr) return launch_rollout2_na<NC, 0>(h, p, s);
-    switch ((p.policy_actions + 3) / 4) {
-        case 1: return launch_rollout2_na<NC, 1>(h, p, s);
-        case 2: return launch_rollout2_na<NC, 2>(h, p, s);
-        case 3: return launch_rollout2_na<NC, 3>(h, p, s);
-        default: return launch_rollout2_na<NC, 4>(h, p, s);
-    }
-}
-
 static int launch_step(ngw_handle* h, const StepParams& p, cudaStream_t s) {
     if (p.env_end <= p.env_begin) return 0;
     int nc = h->force_global_cfg ? 0 : h->n_cfgs;
     cudaError_t e;
     if (is_multi(p)) {
-        e = nc == 1 ? launch_rollout2_nc<1>(h, p, s) : launch_rollout2_nc<0>(h, p, s);
-        if (e != cudaErrorNotSupported) { /* taken */ }
-        else if (nc == 0 || nc > 16) e = launch_rollout_nc<0>(h, p, s);
-        else if (nc == 1) e = launch_rollout_nc<1>(h, p, s);
-        else if (nc <= 4) e = launch_rollout_nc<4>(h, p, s);
-        else e = launch_rollout_nc<16>(h, p, s);
+        e = ngw_launch_rollout(h, p, s);                  // ngw_rollout.cu
     } else {
         if (nc == 0 || nc > 16) e = launch_step1w_nc<0>(h, p, s);
         else if (nc == 1) e = launch_step1w_nc<1>(h, p, s);

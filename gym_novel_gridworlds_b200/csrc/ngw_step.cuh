@@ -155,7 +155,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // Cold: fused auto-reset.  Called by the whole step warp; every lane that finished an episode is regenerated in turn by
 // all 32 lanes (reset_env_warp), then its grid row goes back to HBM with coalesced stores.
-__device__ __noinline__ void auto_reset_warp(const StepParams& p, const DevConfig* dcfgs, int cfg_i, bool need,
+static __device__ __noinline__ void auto_reset_warp(const StepParams& p, const DevConfig* dcfgs, int cfg_i, bool need,
                                              int8_t* smap, int32_t* sinv, uint32_t* hist, long long e0, uchar4& ps) {
     const int lane = threadIdx.x & 31;
     __syncwarp();                                                    // every lane's step writes to the tile are visible

@@ -39,6 +39,7 @@ int fail(const std::string& m) { g_err = m; return 1; }
 // distance.  The first launch of a stream capture is always conservative: a graph can be replayed after anything.
 static std::mutex g_order_mu;
 static std::unordered_map<cudaStream_t, StreamTail> g_last_writer;
+static thread_local bool g_capturing = false;        // capture state of the stream seen by the latest claim_stream of this thread
 static thread_local bool g_adjacent_hint = false;   // ngw_step_many: this launch directly follows the library's previous launch on the stream
 
 static bool overlaps(const MemRange* a, int na, const MemRange* b, int nb) {
@@ -62,6 +63,7 @@ int claim_stream(ngw_handle* h, cudaStream_t s, bool want_early, const StreamTai
         cudaGetLastError(); cap = cudaStreamCaptureStatusNone; n_deps = 0;
     }
     if (cap != cudaStreamCaptureStatusActive) { cap_id = 0; n_deps = 0; }
+    g_capturing = cap == cudaStreamCaptureStatusActive;
     std::lock_guard<std::mutex> lk(g_order_mu);
     auto it = g_last_writer.find(s);
     int mode = 0;
@@ -88,7 +90,8 @@ static void note_launched(cudaStream_t s, bool pure_step) {
     unsigned long long cap_id = 0;
     const cudaGraphNode_t* deps = nullptr;
     size_t n_deps = 0;
-    if (cudaStreamGetCaptureInfo(s, &cap, &cap_id, nullptr, &deps, &n_deps) != cudaSuccess) { cudaGetLastError(); return; }
+    // (eager launches have no graph node: the driver call is only made while the stream is being captured)
+    if (g_capturing && cudaStreamGetCaptureInfo(s, &cap, &cap_id, nullptr, &deps, &n_deps) != cudaSuccess) { cudaGetLastError(); return; }
     std::lock_guard<std::mutex> lk(g_order_mu);
     auto it = g_last_writer.find(s);
     if (it == g_last_writer.end()) return;

@@ -82,6 +82,9 @@ class BatchHandle(object):
             self.step_cost = torch.zeros(self.n, dtype=torch.float32, device=self.device)
             self.result = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
             self._stats = torch.zeros(8, dtype=torch.float64, device=self.device)
+        # the output tensors live as long as the handle: their pointers are converted once (step() is host-bound)
+        self._out_ptrs = (_ptr(self.obs) if self.obs_dim else None, _ptr(self.reward), _ptr(self.done),
+                          _ptr(self.step_cost), _ptr(self.result))
         self._host = None
         if cfg_id is not None:
             self.set_env_configs(cfg_id)
@@ -165,10 +168,9 @@ class BatchHandle(object):
         """Device path: `actions` is an int32 CUDA tensor [n]; outputs are the handle's reused tensors."""
         if actions.dtype != torch.int32 or not actions.is_cuda or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
-        capi.check(self.lib, self.lib.ngw_step(self._h, _ptr(actions), _ptr(self.obs) if self.obs_dim else None,
-                                               _ptr(self.reward), _ptr(self.done), _ptr(self.step_cost),
-                                               _ptr(self.result), int(bool(auto_reset)), int(max_episode_steps),
-                                               self._stream()))
+        o = self._out_ptrs
+        capi.check(self.lib, self.lib.ngw_step(self._h, actions.data_ptr(), o[0], o[1], o[2], o[3], o[4],
+                                               1 if auto_reset else 0, int(max_episode_steps), self._stream()))
         return self.obs, self.reward, self.done, self.step_cost, self.result
 
     def rollout(self, n_steps, actions=None, policy_seed=0, auto_reset=False, max_episode_steps=0,

@@ -350,7 +350,8 @@ int64_t ngw_launch_count(ngw_handle* h);
  * them, which it can inside a stream capture (the stream's dependency set is exactly the previous launch's graph node):
  * the tile warps of the second launch then do not wait for the first grid, while one gate warp per CTA does and only
  * then lets the third launch start — at most two launches are in flight, completion stays in stream order, results are
- * identical.  Eager launches always wait.  NGW_NO_CONCURRENT=1 (read by ngw_create) turns the overlap off. */
+ * identical.  Single eager ngw_step calls always wait (ngw_step_many carries the same proof without a capture).
+ * NGW_NO_CONCURRENT=1 (read by ngw_create) turns the overlap off. */
 int64_t ngw_concurrent_launch_count(ngw_handle* h);
 
 #ifdef __cplusplus

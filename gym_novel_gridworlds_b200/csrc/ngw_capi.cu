@@ -265,6 +265,7 @@ static int create_init(ngw_handle* h, const ngw_config* cfgs, int32_t n_cfgs, in
     h->concurrent_waves = getenv("NGW_NO_CONCURRENT_WAVES") == nullptr;
     h->rollout2 = getenv("NGW_NO_ROLLOUT2") == nullptr;
     h->alias = getenv("NGW_NO_ALIAS") == nullptr;
+    h->row_pad = getenv("NGW_NO_ROW_PAD") == nullptr;
     if (const char* rg = getenv("NGW_RESET_GRID")) { int v = atoi(rg); if (v >= 1 && v <= 4) h->reset_grid = v; }
     h->pdl_early = getenv("NGW_NO_PDL_EARLY") == nullptr;   // trigger right after the wait: C2 7.70 -> 7.60 us/step
     // streaming data (each tile is read once and its observations written once per step) should not linger in L2:
@@ -560,7 +561,7 @@ static cudaError_t launch_step1_nc(ngw_handle* h, StepParams p, cudaStream_t s) 
     p.off_luts = NGW_CTA_HDR;
     p.off_groups = p.off_luts + luts;
     // shared-memory row stride of the observation tile: rows of a multiple of 8 words get 16 bytes of padding
-    p.obs_srow = p.obs_row_bytes + (((p.obs_row_bytes >> 2) % 8 == 0 && p.obs_row_bytes > 0 && !getenv("NGW_NO_ROW_PAD")) ? 16 : 0);
+    p.obs_srow = p.obs_row_bytes + (((p.obs_row_bytes >> 2) % 8 == 0 && p.obs_row_bytes > 0 && h->row_pad) ? 16 : 0);
     p.group_bytes = (NGW_GROUP_HDR + p.map_bytes + p.inv_bytes + 32 * p.obs_srow + 127) & ~127;
     // alias plan (one tile per CTA, see step1_kernel<.., kAlias>): the observation tile shares the rows' shared memory
     bool alias = h->alias && h->use_tma && h->tiles_per_cta <= 1;
@@ -646,7 +647,7 @@ static cudaError_t launch_step1w_nc(ngw_handle* h, StepParams p, cudaStream_t s)
     const int luts = (NGW_MAX_MAP_SIZE + NGW_MAX_ITEMS * (NC > 0 ? NC : 0) + 127) & ~127;
     p.off_luts = NGW_WCTA_HDR;
     p.off_groups = p.off_luts + luts;
-    p.obs_srow = p.obs_row_bytes + (((p.obs_row_bytes >> 2) % 8 == 0 && p.obs_row_bytes > 0 && !getenv("NGW_NO_ROW_PAD")) ? 16 : 0);
+    p.obs_srow = p.obs_row_bytes + (((p.obs_row_bytes >> 2) % 8 == 0 && p.obs_row_bytes > 0 && h->row_pad) ? 16 : 0);
     const int in_bytes = p.map_bytes + p.inv_bytes, obs_tile = p.obs ? 32 * p.obs_srow : 0;
     p.group_bytes = (NGW_WTILE_HDR + (in_bytes > obs_tile ? in_bytes : obs_tile) + 127) & ~127;
     const long long tiles = (p.env_end - p.env_begin + 31) / 32;

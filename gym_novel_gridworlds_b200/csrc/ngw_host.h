@@ -29,6 +29,7 @@ struct ngw_handle {
     bool concurrent = true;                        // independent consecutive launches may overlap (NGW_NO_CONCURRENT)
     bool concurrent_waves = true;                  // ... also launches of several waves (NGW_NO_CONCURRENT_WAVES)
     bool rollout2 = true;                          // lane-pair rollout kernel (NGW_NO_ROLLOUT2)
+    bool row_pad = true;                           // shared-memory observation rows of 8k words get 16 bytes of padding (NGW_NO_ROW_PAD)
     bool alias = true;                             // tile-group kernel, one tile per CTA: observation tile aliases the rows (NGW_NO_ALIAS)
     DevConfig* d_cfgs = nullptr;
     std::vector<int16_t*> d_luts;

@@ -20,7 +20,12 @@ def measure(workload, knobs, obs_format='i32'):
         saved[k] = os.environ.get(k)
         os.environ[k] = v
     try:
+        size = None
+        if '@' in workload:                          # "C4@131072": the workload at another batch size (per-GPU share of a strong-scaled job)
+            workload, size = workload.split('@')[0], int(workload.split('@')[1])
         desc, compiled, envs, rule, kw = bench.build_workload(workload.replace('-noreset', ''))
+        if size:
+            envs = size
         if workload.endswith('-noreset'):
             kw = {}
         bytes_step = float(np.mean([bench.algorithmic_bytes_per_env_step(cc, obs_format) for cc in compiled])) + (1 if len(compiled) > 1 else 0)

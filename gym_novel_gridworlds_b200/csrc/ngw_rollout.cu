@@ -76,7 +76,6 @@ template <int NC>
 static cudaError_t launch_rollout2_nc(ngw_handle* h, const StepParams& p, cudaStream_t s) {
     if (h->wshape == 0 || !h->use_tma || h->ms > 32 || !h->rollout2) return cudaErrorNotSupported;
     if (h->obs_dim > 0 && h->lidar_mode != 1) return cudaErrorNotSupported;
-    if (h->obs_u8 && p.obs && p.obs_row_bytes % 16 != 0 && false) return cudaErrorNotSupported;
     for (const DevConfig& dc : h->h_cfgs)
         if (dc.c.n_inv_obs > NGW_REGSINK_TAIL) return cudaErrorNotSupported;
     if (p.policy_w == nullptr) return launch_rollout2_na<NC, 0>(h, p, s);

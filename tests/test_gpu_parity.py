@@ -750,7 +750,7 @@ def _c4_descs():
         ([], ['novelty', 'additem', 'medium', 'spring', '']), ([], ['novelty', 'remapaction', 'hard', '', '']))]
 
 
-@pytest.mark.parametrize('case', ['pogo_ms23', 'bow_ms13', 'c4_mixed', 'c3_layers', 'pogo_ms40', 'bow12_16beams'])
+@pytest.mark.parametrize('case', ['pogo_ms23', 'bow_ms13', 'c4_mixed', 'c3_layers', 'pogo_ms40', 'bow12_16beams', 'c2_u8', 'pogo_ms40_u8'])
 @pytest.mark.parametrize('mode', ['given', 'given+autoreset', 'policy', 'random'])
 def test_rollout_kernels_equal_repeated_steps_on_other_shapes(case, mode):
     """The K-step rollout kernels (lane-pair kernel on grids up to 32x32 incl. its generic-size lidar, mixed configs through
@@ -758,7 +758,14 @@ def test_rollout_kernels_equal_repeated_steps_on_other_shapes(case, mode):
     steps issued one launch at a time: states, sums, final observation, episode counters; closed loop: every action is the
     argmax of the integer policy on the twin's observation; auto-reset with truncation regenerates the same episodes."""
     cfg_id = None
-    if case == 'pogo_ms23':
+    fmt = 'u8' if case.endswith('_u8') else 'i32'
+    if fmt == 'u8' and mode == 'policy':
+        pytest.skip("the device policy reads int32 observation rows")
+    if case == 'c2_u8':
+        compiled, n = [_compiled(C2_DESC)], 32 * 20 + 11
+    elif case == 'pogo_ms40_u8':
+        compiled, n = [_compiled(golden_util.get('pogo_ms40_additem_hard')['meta'])], 32 * 2 + 9
+    elif case == 'pogo_ms23':
         compiled, n = [_compiled({'env': scenarios.POGO, 'map_size': 23, 'chain': [['limit', scenarios.C2_SET], ['lidar', 8]]})], 32 * 9 + 7
     elif case == 'bow_ms13':
         compiled, n = [_compiled(golden_util.get('bow_ms13_lidar')['meta'])], 32 * 11 + 1
@@ -773,8 +780,8 @@ def test_rollout_kernels_equal_repeated_steps_on_other_shapes(case, mode):
         compiled, n = [_compiled({'env': scenarios.BOW, 'map_size': 12, 'chain': [['lidar', 16]]})], 200
     T = 24
     kw = dict(auto_reset=True, max_episode_steps=7) if mode == 'given+autoreset' else {}
-    h1 = BatchHandle(compiled, n, seed=21, cfg_id=cfg_id)             # one launch per step
-    h2 = BatchHandle(compiled, n, seed=21, cfg_id=cfg_id)             # one launch for all T steps
+    h1 = BatchHandle(compiled, n, seed=21, cfg_id=cfg_id, obs_format=fmt)   # one launch per step
+    h2 = BatchHandle(compiled, n, seed=21, cfg_id=cfg_id, obs_format=fmt)   # one launch for all T steps
     h1.reset(); h2.reset()
     n_act = torch.tensor([cc.c.n_actions for cc in compiled], device='cuda')[h1.cfg_id.long()]
     A = int(n_act.max().item())

@@ -39,6 +39,7 @@ int fail(const std::string& m) { g_err = m; return 1; }
 // distance.  The first launch of a stream capture is always conservative: a graph can be replayed after anything.
 static std::mutex g_order_mu;
 static std::unordered_map<cudaStream_t, StreamTail> g_last_writer;
+static thread_local bool g_first_in_capture = false; // the latest claim_stream saw the first library launch of a stream capture
 static thread_local bool g_capturing = false;        // capture state of the stream seen by the latest claim_stream of this thread
 static thread_local bool g_adjacent_hint = false;   // ngw_step_many: this launch directly follows the library's previous launch on the stream
 
@@ -66,6 +67,7 @@ int claim_stream(ngw_handle* h, cudaStream_t s, bool want_early, const StreamTai
     g_capturing = cap == cudaStreamCaptureStatusActive;
     std::lock_guard<std::mutex> lk(g_order_mu);
     auto it = g_last_writer.find(s);
+    g_first_in_capture = cap_id != 0 && (it == g_last_writer.end() || it->second.cap_id != cap_id);
     int mode = 0;
     if (want_early && it != g_last_writer.end() && it->second.h != nullptr && it->second.h != h && it->second.cap_id == cap_id) {
         mode = 1;
@@ -670,7 +672,8 @@ static cudaError_t launch_step1w_nc(ngw_handle* h, StepParams p, cudaStream_t s)
         // 7-tile CTAs in.  Several waves: 8 (C3 19.5 / 20.3 / 20.4 us with 8 / 4 / 6, C4 98.6 / 99.9 / 99.7; odd counts
         // leave partial CTAs).
         if (!one_wave) C = h->wshape == 3 ? c_cap : 8;
-        else if (p.concurrent) C = (int)((tiles + 2 * h->sm_count - 1) / (2 * h->sm_count));
+        else if (p.concurrent || (g_first_in_capture && h->concurrent && h->use_pdl && p.actions != nullptr))
+            C = (int)((tiles + 2 * h->sm_count - 1) / (2 * h->sm_count));   // (a capture's first launch waits, but its successor overlaps it)
         else C = (int)((tiles + h->sm_count - 1) / h->sm_count);
         if (C < 1) C = 1;
     }

@@ -744,6 +744,45 @@ def test_step_many_overlaps_handles_in_eager_mode():
         assert sum(x.concurrent_launch_count() for x in hs) - c0 == 1
 
 
+def test_step_many_mixes_kernel_shapes():
+    """One ngw_step_many call over handles that take DIFFERENT kernels (warp-per-tile, tile groups with the alias plan,
+    tile groups with the generic lidar, mixed configs): launches of neighbouring items overlap across kernel shapes (gate
+    warp next to gate CTA); same results as stepping every handle alone."""
+    from gym_novel_gridworlds_b200.runtime import StepGroup
+    specs = [([_compiled(C2_DESC)], 32 * 70 + 3, None),
+             ([_compiled(golden_util.get('pogo_ms40_additem_hard')['meta'])], 32 * 6 + 1, None),
+             ([_compiled({'env': scenarios.BOW, 'map_size': 12, 'chain': [['lidar', 16]]})], 300, None),
+             ([_compiled(d) for d in _c4_descs()], 32 * 40 + 5, 4),
+             ([_compiled(golden_util.get('bow_C3_axe_medium_fence_hard')['meta'])], 32 * 148 * 14 + 9, None)]
+    hs, ref = [], []
+    for k, (compiled, n, ncfg) in enumerate(specs):
+        cfg_id = None if ncfg is None else (np.arange(n) % ncfg).astype(np.int32)
+        for group in (hs, ref):
+            h = BatchHandle(compiled, n, seed=300 + k, cfg_id=cfg_id)
+            h.reset()
+            group.append(h)
+    torch.cuda.synchronize()
+    group = StepGroup(hs)
+    rng = np.random.RandomState(9)
+    c0 = sum(x.concurrent_launch_count() for x in hs)
+    for rnd in range(10):
+        acts = []
+        for h in hs:
+            n_act = torch.tensor([cc.c.n_actions for cc in h.compiled], device='cuda')[h.cfg_id.long()]
+            acts.append((torch.from_numpy(rng.randint(0, 1 << 30, size=h.n)).cuda() % n_act).to(torch.int32))
+        outs = group.step(acts, auto_reset=True, max_episode_steps=4)
+        torch.cuda.synchronize()
+        for k, h in enumerate(ref):
+            want = h.step(acts[k], auto_reset=True, max_episode_steps=4)
+            torch.cuda.synchronize()
+            for x, y in zip(outs[k], want):
+                assert torch.equal(x, y), "round %d handle %d" % (rnd, k)
+    assert sum(x.concurrent_launch_count() for x in hs) - c0 == 10 * (len(hs) - 1)
+    for a, b in zip(hs, ref):
+        assert torch.equal(a.map, b.map) and torch.equal(a.inventory, b.inventory) and torch.equal(a.pose, b.pose)
+        assert torch.equal(a.episode, b.episode) and torch.equal(a.ep_len, b.ep_len)
+
+
 def _c4_descs():
     return [dict(C2_DESC, chain=[['limit', scenarios.C2_SET + ex], ['lidar', 8], nov]) for ex, nov in (
         (['Chop'], ['novelty', 'addchop', 'hard', '', '']), (['Jump'], ['novelty', 'addjump', 'hard', '', '']),

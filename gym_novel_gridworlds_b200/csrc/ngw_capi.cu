@@ -134,7 +134,7 @@ void ngw_destroy(ngw_handle* h) {
     for (auto p : h->d_luts) cudaFree(p);
     cudaFree(h->d_cfgs); cudaFree(h->map); cudaFree(h->pose); cudaFree(h->inv); cudaFree(h->cfg_id);
     cudaFree(h->episode); cudaFree(h->ep_len); cudaFree(h->err); cudaFree(h->stats); cudaFree(h->zero_byte); cudaFree(h->reset_list); cudaFree(h->reset_ctl);
-    cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward);   // h_cost / h_done / h_result live in h_reward's block
+    cudaFree(h->h_actions); cudaFree(h->h_obs);   // reward / step_cost / done / result staging lives in h_obs's block
     if (h->hs) cudaStreamDestroy(h->hs);
     if (h->ev_dev) cudaEventDestroy(h->ev_dev);
     delete h;
@@ -831,27 +831,29 @@ int ngw_observe(ngw_handle* h, void* obs, void* stream) {
                        (cudaStream_t)stream);
 }
 
+// Device staging of the host-buffer path: ONE block  observation rows [n] | pad to 16 | reward | step_cost | done | result
+// (n-element sections), so that a caller whose host buffers have the same layout gets a whole step with ONE device-to-host
+// copy (ngw_host_layout gives the offsets).
+static size_t host_small_offset(const ngw_handle* h) { return ((size_t)h->n * h->obs_row_bytes + 15) & ~(size_t)15; }
+
 static int ensure_host_path(ngw_handle* h) {
     if (!h->hs) {
         CK(cudaStreamCreateWithFlags(&h->hs, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&h->ev_dev, cudaEventDisableTiming));
         CK(cudaMalloc(&h->h_actions, (size_t)h->np * 4));
-        // reward | step_cost | done | result share one allocation, n-element sections, so that a caller whose host buffers
-        // have the same layout gets them with ONE device-to-host copy
-        unsigned char* small = nullptr;
-        CK(cudaMalloc(&small, (size_t)h->n * 10 + 64));
-        h->h_reward = reinterpret_cast<float*>(small);
-        h->h_cost = reinterpret_cast<float*>(small + (size_t)h->n * 4);
-        h->h_done = small + (size_t)h->n * 8;
-        h->h_result = small + (size_t)h->n * 9;
     }
-    const size_t need = (size_t)h->np * h->obs_row_bytes;
-    if (need > h->h_obs_bytes) {                                    // (re)sized for the current observation format
+    const size_t off = host_small_offset(h), need = off + (size_t)h->n * 10 + 64;
+    if (need != h->h_obs_bytes) {                                   // (re)built for the current observation format
         CK(cudaStreamSynchronize(h->hs));
         cudaFree(h->h_obs);
         h->h_obs = nullptr; h->h_obs_bytes = 0;
         CK(cudaMalloc(&h->h_obs, need));
         h->h_obs_bytes = need;
+        unsigned char* small = h->h_obs + off;
+        h->h_reward = reinterpret_cast<float*>(small);
+        h->h_cost = reinterpret_cast<float*>(small + (size_t)h->n * 4);
+        h->h_done = small + (size_t)h->n * 8;
+        h->h_result = small + (size_t)h->n * 9;
     }
     return 0;
 }
@@ -903,10 +905,17 @@ int ngw_step_host_begin(ngw_handle* h, const int32_t* actions, void* obs, float*
     if (launch_step(h, step_params(h, h->h_actions, h->h_obs, h->h_reward, h->h_done, h->h_cost, h->h_result,
                                    auto_reset, max_episode_steps, 0, n), s)) return 1;
     h->host_dirty = true;
+    const unsigned char* r8 = reinterpret_cast<const unsigned char*>(reward);
+    const bool small_packed = reinterpret_cast<const unsigned char*>(step_cost) == r8 + cnt * 4 && done == r8 + cnt * 8 &&
+                              result == r8 + cnt * 9;
+    if (h->obs_dim > 0 && obs && small_packed && r8 == static_cast<const unsigned char*>(obs) + host_small_offset(h)) {
+        // the caller's buffers mirror the staging block: the whole step leaves with one copy
+        CK(cudaMemcpyAsync(obs, h->h_obs, host_small_offset(h) + cnt * 10, cudaMemcpyDeviceToHost, s));
+        return 0;
+    }
     if (h->obs_dim > 0 && obs)
         CK(cudaMemcpyAsync(obs, h->h_obs, cnt * h->obs_row_bytes, cudaMemcpyDeviceToHost, s));
-    const unsigned char* r8 = reinterpret_cast<const unsigned char*>(reward);
-    if (reinterpret_cast<const unsigned char*>(step_cost) == r8 + cnt * 4 && done == r8 + cnt * 8 && result == r8 + cnt * 9) {
+    if (small_packed) {
         CK(cudaMemcpyAsync(reward, h->h_reward, cnt * 10, cudaMemcpyDeviceToHost, s));   // same layout: one copy
     } else {
         CK(cudaMemcpyAsync(reward, h->h_reward, cnt * 4, cudaMemcpyDeviceToHost, s));

@@ -254,13 +254,22 @@ class BatchHandle(object):
         if self._host is None:
             d = max(self.obs_dim, 1)
             n = self.n
-            small = torch.zeros(10 * n + 64, dtype=torch.uint8).pin_memory()   # reward | step_cost | done | result
-            if self.obs_format == 'u8':
-                host_obs = torch.zeros((n, max(self.obs_row_bytes, 4)), dtype=torch.uint8).pin_memory()
+            # ONE pinned block mirroring the library's device staging (observation rows | pad to 16 | reward | step_cost |
+            # done | result): ngw_step_host then brings a whole step back with a single device-to-host copy
+            row = max(self.obs_row_bytes, 4) if self.obs_format == 'u8' else 4 * d
+            obs_bytes = n * row if self.obs_dim else 0
+            off = (obs_bytes + 15) & ~15
+            block = torch.zeros(off + 10 * n + 64, dtype=torch.uint8).pin_memory()
+            small = block[off:off + 10 * n]
+            if self.obs_dim == 0:
+                host_obs = torch.zeros((n, 1), dtype=torch.int32)
+            elif self.obs_format == 'u8':
+                host_obs = block[:obs_bytes].view(n, row)
             else:
-                host_obs = torch.zeros((n, d), dtype=torch.int32).pin_memory()
+                host_obs = block[:obs_bytes].view(torch.int32).view(n, d)
             self._host = {
                 'actions': torch.zeros(n, dtype=torch.int32).pin_memory(),
+                'block': block,
                 'obs': host_obs,
                 'small': small,
                 'reward': small[:4 * n].view(torch.float32),

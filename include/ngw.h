@@ -300,7 +300,9 @@ int ngw_set_message_buffer(ngw_handle* h, uint16_t* msg_dev);
  * obs/reward/done/step_cost/result out (D2H) on the handle's own stream; returns after the outputs are valid
  * on the host.  The step is ordered after everything earlier calls on this handle enqueued on the caller's streams
  * (ngw_reset, ngw_load_state, ngw_step ...), and later device-path calls wait for it.  Pinned buffers make the copies true DMA; if step_cost == reward + n, done == step_cost + n and
- * result == done + n (bytes: reward | step_cost | done | result contiguous) the four small outputs travel in one copy. */
+ * result == done + n (bytes: reward | step_cost | done | result contiguous) the four small outputs travel in one copy;
+ * if moreover reward == (char*)obs + round_up(n_envs * obs_row_bytes, 16) — one block: observation rows | pad to 16 |
+ * reward | step_cost | done | result — the WHOLE step travels in one copy. */
 int ngw_step_host(ngw_handle* h, const int32_t* actions, void* obs, float* reward, uint8_t* done,
                   float* step_cost, uint8_t* result, int32_t auto_reset, int32_t max_episode_steps);
 
